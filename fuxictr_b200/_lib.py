@@ -1,0 +1,96 @@
+"""ctypes binding of libfuxictr_b200.so (the C-ABI declared in include/fuxictr_b200.h).
+
+This is the *only* place Python touches the native library.  Arguments are raw device
+pointers (``tensor.data_ptr()``), sizes and the caller's CUDA stream handle; no torch
+type crosses the boundary.  A missing library is a hard error: there is no CPU or eager
+fallback behind these calls.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfuxictr_b200.so")
+
+# dtype / mode codes (mirror include/fuxictr_b200.h)
+B2_F32, B2_BF16, B2_F64, B2_I64, B2_I32 = 0, 1, 2, 3, 4
+B2_POOL_NONE, B2_POOL_SUM, B2_POOL_MEAN = 0, 1, 2
+B2_ACT_NONE, B2_ACT_RELU, B2_ACT_SIGMOID = 0, 1, 2
+B2_MAX_FIELDS = 128
+FM_PRODUCT_SUM, FM_BI_INTERACTION, FM_INNER_PRODUCT = 0, 1, 2
+
+c_void_p, c_int, c_int32, c_int64, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32,
+                                              ctypes.c_int64, ctypes.c_float)
+
+
+class b2_field(ctypes.Structure):
+    """struct b2_field of include/fuxictr_b200.h (64 bytes)."""
+    _fields_ = [
+        ("table", c_void_p), ("idx", c_void_p), ("out", c_void_p),
+        ("vocab", c_int64), ("idx_stride", c_int64), ("out_stride", c_int64),
+        ("dim", c_int32), ("seq_len", c_int32), ("pool", c_int32), ("padding_idx", c_int32),
+    ]
+
+
+_FIELD_P = ctypes.POINTER(b2_field)
+
+# name -> (restype, argtypes); every symbol the header declares must appear here
+# (tests/test_abi.py cross-checks this table against the header text).
+SIGNATURES = {
+    "b2_version": (ctypes.c_char_p, []),
+    "b2_last_error": (ctypes.c_char_p, []),
+    "b2_device_cc": (c_int, [c_int]),
+    "b2_embed_gather_fwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2_embed_scatter_bwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "b2_lr_fwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2_lr_bwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2_fm_fwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b2_fm_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b2_crossnet_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2_crossnet_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2_gemm_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+                            c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "b2_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "b2_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "b2_logit_bce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "b2_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
+                             c_float, c_float, c_float, c_void_p, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class B2Error(RuntimeError):
+    """A C-ABI call returned a negative status (message from b2_last_error())."""
+
+
+def load():
+    """dlopen the in-tree library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "fuxictr_b200: %s is missing. Build it with `python -m fuxictr_b200.build` "
+            "(needs nvcc); there is no CPU fallback for the B200 hot path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise B2Error on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise B2Error("%s failed (%d): %s" % (name, rc, lib.b2_last_error().decode()))
+
+
+def version():
+    return load().b2_version().decode()

@@ -1,0 +1,120 @@
+"""Flat HBM arenas for parameters, gradients and Adam state + the fused dense optimizer.
+
+B200-first memory layout: every trainable tensor of a model is a 16-byte-aligned slice
+of ONE fp32 arena `P`; its gradient is the same slice of arena `G`; Adam's moments are
+the same slices of `M` and `V`.  The Parameter *objects* are kept (the reference builds
+its optimizer and state_dict around them, rank_model.py:92, 417-433) — only their
+`.data` is re-pointed.  Backward kernels write gradients straight into `G`
+(functional._grad_buffer), so `clip_grad_norm_ + Adam` (rank_model.py:321-322) becomes
+two streaming kernels over the arena instead of ~6 launches per parameter.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+class _Slot(object):
+    __slots__ = ("arena", "offset", "numel", "shape", "step_mark")
+
+    def __init__(self, arena, offset, numel, shape):
+        self.arena, self.offset, self.numel, self.shape = arena, offset, numel, shape
+        self.step_mark = -1
+
+
+class ParamArena(object):
+    """Re-homes the trainable fp32 CUDA parameters of `module` into one flat buffer."""
+
+    ALIGN = 4  # floats (16 bytes): every slice is float4-addressable
+
+    def __init__(self, module):
+        params = [p for p in module.parameters() if p.requires_grad]
+        seen, uniq = set(), []
+        for p in params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        if not uniq:
+            raise ValueError("module has no trainable parameters")
+        dev = uniq[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("ParamArena needs CUDA parameters (model_to_device() first)")
+        for p in uniq:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise RuntimeError("ParamArena supports float32 parameters on one device")
+        off = 0
+        slots = []
+        for p in uniq:
+            slots.append((p, off))
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.P = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.G = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.params = uniq
+        self.step_id = 0
+        self.grads_are_zero = True
+        with torch.no_grad():
+            for p, o in slots:
+                dst = self.P[o:o + p.numel()].view(p.shape)
+                dst.copy_(p.data)
+                p.data = dst
+                p._b2_slot = _Slot(self, o, p.numel(), tuple(p.shape))
+                p.grad = None
+
+    def grad_view(self, slot):
+        return self.G[slot.offset:slot.offset + slot.numel].view(slot.shape)
+
+    def begin_step(self, grads_zeroed):
+        """Call once per training step before backward. `grads_zeroed`: G is already all-zero
+        (e.g. the previous fused Adam step cleared it); otherwise sparse-written grads
+        (embedding tables) are zero-filled lazily by the kernels' wrappers."""
+        self.step_id += 1
+        self.grads_are_zero = bool(grads_zeroed)
+        for p in self.params:
+            p.grad = None
+
+    def zero_grads(self):
+        self.G.zero_()
+
+
+class FusedAdam(object):
+    """clip_grad_norm_(max_norm) + Adam over a ParamArena, two kernels per step.
+
+    Semantics: nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam with
+    its defaults (rank_model.py:321-322, torch_utils.py:58-79).  The step counter lives on
+    the device so the whole step can be captured in a CUDA graph.
+    """
+
+    def __init__(self, arena, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_norm=10.0,
+                 zero_grad_in_step=True):
+        self.arena = arena
+        self.lr, self.betas, self.eps, self.max_norm = float(lr), betas, float(eps), max_norm
+        dev = arena.P.device
+        self.M = torch.zeros_like(arena.P)
+        self.V = torch.zeros_like(arena.P)
+        self.step_dev = torch.zeros((), dtype=torch.int64, device=dev)
+        self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
+        self.zero_grad_in_step = zero_grad_in_step
+
+    def zero_grad(self, set_to_none=True):
+        self.arena.begin_step(grads_zeroed=self.zero_grad_in_step and self._stepped)
+
+    _stepped = False
+
+    def step(self):
+        a = self.arena
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.step_dev.add_(1)
+        sumsq_ptr = ctypes.c_void_p(0)
+        if self.max_norm is not None:
+            self.sumsq.zero_()
+            _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr()), a.numel,
+                      ctypes.c_void_p(self.sumsq.data_ptr()), st)
+            sumsq_ptr = ctypes.c_void_p(self.sumsq.data_ptr())
+        _lib.call("b2_adam_step", ctypes.c_void_p(a.P.data_ptr()), ctypes.c_void_p(a.G.data_ptr()),
+                  ctypes.c_void_p(self.M.data_ptr()), ctypes.c_void_p(self.V.data_ptr()), a.numel,
+                  sumsq_ptr, float(self.max_norm or 0.0), self.lr, self.betas[0], self.betas[1],
+                  self.eps, ctypes.c_void_p(self.step_dev.data_ptr()),
+                  1 if self.zero_grad_in_step else 0, st)
+        self._stepped = True

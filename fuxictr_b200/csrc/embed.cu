@@ -1,0 +1,588 @@
+// embed.cu — fused multi-field embedding gather / scatter-add and the D=1
+// LogisticRegression gather-reduce, sm_100a.
+//
+// Reference semantics (reczoo/FuxiCTR v2.3.10):
+//   FeatureEmbeddingDict.forward   fuxictr/pytorch/layers/embeddings/feature_embedding.py:261-297
+//   FeatureEmbeddingDict.dict2tensor                                  feature_embedding.py:230-259
+//   MaskedAveragePooling / MaskedSumPooling        fuxictr/pytorch/layers/pooling.py:33-49, 62-73
+//   LogisticRegression.forward      fuxictr/pytorch/layers/blocks/logistic_regression.py:46-59
+//
+// HBM-bound integer/byte work: no tensor cores.  A work item is one table row
+// (one (sample, field[, position]) triple); LPR = 2^k lanes own one row and move
+// it with 16-byte accesses, so a warp reads 32/LPR independent rows per
+// instruction and writes a contiguous span of the stacked/concatenated output.
+// Field descriptors travel as a __grid_constant__ launch parameter (no H2D
+// copy, CUDA-graph friendly) and are staged once per CTA in shared memory.
+#include "b2_common.cuh"
+
+struct B2FieldPack {
+  b2_field f[B2_MAX_FIELDS];
+  int32_t slot_start[B2_MAX_FIELDS + 1];  // prefix sum of slots per field
+  int32_t nfields;
+  int32_t nslots;
+  int32_t all_len1;  // every field has exactly one slot
+  int32_t pad_;
+};
+
+// Shared-memory image of the pack, trimmed to nfields.
+struct SmemFields {
+  b2_field* f;
+  int32_t* slot_start;
+};
+
+__device__ __forceinline__ SmemFields b2_stage_fields(const B2FieldPack& pack, unsigned char* smem) {
+  SmemFields s;
+  s.f = reinterpret_cast<b2_field*>(smem);
+  s.slot_start = reinterpret_cast<int32_t*>(smem + sizeof(b2_field) * pack.nfields);
+  const int nwords = (int) (sizeof(b2_field) / 4) * pack.nfields;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&pack.f[0]);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  for (int i = threadIdx.x; i <= pack.nfields; i += blockDim.x) s.slot_start[i] = pack.slot_start[i];
+  __syncthreads();
+  return s;
+}
+
+// slot -> field by binary search over the prefix sums (<= 7 steps).
+__device__ __forceinline__ int b2_slot_field(const int32_t* slot_start, int nfields, int slot) {
+  int lo = 0, hi = nfields;  // invariant: slot_start[lo] <= slot < slot_start[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (slot_start[mid] <= slot) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC>
+__device__ __forceinline__ typename VecT<VEC>::type b2_vzero();
+template <> __device__ __forceinline__ float4 b2_vzero<4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ float2 b2_vzero<2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float b2_vzero<1>() { return 0.f; }
+
+__device__ __forceinline__ void b2_vadd(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void b2_vadd(float2& a, const float2& b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void b2_vadd(float& a, const float& b) { a += b; }
+__device__ __forceinline__ float b2_vsum(const float4& a) { return (a.x + a.y) + (a.z + a.w); }
+__device__ __forceinline__ float b2_vsum(const float2& a) { return a.x + a.y; }
+__device__ __forceinline__ float b2_vsum(const float& a) { return a; }
+__device__ __forceinline__ float4 b2_vscale(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float2 b2_vscale(const float2& a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float b2_vscale(const float& a, float s) { return a * s; }
+__device__ __forceinline__ float4 b2_vdiv(const float4& a, float s) { return make_float4(a.x / s, a.y / s, a.z / s, a.w / s); }
+__device__ __forceinline__ float2 b2_vdiv(const float2& a, float s) { return make_float2(a.x / s, a.y / s); }
+__device__ __forceinline__ float b2_vdiv(const float& a, float s) { return a / s; }
+
+__device__ __forceinline__ void b2_vred(float* p, const float4& v) { b2_red_add_v4(p, v); }
+__device__ __forceinline__ void b2_vred(float* p, const float2& v) { b2_red_add_v2(p, v.x, v.y); }
+__device__ __forceinline__ void b2_vred(float* p, const float& v) { b2_red_add(p, v); }
+
+// ---------------------------------------------------------------------------------
+// Forward, fast path: no pooled field, every row fits one pass of its LPR lanes.
+// ---------------------------------------------------------------------------------
+template <typename IdxT, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256)
+gather_fast_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int lpr_log2,
+                   int32_t* __restrict__ status) {
+  using V = typename VecT<VEC>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SmemFields sf = b2_stage_fields(pack, smem_raw);
+  const int nslots = pack.nslots, nfields = pack.nfields;
+  const bool all_len1 = pack.all_len1 != 0;
+  const int sub = threadIdx.x & ((1 << lpr_log2) - 1);
+  const int e = sub * VEC;  // first element this lane moves
+  const int64_t nitems = batch * (int64_t) nslots;
+  const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> lpr_log2;
+  const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> lpr_log2;
+  const bool small = nitems < (int64_t) 0x7fffffff;
+
+  for (int64_t base = group; base < nitems; base += ngroups * UNROLL) {
+    const V* src[UNROLL];
+    V* dst[UNROLL];
+    bool live[UNROLL];
+    // Phase 1: all index loads in flight together.
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t item = base + (int64_t) u * ngroups;
+      live[u] = false;
+      src[u] = nullptr;
+      dst[u] = nullptr;
+      if (item < nitems) {
+        int64_t b;
+        int slot;
+        if (small) {
+          const uint32_t it = (uint32_t) item;
+          const uint32_t bq = it / (uint32_t) nslots;
+          b = bq;
+          slot = (int) (it - bq * (uint32_t) nslots);
+        } else {
+          b = item / nslots;
+          slot = (int) (item - b * nslots);
+        }
+        const int fi = all_len1 ? slot : b2_slot_field(sf.slot_start, nfields, slot);
+        const b2_field& fd = sf.f[fi];
+        const int l = slot - sf.slot_start[fi];
+        const int64_t row = b2_load_index<IdxT>(fd.idx, b * fd.idx_stride + l);
+        const bool lane_on = e < fd.dim;
+        if (lane_on) {
+          dst[u] = reinterpret_cast<V*>(reinterpret_cast<float*>(fd.out) + b * fd.out_stride +
+                                        (int64_t) l * fd.dim + e);
+          if (row >= 0 && row < fd.vocab) {
+            src[u] = reinterpret_cast<const V*>(reinterpret_cast<const float*>(fd.table) +
+                                                row * fd.dim + e);
+            live[u] = true;
+          } else if (status != nullptr && sub == 0) {
+            atomicMax(status, fi + 1);  // reference raises IndexError; we flag and zero-fill
+          }
+        }
+      }
+    }
+    // Phase 2: all row loads in flight together.
+    V val[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      val[u] = b2_vzero<VEC>();
+      if (live[u]) val[u] = __ldg(src[u]);
+    }
+    // Phase 3: coalesced stores of the stacked/concatenated tensor.
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (dst[u] != nullptr) *dst[u] = val[u];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Forward, general path: pooled sequence fields and rows longer than one pass.
+// One group of LPR lanes per (sample, slot); a pooled field is a single slot whose
+// group walks the L positions and reduces in registers (fp32, position order —
+// the same order torch.sum(dim=1) uses for a short inner loop).
+// ---------------------------------------------------------------------------------
+template <typename IdxT, int VEC>
+__global__ void __launch_bounds__(256)
+gather_general_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int lpr_log2,
+                      float* __restrict__ mean_count, int32_t* __restrict__ status) {
+  using V = typename VecT<VEC>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SmemFields sf = b2_stage_fields(pack, smem_raw);
+  const int nslots = pack.nslots, nfields = pack.nfields;
+  const int LPR = 1 << lpr_log2;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPR - 1);
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
+  const int64_t nitems = batch * (int64_t) nslots;
+  const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> lpr_log2;
+  const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> lpr_log2;
+
+  for (int64_t item = group; item < nitems; item += ngroups) {
+    const int64_t b = item / nslots;
+    const int slot = (int) (item - b * nslots);
+    const int fi = b2_slot_field(sf.slot_start, nfields, slot);
+    const b2_field fd = sf.f[fi];
+    const float* table = reinterpret_cast<const float*>(fd.table);
+    float* out = reinterpret_cast<float*>(fd.out) + b * fd.out_stride;
+    const bool pooled = (fd.seq_len > 1 && fd.pool != B2_POOL_NONE);
+    if (!pooled) {
+      const int l = slot - sf.slot_start[fi];
+      const int64_t row = b2_load_index<IdxT>(fd.idx, b * fd.idx_stride + l);
+      const bool ok = row >= 0 && row < fd.vocab;
+      if (!ok && status != nullptr && sub == 0) atomicMax(status, fi + 1);
+      for (int e = sub * VEC; e < fd.dim; e += LPR * VEC) {
+        V v = b2_vzero<VEC>();
+        if (ok) v = __ldg(reinterpret_cast<const V*>(table + row * fd.dim + e));
+        *reinterpret_cast<V*>(out + (int64_t) l * fd.dim + e) = v;
+      }
+    } else {
+      // MaskedSumPooling: sum over positions (pooling.py:73).
+      // MaskedAveragePooling: sum / (count(rows whose vector sum != 0) + 1e-12) (pooling.py:45-49).
+      float count = 0.f;
+      if (fd.pool == B2_POOL_MEAN) {
+        for (int l = 0; l < fd.seq_len; ++l) {
+          const int64_t row = b2_load_index<IdxT>(fd.idx, b * fd.idx_stride + l);
+          const bool ok = row >= 0 && row < fd.vocab;
+          float part = 0.f;
+          if (ok)
+            for (int e = sub * VEC; e < fd.dim; e += LPR * VEC)
+              part += b2_vsum(__ldg(reinterpret_cast<const V*>(table + row * fd.dim + e)));
+          for (int o = LPR >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o);
+          count += (part != 0.f) ? 1.f : 0.f;
+        }
+        if (mean_count != nullptr && sub == 0) mean_count[(int64_t) fi * batch + b] = count;
+      }
+      for (int e = sub * VEC; e < fd.dim; e += LPR * VEC) {
+        V acc = b2_vzero<VEC>();
+        for (int l = 0; l < fd.seq_len; ++l) {
+          const int64_t row = b2_load_index<IdxT>(fd.idx, b * fd.idx_stride + l);
+          const bool ok = row >= 0 && row < fd.vocab;
+          if (!ok && status != nullptr && sub == 0 && e == 0) atomicMax(status, fi + 1);
+          if (ok) b2_vadd(acc, __ldg(reinterpret_cast<const V*>(table + row * fd.dim + e)));
+        }
+        if (fd.pool == B2_POOL_MEAN) acc = b2_vdiv(acc, count + 1e-12f);
+        *reinterpret_cast<V*>(out + e) = acc;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Backward: dense-gradient scatter-add with warp-level aggregation.
+// Before issuing its vector `red`, each LPR-lane group looks (match.any on the
+// destination row address) for other groups of the same warp that target the
+// same row; the lowest such group sums the duplicates through shuffles and
+// issues ONE reduction.  Hot Zipf rows therefore cost one L2 atomic per warp
+// instead of one per occurrence.
+// ---------------------------------------------------------------------------------
+template <typename IdxT, int VEC>
+__global__ void __launch_bounds__(256)
+scatter_bwd_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int lpr_log2,
+                   const float* __restrict__ mean_count) {
+  using V = typename VecT<VEC>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SmemFields sf = b2_stage_fields(pack, smem_raw);
+  const int nfields = pack.nfields;
+  // In the backward every (field, position) is its own slot — pooled fields fan the
+  // same incoming gradient out to all L rows.  slot_start here counts seq_len per field.
+  const int nslots = pack.nslots;
+  const int LPR = 1 << lpr_log2;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPR - 1);
+  const int my_group = lane >> lpr_log2;
+  const int groups_per_warp = 32 >> lpr_log2;
+  const int64_t nitems = batch * (int64_t) nslots;
+  const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> lpr_log2;
+  const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> lpr_log2;
+  // Warp-uniform trip count so the shuffles below are executed by all 32 lanes.
+  const int64_t warp_first = group - my_group;
+
+  for (int64_t wbase = warp_first; wbase < nitems; wbase += ngroups) {
+    const int64_t item = wbase + my_group;
+    float* drow = nullptr;        // destination row (gradient table), null = nothing to add
+    const float* grow = nullptr;  // incoming gradient row
+    int dim = 0;
+    float scale = 1.f;
+    if (item < nitems) {
+      const int64_t b = item / nslots;
+      const int slot = (int) (item - b * nslots);
+      const int fi = pack.all_len1 ? slot : b2_slot_field(sf.slot_start, nfields, slot);
+      const b2_field& fd = sf.f[fi];
+      const int l = slot - sf.slot_start[fi];
+      const int64_t row = b2_load_index<IdxT>(fd.idx, b * fd.idx_stride + l);
+      if (row >= 0 && row < fd.vocab && row != (int64_t) fd.padding_idx) {
+        dim = fd.dim;
+        drow = reinterpret_cast<float*>(const_cast<void*>(fd.table)) + row * fd.dim;
+        const bool pooled = (fd.seq_len > 1 && fd.pool != B2_POOL_NONE);
+        grow = reinterpret_cast<const float*>(fd.out) + b * fd.out_stride +
+               (pooled ? 0 : (int64_t) l * fd.dim);
+        if (pooled && fd.pool == B2_POOL_MEAN)
+          scale = 1.f / (mean_count[(int64_t) fi * batch + b] + 1e-12f);
+      }
+    }
+    // Peers: lanes of the warp aiming at the same destination row.
+    const unsigned peers = __match_any_sync(0xffffffffu, (unsigned long long) drow);
+    // Bit g of gset = group g targets my row (take each group's sub-lane 0 bit).
+    unsigned gset = 0;
+    for (int g = 0; g < groups_per_warp; ++g) gset |= ((peers >> (g << lpr_log2)) & 1u) << g;
+    const bool leader = (drow != nullptr) && ((gset & ((1u << my_group) - 1u)) == 0u);
+    const bool has_dups = (drow != nullptr) && (gset != (1u << my_group));
+    const unsigned any_dups = __ballot_sync(0xffffffffu, has_dups);
+    const int max_dim = __reduce_max_sync(0xffffffffu, dim);
+
+    for (int e0 = 0; e0 < max_dim; e0 += LPR * VEC) {
+      const int e = e0 + sub * VEC;
+      V v = b2_vzero<VEC>();
+      if (grow != nullptr && e < dim) {
+        v = *reinterpret_cast<const V*>(grow + e);
+        if (scale != 1.f) v = b2_vscale(v, scale);
+      }
+      if (any_dups != 0u) {
+        // Sum duplicates into the leader: walk the groups, pull lane (g*LPR+sub)'s value.
+        V acc = v;
+        for (int g = 0; g < groups_per_warp; ++g) {
+          const int srcl = (g << lpr_log2) + sub;
+          V o;
+          if constexpr (VEC == 4) {
+            o.x = __shfl_sync(0xffffffffu, v.x, srcl);
+            o.y = __shfl_sync(0xffffffffu, v.y, srcl);
+            o.z = __shfl_sync(0xffffffffu, v.z, srcl);
+            o.w = __shfl_sync(0xffffffffu, v.w, srcl);
+          } else if constexpr (VEC == 2) {
+            o.x = __shfl_sync(0xffffffffu, v.x, srcl);
+            o.y = __shfl_sync(0xffffffffu, v.y, srcl);
+          } else {
+            o = __shfl_sync(0xffffffffu, v, srcl);
+          }
+          if (g != my_group && ((gset >> g) & 1u)) b2_vadd(acc, o);
+        }
+        v = acc;
+      }
+      if (leader && e < dim) b2_vred(drow + e, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// LogisticRegression: out[b] = sum_slots w_f[idx] (+ bias).  One warp per sample,
+// lanes stride over the (field, position) slots, shuffle-reduce.
+// ---------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+lr_fwd_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch,
+              const float* __restrict__ bias, float* __restrict__ out,
+              int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SmemFields sf = b2_stage_fields(pack, smem_raw);
+  const int nslots = pack.nslots, nfields = pack.nfields;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  const float bv = (bias != nullptr) ? __ldg(bias) : 0.f;
+  for (int64_t b = warp; b < batch; b += nwarps) {
+    float acc = 0.f;
+    for (int slot = lane; slot < nslots; slot += 32) {
+      const int fi = pack.all_len1 ? slot : b2_slot_field(sf.slot_start, nfields, slot);
+      const b2_field& fd = sf.f[fi];
+      const int l = slot - sf.slot_start[fi];
+      const int64_t row = b2_load_index<IdxT>(fd.idx, b * fd.idx_stride + l);
+      if (row >= 0 && row < fd.vocab) acc += __ldg(reinterpret_cast<const float*>(fd.table) + row);
+      else if (status != nullptr) atomicMax(status, fi + 1);
+    }
+    acc = b2_warp_sum(acc);
+    if (lane == 0) out[b] = acc + bv;
+  }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+lr_bwd_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch,
+              const float* __restrict__ gout, float* __restrict__ gbias) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SmemFields sf = b2_stage_fields(pack, smem_raw);
+  __shared__ float red[32];
+  const int nslots = pack.nslots, nfields = pack.nfields;
+  const int64_t nitems = batch * (int64_t) nslots;
+  const int64_t nthreads = (int64_t) gridDim.x * blockDim.x;
+  float gb = 0.f;
+  for (int64_t item = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; item < nitems;
+       item += nthreads) {
+    const int64_t b = item / nslots;
+    const int slot = (int) (item - b * nslots);
+    const int fi = pack.all_len1 ? slot : b2_slot_field(sf.slot_start, nfields, slot);
+    const b2_field& fd = sf.f[fi];
+    const int l = slot - sf.slot_start[fi];
+    const float g = __ldg(gout + b);
+    if (slot == 0) gb += g;
+    const int64_t row = b2_load_index<IdxT>(fd.idx, b * fd.idx_stride + l);
+    if (row >= 0 && row < fd.vocab && row != (int64_t) fd.padding_idx)
+      b2_red_add(reinterpret_cast<float*>(const_cast<void*>(fd.table)) + row, g);
+  }
+  if (gbias != nullptr) {
+    const float t = b2_block_sum(gb, red);
+    if (threadIdx.x == 0 && t != 0.f) b2_red_add(gbias, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------
+static int next_pow2_log2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// Builds the launch pack; `bwd_slots` = one slot per (field, position) even for pooled fields.
+static int build_pack(B2FieldPack& pack, const b2_field* fields, int nfields, bool bwd_slots,
+                      bool need_out, int* vec_out, int* max_dim_out, bool* any_pooled_out) {
+  B2_REQUIRE(fields != nullptr, "fields is NULL");
+  B2_REQUIRE(nfields >= 1 && nfields <= B2_MAX_FIELDS, "nfields=%d outside [1,%d]", nfields,
+             B2_MAX_FIELDS);
+  int vec = 4, max_dim = 1;
+  bool any_pooled = false;
+  int slots = 0;
+  for (int i = 0; i < nfields; ++i) {
+    const b2_field& f = fields[i];
+    B2_REQUIRE(f.table != nullptr && f.idx != nullptr, "field %d: NULL table or idx", i);
+    B2_REQUIRE(!need_out || f.out != nullptr, "field %d: NULL out", i);
+    B2_REQUIRE(f.dim >= 1 && f.seq_len >= 1 && f.vocab >= 1, "field %d: bad dim/seq_len/vocab", i);
+    B2_REQUIRE(f.pool >= B2_POOL_NONE && f.pool <= B2_POOL_MEAN, "field %d: bad pool mode", i);
+    const bool pooled = f.seq_len > 1 && f.pool != B2_POOL_NONE;
+    any_pooled |= pooled;
+    pack.f[i] = f;
+    pack.slot_start[i] = slots;
+    slots += (pooled && !bwd_slots) ? 1 : f.seq_len;
+    if (f.dim > max_dim) max_dim = f.dim;
+    if (need_out) {
+      // widest vector every row start of this field is aligned to
+      int v = 4;
+      while (v > 1 && ((f.dim % v) != 0 || (f.out_stride % v) != 0 ||
+                       ((uintptr_t) f.table % (v * 4)) != 0 || ((uintptr_t) f.out % (v * 4)) != 0))
+        v >>= 1;
+      if (v < vec) vec = v;
+    }
+  }
+  pack.slot_start[nfields] = slots;
+  pack.nfields = nfields;
+  pack.nslots = slots;
+  pack.all_len1 = (slots == nfields) ? 1 : 0;
+  pack.pad_ = 0;
+  if (vec_out) *vec_out = vec;
+  if (max_dim_out) *max_dim_out = max_dim;
+  if (any_pooled_out) *any_pooled_out = any_pooled;
+  return B2_OK;
+}
+
+static size_t pack_smem_bytes(int nfields) {
+  return sizeof(b2_field) * nfields + sizeof(int32_t) * (nfields + 1);
+}
+
+// Grid sized in whole waves of 148 SMs x 8 resident 256-thread CTAs, capped by the work.
+static int grid_for(int64_t nthreads_needed, int block) {
+  int64_t blocks = b2_ceil_div(nthreads_needed, block);
+  const int64_t wave = (int64_t) B2_NUM_SMS * 8;
+  if (blocks > wave) blocks = wave;
+  if (blocks < 1) blocks = 1;
+  return (int) blocks;
+}
+
+template <typename IdxT>
+static int launch_gather(const B2FieldPack& pack, int64_t batch, int vec, int max_dim,
+                         bool any_pooled, float* mean_count, int32_t* status, cudaStream_t st) {
+  const int block = 256;
+  const size_t smem = pack_smem_bytes(pack.nfields);
+  int lpr_log2 = next_pow2_log2((max_dim + vec - 1) / vec);
+  if (lpr_log2 > 5) lpr_log2 = 5;
+  const bool one_pass = ((1 << lpr_log2) * vec) >= max_dim;
+  const int64_t nitems = batch * (int64_t) pack.nslots;
+  if (!any_pooled && one_pass) {
+    constexpr int UNROLL = 4;
+    const int grid = grid_for(b2_ceil_div(nitems, UNROLL) << lpr_log2, block);
+    if (vec == 4) gather_fast_kernel<IdxT, 4, UNROLL><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status);
+    else if (vec == 2) gather_fast_kernel<IdxT, 2, UNROLL><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status);
+    else gather_fast_kernel<IdxT, 1, UNROLL><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status);
+  } else {
+    const int grid = grid_for(nitems << lpr_log2, block);
+    if (vec == 4) gather_general_kernel<IdxT, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, mean_count, status);
+    else if (vec == 2) gather_general_kernel<IdxT, 2><<<grid, block, smem, st>>>(pack, batch, lpr_log2, mean_count, status);
+    else gather_general_kernel<IdxT, 1><<<grid, block, smem, st>>>(pack, batch, lpr_log2, mean_count, status);
+  }
+  B2_CUDA_LAUNCH_CHECK("b2_embed_gather_fwd");
+  return B2_OK;
+}
+
+template <typename IdxT>
+static int launch_scatter(const B2FieldPack& pack, int64_t batch, int vec, int max_dim,
+                          const float* mean_count, cudaStream_t st) {
+  const int block = 256;
+  const size_t smem = pack_smem_bytes(pack.nfields);
+  int lpr_log2 = next_pow2_log2((max_dim + vec - 1) / vec);
+  if (lpr_log2 > 5) lpr_log2 = 5;
+  const int64_t nitems = batch * (int64_t) pack.nslots;
+  const int grid = grid_for(nitems << lpr_log2, block);
+  if (vec == 4) scatter_bwd_kernel<IdxT, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, mean_count);
+  else if (vec == 2) scatter_bwd_kernel<IdxT, 2><<<grid, block, smem, st>>>(pack, batch, lpr_log2, mean_count);
+  else scatter_bwd_kernel<IdxT, 1><<<grid, block, smem, st>>>(pack, batch, lpr_log2, mean_count);
+  B2_CUDA_LAUNCH_CHECK("b2_embed_scatter_bwd");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_embed_gather_fwd(const b2_field* fields, int nfields, int64_t batch,
+                                   int idx_dtype, int elem_dtype, float* mean_count,
+                                   int32_t* status, void* stream) {
+  B2_REQUIRE(elem_dtype == B2_F32, "elem_dtype %d unsupported (only B2_F32)", elem_dtype);
+  B2_REQUIRE(batch >= 0, "negative batch");
+  if (batch == 0) return B2_OK;
+  static thread_local B2FieldPack pack;
+  int vec, max_dim;
+  bool any_pooled;
+  int rc = build_pack(pack, fields, nfields, false, true, &vec, &max_dim, &any_pooled);
+  if (rc != B2_OK) return rc;
+  for (int i = 0; i < nfields; ++i)
+    if (fields[i].seq_len > 1 && fields[i].pool == B2_POOL_MEAN)
+      B2_REQUIRE(mean_count != nullptr, "field %d: POOL_MEAN needs mean_count", i);
+  cudaStream_t st = (cudaStream_t) stream;
+  switch (idx_dtype) {
+    case B2_F64: return launch_gather<double>(pack, batch, vec, max_dim, any_pooled, mean_count, status, st);
+    case B2_I64: return launch_gather<int64_t>(pack, batch, vec, max_dim, any_pooled, mean_count, status, st);
+    case B2_I32: return launch_gather<int32_t>(pack, batch, vec, max_dim, any_pooled, mean_count, status, st);
+    default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
+  }
+}
+
+extern "C" B2_API int b2_embed_scatter_bwd(const b2_field* fields, int nfields, int64_t batch,
+                                    int idx_dtype, int elem_dtype, const float* mean_count,
+                                    void* stream) {
+  B2_REQUIRE(elem_dtype == B2_F32, "elem_dtype %d unsupported (only B2_F32)", elem_dtype);
+  B2_REQUIRE(batch >= 0, "negative batch");
+  if (batch == 0) return B2_OK;
+  static thread_local B2FieldPack pack;
+  int vec, max_dim;
+  bool any_pooled;
+  int rc = build_pack(pack, fields, nfields, true, true, &vec, &max_dim, &any_pooled);
+  if (rc != B2_OK) return rc;
+  for (int i = 0; i < nfields; ++i)
+    if (fields[i].seq_len > 1 && fields[i].pool == B2_POOL_MEAN)
+      B2_REQUIRE(mean_count != nullptr, "field %d: POOL_MEAN needs mean_count", i);
+  cudaStream_t st = (cudaStream_t) stream;
+  switch (idx_dtype) {
+    case B2_F64: return launch_scatter<double>(pack, batch, vec, max_dim, mean_count, st);
+    case B2_I64: return launch_scatter<int64_t>(pack, batch, vec, max_dim, mean_count, st);
+    case B2_I32: return launch_scatter<int32_t>(pack, batch, vec, max_dim, mean_count, st);
+    default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
+  }
+}
+
+template <typename IdxT>
+static int launch_lr_fwd(const B2FieldPack& pack, int64_t batch, const float* bias, float* out,
+                         int32_t* status, cudaStream_t st) {
+  const int block = 256;
+  const int grid = grid_for(batch * 32, block);
+  lr_fwd_kernel<IdxT><<<grid, block, pack_smem_bytes(pack.nfields), st>>>(pack, batch, bias, out, status);
+  B2_CUDA_LAUNCH_CHECK("b2_lr_fwd");
+  return B2_OK;
+}
+template <typename IdxT>
+static int launch_lr_bwd(const B2FieldPack& pack, int64_t batch, const float* gout, float* gbias,
+                         cudaStream_t st) {
+  const int block = 256;
+  const int grid = grid_for(batch * (int64_t) pack.nslots, block);
+  lr_bwd_kernel<IdxT><<<grid, block, pack_smem_bytes(pack.nfields), st>>>(pack, batch, gout, gbias);
+  B2_CUDA_LAUNCH_CHECK("b2_lr_bwd");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_lr_fwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype,
+                         const float* bias, float* out, int32_t* status, void* stream) {
+  B2_REQUIRE(out != nullptr, "out is NULL");
+  B2_REQUIRE(batch >= 0, "negative batch");
+  if (batch == 0) return B2_OK;
+  static thread_local B2FieldPack pack;
+  int rc = build_pack(pack, fields, nfields, true, false, nullptr, nullptr, nullptr);
+  if (rc != B2_OK) return rc;
+  cudaStream_t st = (cudaStream_t) stream;
+  switch (idx_dtype) {
+    case B2_F64: return launch_lr_fwd<double>(pack, batch, bias, out, status, st);
+    case B2_I64: return launch_lr_fwd<int64_t>(pack, batch, bias, out, status, st);
+    case B2_I32: return launch_lr_fwd<int32_t>(pack, batch, bias, out, status, st);
+    default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
+  }
+}
+
+extern "C" B2_API int b2_lr_bwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype,
+                         const float* gout, float* gbias, void* stream) {
+  B2_REQUIRE(gout != nullptr, "gout is NULL");
+  B2_REQUIRE(batch >= 0, "negative batch");
+  if (batch == 0) return B2_OK;
+  static thread_local B2FieldPack pack;
+  int rc = build_pack(pack, fields, nfields, true, false, nullptr, nullptr, nullptr);
+  if (rc != B2_OK) return rc;
+  cudaStream_t st = (cudaStream_t) stream;
+  switch (idx_dtype) {
+    case B2_F64: return launch_lr_bwd<double>(pack, batch, gout, gbias, st);
+    case B2_I64: return launch_lr_bwd<int64_t>(pack, batch, gout, gbias, st);
+    case B2_I32: return launch_lr_bwd<int32_t>(pack, batch, gout, gbias, st);
+    default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
+  }
+}

@@ -1,0 +1,489 @@
+"""torch.autograd bindings of the C-ABI kernels (device pointers in, device pointers out).
+
+PyTorch is plumbing here: it owns device memory, the current stream and the autograd
+tape; all arithmetic happens in libfuxictr_b200.so.  Every function requires CUDA
+tensors and raises otherwise — there is no eager/CPU fallback on this path.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+from ._lib import (B2_F32, B2_F64, B2_I32, B2_I64, B2_POOL_NONE, B2_POOL_SUM, B2_POOL_MEAN,
+                   B2_ACT_NONE, B2_ACT_RELU, B2_ACT_SIGMOID, b2_field)
+
+_IDX_CODE = {torch.float64: B2_F64, torch.int64: B2_I64, torch.int32: B2_I32}
+ACT_CODE = {None: B2_ACT_NONE, "none": B2_ACT_NONE, "relu": B2_ACT_RELU, "sigmoid": B2_ACT_SIGMOID}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("fuxictr_b200 kernels need CUDA tensors (got device=%s); "
+                               "there is no CPU path" % t.device)
+
+
+def _f32c(t):
+    """Contiguous fp32 view/copy of an activation (no-op in the steady state)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# Gradient arena hook: a parameter whose gradient should be produced in place inside a
+# flat arena carries `_b2_grad_view` (set by fuxictr_b200.arena.ParamArena).  Backward
+# kernels write there (no extra copy, no per-tensor allocation) the first time the
+# parameter is hit in a step; a second hit falls back to a fresh tensor so autograd can
+# accumulate.
+# --------------------------------------------------------------------------------------
+def _grad_buffer(param, zero):
+    slot = getattr(param, "_b2_slot", None)
+    if slot is not None:
+        arena = slot.arena
+        if param.grad is None and slot.step_mark != arena.step_id:  # first hit this step
+            slot.step_mark = arena.step_id
+            view = arena.grad_view(slot)  # a fresh view object, so AccumulateGrad can steal it
+            if zero and not arena.grads_are_zero:
+                view.zero_()
+            return view
+    return torch.zeros_like(param) if zero else torch.empty_like(param)
+
+
+# --------------------------------------------------------------------------------------
+# Fused multi-field embedding gather
+# --------------------------------------------------------------------------------------
+class GatherField(object):
+    """Static description of one feature of a fused gather (see struct b2_field)."""
+    __slots__ = ("name", "table_slot", "dim", "seq_len", "pool", "padding_idx", "out_offset",
+                 "out_width")
+
+    def __init__(self, name, table_slot, dim, seq_len=1, pool=B2_POOL_NONE, padding_idx=-1,
+                 out_offset=0):
+        self.name = name
+        self.table_slot = table_slot  # index into the de-duplicated weight tuple
+        self.dim = dim
+        self.seq_len = seq_len
+        self.pool = pool
+        self.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        self.out_offset = out_offset  # element offset inside one sample's arena row
+        pooled = seq_len > 1 and pool != B2_POOL_NONE
+        self.out_width = dim if (seq_len == 1 or pooled) else seq_len * dim
+
+
+class GatherPlan(object):
+    """Layout of one fused launch: fields, arena width, persistent descriptor array."""
+
+    def __init__(self, fields):
+        self.fields = list(fields)
+        if not 1 <= len(self.fields) <= _lib.B2_MAX_FIELDS:
+            raise ValueError("a fused gather takes 1..%d fields, got %d"
+                             % (_lib.B2_MAX_FIELDS, len(self.fields)))
+        off = 0
+        for f in self.fields:
+            f.out_offset = off
+            off += f.out_width
+        self.width = off
+        self.needs_count = any(f.seq_len > 1 and f.pool == B2_POOL_MEAN for f in self.fields)
+        self.widths = [f.out_width for f in self.fields]
+        self._descs = (b2_field * len(self.fields))()
+        for d, f in zip(self._descs, self.fields):
+            d.dim, d.seq_len, d.pool, d.padding_idx = f.dim, f.seq_len, f.pool, f.padding_idx
+
+    def fill(self, tables, idx_list, arena, batch):
+        """Point the descriptors at this call's tables / index views / arena rows."""
+        esz = 4
+        base = arena.data_ptr()
+        for d, f, idx in zip(self._descs, self.fields, idx_list):
+            t = tables[f.table_slot]
+            d.table = t.data_ptr()
+            d.vocab = t.shape[0]
+            d.idx = idx.data_ptr()
+            d.idx_stride = idx.stride(0) if batch > 0 else 0
+            d.out = base + f.out_offset * esz
+            d.out_stride = self.width
+        return self._descs
+
+
+def _prep_indices(idx_list, fields):
+    """Validate/normalise the per-feature index views; returns (list, dtype code)."""
+    dtype = idx_list[0].dtype
+    if dtype not in _IDX_CODE or any(t.dtype != dtype for t in idx_list):
+        # mixed or exotic dtypes: fall back to the reference's own cast (.long())
+        idx_list = [t.long() for t in idx_list]
+        dtype = torch.int64
+    out = []
+    for t, f in zip(idx_list, fields):
+        if f.seq_len > 1:
+            if t.dim() != 2 or t.shape[1] != f.seq_len:
+                raise ValueError("feature %s: expected (B, %d) indices, got %s"
+                                 % (f.name, f.seq_len, tuple(t.shape)))
+            if t.stride(1) != 1:
+                t = t.contiguous()
+        else:
+            if t.dim() == 2 and t.shape[1] == 1:
+                t = t[:, 0]
+            if t.dim() != 1:
+                raise ValueError("feature %s: expected (B,) indices, got %s" % (f.name, tuple(t.shape)))
+        out.append(t)
+    return out, _IDX_CODE[dtype]
+
+
+class _EmbedGather(torch.autograd.Function):
+    """arena[b, off_f : off_f + w_f] = rows of table_f (one launch for all features).
+
+    Reference: FeatureEmbeddingDict.forward + dict2tensor
+    (fuxictr/pytorch/layers/embeddings/feature_embedding.py:261-297, 230-259).
+    """
+
+    @staticmethod
+    def forward(ctx, plan, idx_list, status, *tables):
+        batch = idx_list[0].shape[0]
+        dev = tables[0].device
+        arena = torch.empty((batch, plan.width), dtype=torch.float32, device=dev)
+        count = (torch.empty((len(plan.fields), max(batch, 1)), dtype=torch.float32, device=dev)
+                 if plan.needs_count else None)
+        descs = plan.fill(tables, idx_list, arena, batch)
+        _lib.call("b2_embed_gather_fwd", descs, len(plan.fields), batch, ctx_code(idx_list),
+                  B2_F32, _ptr(count), _ptr(status), _stream())
+        ctx.plan, ctx.idx_list, ctx.count, ctx.tables = plan, idx_list, count, tables
+        return arena
+
+    @staticmethod
+    def backward(ctx, garena):
+        plan, idx_list, tables = ctx.plan, ctx.idx_list, ctx.tables
+        batch = idx_list[0].shape[0]
+        garena = _f32c(garena)
+        grads = [None] * len(tables)
+        for slot, t in enumerate(tables):
+            if t.requires_grad:
+                grads[slot] = _grad_buffer(t, zero=True)
+        live = [(f, idx) for f, idx in zip(plan.fields, idx_list) if grads[f.table_slot] is not None]
+        if live and batch > 0:
+            descs = (b2_field * len(live))()
+            base = garena.data_ptr()
+            for d, (f, idx) in zip(descs, live):
+                g = grads[f.table_slot]
+                d.table, d.vocab = g.data_ptr(), g.shape[0]
+                d.idx, d.idx_stride = idx.data_ptr(), idx.stride(0)
+                d.out, d.out_stride = base + f.out_offset * 4, plan.width
+                d.dim, d.seq_len, d.pool, d.padding_idx = f.dim, f.seq_len, f.pool, f.padding_idx
+            count = ctx.count
+            if count is not None:
+                # mean_count is indexed by the position in the *backward* field list
+                rows = [plan.fields.index(f) for f, _ in live]
+                count = count[rows].contiguous()
+            _lib.call("b2_embed_scatter_bwd", descs, len(live), batch, ctx_code(idx_list), B2_F32,
+                      _ptr(count), _stream())
+        return (None, None, None) + tuple(grads)
+
+
+def ctx_code(idx_list):
+    return _IDX_CODE[idx_list[0].dtype]
+
+
+def embed_gather(plan, idx_list, tables, status=None):
+    """Run the fused gather; returns the (B, plan.width) arena (differentiable w.r.t. tables)."""
+    _require_cuda(*tables)
+    _require_cuda(*idx_list)
+    for t in tables:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("embedding tables must be contiguous float32")
+    idx_list, _ = _prep_indices(list(idx_list), plan.fields)
+    return _EmbedGather.apply(plan, idx_list, status, *tables)
+
+
+# --------------------------------------------------------------------------------------
+# LogisticRegression gather-reduce
+# --------------------------------------------------------------------------------------
+class _LRForward(torch.autograd.Function):
+    """out[b,0] = sum_f w_f[idx_f[b]] (+ bias).  logistic_regression.py:55-58."""
+
+    @staticmethod
+    def forward(ctx, plan, idx_list, status, bias, *tables):
+        batch = idx_list[0].shape[0]
+        out = torch.empty((batch, 1), dtype=torch.float32, device=tables[0].device)
+        descs = plan._descs
+        for d, f, idx in zip(descs, plan.fields, idx_list):
+            t = tables[f.table_slot]
+            d.table, d.vocab = t.data_ptr(), t.shape[0]
+            d.idx, d.idx_stride = idx.data_ptr(), (idx.stride(0) if batch > 0 else 0)
+            d.out, d.out_stride = 0, 0
+        _lib.call("b2_lr_fwd", descs, len(plan.fields), batch, ctx_code(idx_list), _ptr(bias),
+                  _ptr(out), _ptr(status), _stream())
+        ctx.plan, ctx.idx_list, ctx.tables, ctx.bias = plan, idx_list, tables, bias
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        plan, idx_list, tables, bias = ctx.plan, ctx.idx_list, ctx.tables, ctx.bias
+        batch = idx_list[0].shape[0]
+        gout = _f32c(gout).view(-1)
+        grads = [None] * len(tables)
+        for slot, t in enumerate(tables):
+            if t.requires_grad:
+                grads[slot] = _grad_buffer(t, zero=True)
+        gbias = None
+        if bias is not None and bias.requires_grad:
+            gbias = _grad_buffer(bias, zero=True)
+        live = [(f, idx) for f, idx in zip(plan.fields, idx_list) if grads[f.table_slot] is not None]
+        if batch > 0 and (live or gbias is not None):
+            if live:
+                descs = (b2_field * len(live))()
+                for d, (f, idx) in zip(descs, live):
+                    g = grads[f.table_slot]
+                    d.table, d.vocab = g.data_ptr(), g.shape[0]
+                    d.idx, d.idx_stride = idx.data_ptr(), idx.stride(0)
+                    d.dim, d.seq_len, d.pool, d.padding_idx = 1, f.seq_len, f.pool, f.padding_idx
+                _lib.call("b2_lr_bwd", descs, len(live), batch, ctx_code(idx_list), _ptr(gout),
+                          _ptr(gbias), _stream())
+            else:
+                gbias.copy_(gout.sum().view(1))
+        return (None, None, None, gbias) + tuple(grads)
+
+
+def lr_forward(plan, idx_list, tables, bias=None, status=None):
+    _require_cuda(*tables)
+    _require_cuda(*idx_list)
+    idx_list, _ = _prep_indices(list(idx_list), plan.fields)
+    return _LRForward.apply(plan, idx_list, status, bias, *tables)
+
+
+# --------------------------------------------------------------------------------------
+# InnerProductInteraction
+# --------------------------------------------------------------------------------------
+class _FMInteraction(torch.autograd.Function):
+    """inner_product.py:55-66 (product_sum / bi_interaction / inner_product)."""
+
+    @staticmethod
+    def forward(ctx, emb, mode):
+        emb = _f32c(emb)
+        B, F, D = emb.shape
+        if mode == _lib.FM_PRODUCT_SUM:
+            out = torch.empty((B, 1), dtype=torch.float32, device=emb.device)
+        elif mode == _lib.FM_BI_INTERACTION:
+            out = torch.empty((B, D), dtype=torch.float32, device=emb.device)
+        else:
+            out = torch.empty((B, F * (F - 1) // 2), dtype=torch.float32, device=emb.device)
+        _lib.call("b2_fm_fwd", _ptr(emb), B, F, D, mode, _ptr(out), _stream())
+        ctx.save_for_backward(emb)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (emb,) = ctx.saved_tensors
+        B, F, D = emb.shape
+        gout = _f32c(gout)
+        gemb = torch.empty_like(emb)
+        _lib.call("b2_fm_bwd", _ptr(emb), _ptr(gout), B, F, D, ctx.mode, _ptr(gemb), _stream())
+        return gemb, None
+
+
+def fm_interaction(emb, mode):
+    _require_cuda(emb)
+    if emb.dim() != 3:
+        raise ValueError("feature_emb must be (batch, num_fields, embedding_dim)")
+    return _FMInteraction.apply(emb, mode)
+
+
+# --------------------------------------------------------------------------------------
+# CrossNet (rank-1)
+# --------------------------------------------------------------------------------------
+class _CrossNet(torch.autograd.Function):
+    """cross_net.py:80-92 with all layers fused; w, b are (L, d)."""
+
+    @staticmethod
+    def forward(ctx, x0, w, b):
+        x0, w, b = _f32c(x0), _f32c(w), _f32c(b)
+        B, d = x0.shape
+        L = w.shape[0]
+        out = torch.empty_like(x0)
+        s = torch.empty((B, L), dtype=torch.float32, device=x0.device)
+        _lib.call("b2_crossnet_fwd", _ptr(x0), _ptr(w), _ptr(b), B, d, L, _ptr(out), _ptr(s), _stream())
+        ctx.save_for_backward(x0, w, b, s)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x0, w, b, s = ctx.saved_tensors
+        B, d = x0.shape
+        L = w.shape[0]
+        gout = _f32c(gout)
+        gx0 = torch.empty_like(x0)
+        gw = torch.zeros_like(w)
+        gb = torch.zeros_like(b)
+        if L > 0:
+            _lib.call("b2_crossnet_bwd", _ptr(x0), _ptr(w), _ptr(b), _ptr(s), _ptr(gout), B, d, L,
+                      _ptr(gx0), _ptr(gw), _ptr(gb), _stream())
+        else:
+            gx0.copy_(gout)
+        return gx0, gw, gb
+
+
+def crossnet(x0, w, b):
+    _require_cuda(x0, w, b)
+    return _CrossNet.apply(x0, w, b)
+
+
+# --------------------------------------------------------------------------------------
+# Dense layer (fp32 parity path)
+# --------------------------------------------------------------------------------------
+def gemm_f32(a, b, out, a_t=False, b_t=False, bias=None, act=B2_ACT_NONE, mul=None, add=None,
+             accumulate=False):
+    """out (M,N) = epi(op(a) @ op(b)); a is (M,K) [or (K,M) if a_t], b is (K,N) [or (N,K) if b_t]."""
+    if a_t:
+        K, M = a.shape
+        a_rs, a_cs = a.stride(1), a.stride(0)
+    else:
+        M, K = a.shape
+        a_rs, a_cs = a.stride(0), a.stride(1)
+    if b_t:
+        N, K2 = b.shape
+        b_rs, b_cs = b.stride(1), b.stride(0)
+    else:
+        K2, N = b.shape
+        b_rs, b_cs = b.stride(0), b.stride(1)
+    if K != K2 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
+        raise ValueError("gemm shape mismatch: a%s b%s out%s" % (tuple(a.shape), tuple(b.shape), tuple(out.shape)))
+    _lib.call("b2_gemm_f32", _ptr(a), a_rs, a_cs, _ptr(b), b_rs, b_cs, _ptr(out), out.stride(0), M, N, K,
+              _ptr(bias), act, _ptr(mul), _ptr(add), 1 if accumulate else 0, _stream())
+    return out
+
+
+class _LinearAct(torch.autograd.Function):
+    """y = act(x W^T + b): nn.Linear (+ReLU/Sigmoid) of MLP_Block (mlp_block.py:74-80)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        x = _f32c(x)
+        M, K = x.shape
+        N = weight.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        gemm_f32(x, weight, y, b_t=True, bias=bias, act=act)
+        ctx.act = act
+        ctx.save_for_backward(x, weight, y if act != B2_ACT_NONE else None)
+        ctx.has_bias = bias is not None
+        ctx.bias = bias
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        gy = _f32c(gy)
+        M, K = x.shape
+        N = weight.shape[0]
+        if ctx.act != B2_ACT_NONE:
+            gz = torch.empty_like(gy)
+            _lib.call("b2_act_bwd", _ptr(y), _ptr(gy), _ptr(gz), gy.numel(), ctx.act, _stream())
+        else:
+            gz = gy
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty((M, K), dtype=torch.float32, device=x.device)
+            gemm_f32(gz, weight, gx)                      # dX = dZ W        (M,N)x(N,K)
+        if ctx.needs_input_grad[1]:
+            gw = _grad_buffer(weight, zero=False)
+            gemm_f32(gz, x, gw, a_t=True)                 # dW = dZ^T X      (N,M)x(M,K)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = _grad_buffer(ctx.bias, zero=False)
+            _lib.call("b2_colsum", _ptr(gz), M, N, gz.stride(0), _ptr(gb), 0, _stream())
+        return gx, gw, gb, None
+
+
+def linear_act(x, weight, bias=None, act=B2_ACT_NONE):
+    _require_cuda(x, weight, bias)
+    if x.dim() != 2:
+        lead = x.shape[:-1]
+        return _LinearAct.apply(x.reshape(-1, x.shape[-1]), weight, bias, act).view(*lead, -1)
+    return _LinearAct.apply(x, weight, bias, act)
+
+
+# --------------------------------------------------------------------------------------
+# Fused logit + sigmoid + BCE(mean)
+# --------------------------------------------------------------------------------------
+class _LogitBCE(torch.autograd.Function):
+    """loss = BCE(sigmoid(sum(terms)), y).mean(); also returns y_pred (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, label, *terms):
+        ctx.shapes = [t.shape for t in terms]
+        terms = [_f32c(t).view(-1) for t in terms]
+        B = terms[0].numel()
+        dev = terms[0].device
+        label = _f32c(label).view(-1)
+        y_pred = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        glogit = torch.empty((B,), dtype=torch.float32, device=dev)
+        ptrs = [_ptr(t) for t in terms] + [ctypes.c_void_p(0)] * (4 - len(terms))
+        _lib.call("b2_logit_bce_fwd", ptrs[0], ptrs[1], ptrs[2], ptrs[3], _ptr(label), B,
+                  _ptr(y_pred), _ptr(loss), _ptr(glogit), _stream())
+        ctx.save_for_backward(glogit)
+        ctx.mark_non_differentiable(y_pred)
+        return loss, y_pred
+
+    @staticmethod
+    def backward(ctx, gloss, _gy):
+        (glogit,) = ctx.saved_tensors
+        g = glogit * gloss
+        return (None,) + tuple(g.view(shape) for shape in ctx.shapes)
+
+
+def logit_bce(label, *terms):
+    """terms: 1..4 tensors of (B,1)/(B,) logits that are summed. Returns (loss, y_pred)."""
+    if not 1 <= len(terms) <= 4:
+        raise ValueError("logit_bce takes 1..4 logit terms")
+    _require_cuda(label, *terms)
+    return _LogitBCE.apply(label, *terms)
+
+
+# --------------------------------------------------------------------------------------
+# Compositions whose dense contractions already run on the b2 GEMM; the remaining
+# elementwise/outer-product pieces are stock torch ops until their fused kernels land
+# (tracked in DESIGN.md "kernel status").
+# --------------------------------------------------------------------------------------
+def cin_forward(feature_emb, conv_layers, fc):
+    """CompressedInteractionNet.forward (compressed_interaction_net.py:64-76)."""
+    X0 = feature_emb
+    B, _, D = X0.shape
+    Xi = X0
+    pools = []
+    for conv in conv_layers:
+        had = torch.einsum("bhd,bmd->bhmd", X0, Xi).reshape(B, -1, D)          # (B, F*H, D)
+        w = conv.weight.view(conv.out_channels, -1)                              # 1x1 conv == GEMM
+        rows = had.transpose(1, 2).reshape(B * D, -1)                            # (B*D, F*H)
+        Xi = linear_act(rows, w, conv.bias, B2_ACT_NONE).view(B, D, -1).transpose(1, 2)
+        pools.append(Xi.sum(dim=-1))
+    return linear_act(torch.cat(pools, dim=-1), fc.weight, fc.bias, B2_ACT_NONE)
+
+
+def dice_forward(X, bn, alpha, training):
+    """Dice.forward (activations.py:49-50)."""
+    p = torch.sigmoid(bn(X))
+    return p * X + alpha * (1 - p) * X
+
+
+def din_attention(module, target_item, history_sequence, mask=None):
+    """DIN_Attention.forward (target_attention.py:79-92)."""
+    seq_len = history_sequence.size(1)
+    target_item = target_item.unsqueeze(1).expand(-1, seq_len, -1)
+    attention_input = torch.cat([target_item, history_sequence, target_item - history_sequence,
+                                 target_item * history_sequence], dim=-1)
+    attention_weight = module.attention_layer(attention_input.view(-1, 4 * module.embedding_dim))
+    attention_weight = attention_weight.view(-1, seq_len)
+    if mask is not None:
+        attention_weight = attention_weight * mask.float()
+    if module.use_softmax:
+        if mask is not None:
+            attention_weight = attention_weight + -1.e9 * (1 - mask.float())
+        attention_weight = attention_weight.softmax(dim=-1)
+    return (attention_weight.unsqueeze(-1) * history_sequence).sum(dim=1)

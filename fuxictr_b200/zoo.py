@@ -1,0 +1,407 @@
+"""Callers of the hot path: the five in-scope model forwards and one training step.
+
+These are NOT a model-zoo rewrite.  On a machine that has the reference installed the
+unmodified ``model_zoo`` classes call the patched layers (fuxictr_b200.patch.enable()).
+The GPU box has no reference checkout, so parity tests and bench.py need the same
+callers in-tree: each class below wires the layers exactly like the reference class of
+the same name (same attribute names => same state_dict keys, same construction order =>
+same RNG consumption) and nothing else.
+
+  DeepFM   model_zoo/DeepFM/DeepFM_torch/src/DeepFM.py:41-88
+  DCNv2    model_zoo/DCNv2/src/DCNv2.py:47-132
+  DLRM     model_zoo/DLRM/src/DLRM.py:43-123
+  DIN      model_zoo/DIN/src/DIN.py:50-149
+  xDeepFM  model_zoo/xDeepFM/src/xDeepFM.py:41-97
+  RankModel = the slice of BaseModel a training step touches,
+             fuxictr/pytorch/models/rank_model.py:84-189, 307-323, 435-448
+"""
+import torch
+from torch import nn
+
+from .layers import (FeatureEmbedding, FeatureEmbeddingDict, MLP_Block, FactorizationMachine,
+                     CrossNetV2, InnerProductInteraction, DIN_Attention, Dice,
+                     CompressedInteractionNet, LogisticRegression, not_in_whitelist)
+from .arena import ParamArena, FusedAdam
+from . import functional as F2
+
+
+def _flatten(items):
+    for x in items:
+        if isinstance(x, (list, tuple)):
+            for y in _flatten(x):
+                yield y
+        else:
+            yield x
+
+
+class RankModel(nn.Module):
+    """Device placement, input/label extraction, loss and one optimisation step."""
+
+    def __init__(self, feature_map, model_id="RankModel", task="binary_classification", gpu=-1,
+                 embedding_regularizer=None, net_regularizer=None, **kwargs):
+        super(RankModel, self).__init__()
+        self.device = torch.device("cuda:%d" % gpu) if gpu >= 0 and torch.cuda.is_available() \
+            else torch.device("cpu")
+        self.feature_map = feature_map
+        self.model_id = model_id
+        self._embedding_regularizer = embedding_regularizer
+        self._net_regularizer = net_regularizer
+        self._max_gradient_norm = 10.0
+        if task == "binary_classification":
+            self.output_activation = nn.Sigmoid()
+        elif task == "regression":
+            self.output_activation = nn.Identity()
+        else:
+            raise NotImplementedError("task={} is not supported.".format(task))
+        self._arena = None
+        self._fused_optimizer = None
+
+    # -- rank_model.py:84-93 ------------------------------------------------------------
+    def compile(self, optimizer="adam", loss="binary_crossentropy", lr=1e-3):
+        name = "Adam" if str(optimizer).lower() == "adam" else optimizer
+        self._lr = lr
+        self._optimizer_name = name
+        self.optimizer = getattr(torch.optim, name)(self.parameters(), lr=lr)
+        if loss not in ("bce", "binary_crossentropy", "binary_cross_entropy"):
+            raise NotImplementedError("loss={} is not supported on the B200 path.".format(loss))
+        self.loss_fn = torch.nn.functional.binary_cross_entropy
+
+    # -- rank_model.py:146-167 --------------------------------------------------------------
+    def reset_parameters(self):
+        def default_reset(m):
+            if type(m) in [nn.Linear, nn.Conv1d]:
+                nn.init.xavier_normal_(m.weight)
+                if m.bias is not None:
+                    m.bias.data.fill_(0)
+
+        def custom_reset(m):
+            if hasattr(m, "init_weights"):
+                m.init_weights()
+        self.apply(default_reset)
+        self.apply(custom_reset)
+
+    def model_to_device(self):
+        self.to(device=self.device)
+
+    # -- rank_model.py:169-203 --------------------------------------------------------------
+    def get_inputs(self, inputs, feature_source=None):
+        X = dict()
+        for feature in inputs.keys():
+            if feature in self.feature_map.labels:
+                continue
+            spec = self.feature_map.features[feature]
+            if spec["type"] == "meta":
+                continue
+            if feature_source and not_in_whitelist(spec["source"], feature_source):
+                continue
+            X[feature] = inputs[feature].to(self.device)
+        return X
+
+    def get_labels(self, inputs):
+        y = inputs[self.feature_map.labels[0]].to(self.device)
+        return y.float().view(-1, 1)
+
+    # -- rank_model.py:95-131 ---------------------------------------------------------------
+    def regularization_loss(self):
+        reg = 0
+        if not (self._embedding_regularizer or self._net_regularizer):
+            return reg
+        emb_reg = _parse_regularizer(self._embedding_regularizer)
+        net_reg = _parse_regularizer(self._net_regularizer)
+        emb_params = set()
+        for m_name, module in self.named_modules():
+            if type(module) == FeatureEmbeddingDict:
+                for p_name, param in module.named_parameters():
+                    if param.requires_grad:
+                        emb_params.add(".".join([m_name, p_name]))
+                        for p, lam in emb_reg:
+                            reg = reg + (lam / p) * torch.norm(param, p) ** p
+        for name, param in self.named_parameters():
+            if param.requires_grad and name not in emb_params:
+                for p, lam in net_reg:
+                    reg = reg + (lam / p) * torch.norm(param, p) ** p
+        return reg
+
+    def compute_loss(self, return_dict, y_true):
+        return self.loss_fn(return_dict["y_pred"], y_true, reduction="mean") + self.regularization_loss()
+
+    # -- rank_model.py:307-323 ---------------------------------------------------------------
+    def train_step(self, batch_data):
+        self.optimizer.zero_grad()
+        return_dict = self.forward(batch_data)
+        y_true = self.get_labels(batch_data)
+        loss = self.compute_loss(return_dict, y_true)
+        loss.backward()
+        nn.utils.clip_grad_norm_(self.parameters(), self._max_gradient_norm)
+        self.optimizer.step()
+        return loss
+
+    # -- B200 extension: flat arenas + 2-kernel clip/Adam -------------------------------------
+    def use_fused_optimizer(self):
+        """Re-home parameters into one HBM arena and replace clip_grad_norm_ + torch Adam by
+        the two-kernel FusedAdam (same arithmetic; see arena.py).  Call after model_to_device()."""
+        if self._optimizer_name != "Adam":
+            raise NotImplementedError("the fused optimizer implements Adam only")
+        self._arena = ParamArena(self)
+        self._fused_optimizer = FusedAdam(self._arena, lr=self._lr, max_norm=self._max_gradient_norm)
+        self.optimizer = None
+        return self._fused_optimizer
+
+    def fused_train_step(self, batch_data):
+        """train_step with the arena optimizer and the fused logit+BCE kernel when the model
+        exposes its pre-sigmoid logit terms (`forward_logits`)."""
+        opt = self._fused_optimizer
+        opt.zero_grad()
+        y_true = self.get_labels(batch_data)
+        if hasattr(self, "forward_logits") and not (self._embedding_regularizer or self._net_regularizer):
+            loss, _ = F2.logit_bce(y_true, *self.forward_logits(batch_data))
+        else:
+            loss = self.compute_loss(self.forward(batch_data), y_true)
+        loss.backward()
+        opt.step()
+        return loss
+
+
+def _parse_regularizer(reg):
+    """torch_utils.py:104-135: float => L2; 'l1(x)', 'l2(x)', 'l1_l2(x,y)'."""
+    pairs = []
+    if isinstance(reg, float):
+        pairs.append((2, reg))
+    elif isinstance(reg, str):
+        body = reg.rstrip(")").split("(")[-1]
+        if reg.startswith("l1(") or reg.startswith("l2("):
+            pairs.append((int(reg[1]), float(body)))
+        elif reg.startswith("l1_l2"):
+            l1, l2 = body.split(",")
+            pairs += [(1, float(l1)), (2, float(l2))]
+        else:
+            raise NotImplementedError("regularizer={} is not supported.".format(reg))
+    return pairs
+
+
+class DeepFM(RankModel):
+    def __init__(self, feature_map, model_id="DeepFM", gpu=-1, learning_rate=1e-3, embedding_dim=10,
+                 hidden_units=[64, 64, 64], hidden_activations="ReLU", net_dropout=0, batch_norm=False,
+                 embedding_regularizer=None, net_regularizer=None, **kwargs):
+        super(DeepFM, self).__init__(feature_map, model_id=model_id, gpu=gpu,
+                                     embedding_regularizer=embedding_regularizer,
+                                     net_regularizer=net_regularizer, **kwargs)
+        self.embedding_layer = FeatureEmbedding(feature_map, embedding_dim)
+        self.fm = FactorizationMachine(feature_map)
+        self.mlp = MLP_Block(input_dim=feature_map.sum_emb_out_dim(), output_dim=1,
+                             hidden_units=hidden_units, hidden_activations=hidden_activations,
+                             output_activation=None, dropout_rates=net_dropout, batch_norm=batch_norm)
+        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
+        self.reset_parameters()
+        self.model_to_device()
+
+    def forward_logits(self, inputs):
+        X = self.get_inputs(inputs)
+        feature_emb = self.embedding_layer(X)
+        return (self.fm.fm_layer(feature_emb), self.fm.lr_layer(X),
+                self.mlp(feature_emb.flatten(start_dim=1)))
+
+    def forward(self, inputs):
+        X = self.get_inputs(inputs)
+        feature_emb = self.embedding_layer(X)
+        y_pred = self.fm(X, feature_emb)
+        y_pred = y_pred + self.mlp(feature_emb.flatten(start_dim=1))
+        return {"y_pred": self.output_activation(y_pred)}
+
+
+class DCNv2(RankModel):
+    def __init__(self, feature_map, model_id="DCNv2", gpu=-1, model_structure="parallel",
+                 use_low_rank_mixture=False, low_rank=32, num_experts=4, learning_rate=1e-3,
+                 embedding_dim=10, stacked_dnn_hidden_units=[], parallel_dnn_hidden_units=[],
+                 dnn_activations="ReLU", num_cross_layers=3, net_dropout=0, batch_norm=False,
+                 embedding_regularizer=None, net_regularizer=None, **kwargs):
+        super(DCNv2, self).__init__(feature_map, model_id=model_id, gpu=gpu,
+                                    embedding_regularizer=embedding_regularizer,
+                                    net_regularizer=net_regularizer, **kwargs)
+        if use_low_rank_mixture:
+            raise NotImplementedError("CrossNetMix is outside the B200 hot path (SURVEY.md section 2 row 6)")
+        if model_structure not in ["crossnet_only", "stacked", "parallel", "stacked_parallel"]:
+            raise AssertionError("model_structure={} not supported!".format(model_structure))
+        self.model_structure = model_structure
+        self.embedding_layer = FeatureEmbedding(feature_map, embedding_dim)
+        input_dim = feature_map.sum_emb_out_dim()
+        self.crossnet = CrossNetV2(input_dim, num_cross_layers)
+        final_dim = input_dim
+        if model_structure in ["stacked", "stacked_parallel"]:
+            self.stacked_dnn = MLP_Block(input_dim=input_dim, output_dim=None,
+                                         hidden_units=stacked_dnn_hidden_units,
+                                         hidden_activations=dnn_activations, output_activation=None,
+                                         dropout_rates=net_dropout, batch_norm=batch_norm)
+            final_dim = stacked_dnn_hidden_units[-1]
+        if model_structure in ["parallel", "stacked_parallel"]:
+            self.parallel_dnn = MLP_Block(input_dim=input_dim, output_dim=None,
+                                          hidden_units=parallel_dnn_hidden_units,
+                                          hidden_activations=dnn_activations, output_activation=None,
+                                          dropout_rates=net_dropout, batch_norm=batch_norm)
+            final_dim = input_dim + parallel_dnn_hidden_units[-1]
+        if model_structure == "stacked_parallel":
+            final_dim = stacked_dnn_hidden_units[-1] + parallel_dnn_hidden_units[-1]
+        self.fc = nn.Linear(final_dim, 1)
+        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
+        self.reset_parameters()
+        self.model_to_device()
+
+    def _final_out(self, inputs):
+        X = self.get_inputs(inputs)
+        feature_emb = self.embedding_layer(X, flatten_emb=True)
+        cross_out = self.crossnet(feature_emb)
+        if self.model_structure == "crossnet_only":
+            return cross_out
+        if self.model_structure == "stacked":
+            return self.stacked_dnn(cross_out)
+        if self.model_structure == "parallel":
+            return torch.cat([cross_out, self.parallel_dnn(feature_emb)], dim=-1)
+        return torch.cat([self.stacked_dnn(cross_out), self.parallel_dnn(feature_emb)], dim=-1)
+
+    def forward_logits(self, inputs):
+        final_out = self._final_out(inputs)
+        return (F2.linear_act(final_out, self.fc.weight, self.fc.bias),)
+
+    def forward(self, inputs):
+        y_pred = F2.linear_act(self._final_out(inputs), self.fc.weight, self.fc.bias)
+        return {"y_pred": self.output_activation(y_pred)}
+
+
+class DLRM(RankModel):
+    def __init__(self, feature_map, model_id="DLRM", gpu=-1, learning_rate=1e-3, embedding_dim=10,
+                 top_mlp_units=[64, 64, 64], bottom_mlp_units=[64, 64, 64], top_mlp_activations="ReLU",
+                 bottom_mlp_activations="ReLU", top_mlp_dropout=0, bottom_mlp_dropout=0,
+                 interaction_op="dot", batch_norm=False, embedding_regularizer=None,
+                 net_regularizer=None, **kwargs):
+        super(DLRM, self).__init__(feature_map, model_id=model_id, gpu=gpu,
+                                   embedding_regularizer=embedding_regularizer,
+                                   net_regularizer=net_regularizer, **kwargs)
+        self.dense_feats = [f for f, spec in feature_map.features.items() if spec["type"] == "numeric"]
+        self.embedding_layer = FeatureEmbedding(feature_map, embedding_dim,
+                                                not_required_feature_columns=self.dense_feats)
+        n_fields = feature_map.num_fields
+        if self.dense_feats:
+            n_fields = feature_map.num_fields - len(self.dense_feats) + 1
+            self.bottom_mlp = MLP_Block(input_dim=len(self.dense_feats), output_dim=embedding_dim,
+                                        hidden_units=bottom_mlp_units,
+                                        hidden_activations=bottom_mlp_activations,
+                                        output_activation=bottom_mlp_activations,
+                                        dropout_rates=bottom_mlp_dropout, batch_norm=batch_norm)
+        self.interaction_op = interaction_op
+        if interaction_op == "dot":
+            self.interact = InnerProductInteraction(num_fields=n_fields, output="inner_product")
+            top_input_dim = (n_fields * (n_fields - 1)) // 2 + embedding_dim * int(len(self.dense_feats) > 0)
+        elif interaction_op == "cat":
+            self.interact = nn.Flatten(start_dim=1)
+            top_input_dim = n_fields * embedding_dim
+        else:
+            raise ValueError("interaction_op={} not supported.".format(interaction_op))
+        self.top_mlp = MLP_Block(input_dim=top_input_dim, output_dim=1, hidden_units=top_mlp_units,
+                                 hidden_activations=top_mlp_activations,
+                                 output_activation=self.output_activation,
+                                 dropout_rates=top_mlp_dropout, batch_norm=batch_norm)
+        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
+        self.reset_parameters()
+        self.model_to_device()
+
+    def forward(self, inputs):
+        X = self.get_inputs(inputs)
+        feat_emb = self.embedding_layer(X)
+        if self.dense_feats:
+            dense_x = torch.cat([X[k] for k in self.dense_feats], dim=-1)
+            dense_emb = self.bottom_mlp(dense_x)
+            feat_emb = torch.cat([feat_emb, dense_emb.unsqueeze(1)], dim=1)
+        interact_out = self.interact(feat_emb)
+        if self.interaction_op == "dot" and self.dense_feats:
+            interact_out = torch.cat([interact_out, dense_emb], dim=-1)
+        return {"y_pred": self.top_mlp(interact_out)}
+
+
+class DIN(RankModel):
+    def __init__(self, feature_map, model_id="DIN", gpu=-1, dnn_hidden_units=[512, 128, 64],
+                 dnn_activations="ReLU", attention_hidden_units=[64], attention_hidden_activations="Dice",
+                 attention_output_activation=None, attention_dropout=0, learning_rate=1e-3,
+                 embedding_dim=10, net_dropout=0, batch_norm=False,
+                 din_target_field=[("item_id", "cate_id")],
+                 din_sequence_field=[("click_history", "cate_history")], din_use_softmax=False,
+                 embedding_regularizer=None, net_regularizer=None, **kwargs):
+        super(DIN, self).__init__(feature_map, model_id=model_id, gpu=gpu,
+                                  embedding_regularizer=embedding_regularizer,
+                                  net_regularizer=net_regularizer, **kwargs)
+        self.din_target_field = din_target_field if isinstance(din_target_field, list) else [din_target_field]
+        self.din_sequence_field = din_sequence_field if isinstance(din_sequence_field, list) \
+            else [din_sequence_field]
+        assert len(self.din_target_field) == len(self.din_sequence_field), \
+            "len(din_target_field) != len(din_sequence_field)"
+        if isinstance(dnn_activations, str) and dnn_activations.lower() == "dice":
+            dnn_activations = [Dice(units) for units in dnn_hidden_units]
+        self.embedding_dim = embedding_dim
+        self.embedding_layer = FeatureEmbeddingDict(feature_map, embedding_dim)
+        self.attention_layers = nn.ModuleList(
+            [DIN_Attention(embedding_dim * len(tf) if type(tf) == tuple else embedding_dim,
+                           attention_units=attention_hidden_units,
+                           hidden_activations=attention_hidden_activations,
+                           output_activation=attention_output_activation,
+                           dropout_rate=attention_dropout, use_softmax=din_use_softmax)
+             for tf in self.din_target_field])
+        self.dnn = MLP_Block(input_dim=feature_map.sum_emb_out_dim(), output_dim=1,
+                             hidden_units=dnn_hidden_units, hidden_activations=dnn_activations,
+                             output_activation=self.output_activation, dropout_rates=net_dropout,
+                             batch_norm=batch_norm)
+        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
+        self.reset_parameters()
+        self.model_to_device()
+
+    def get_embedding(self, field, feature_emb_dict):
+        if type(field) == tuple:
+            return torch.cat([feature_emb_dict[f] for f in field], dim=-1)
+        return feature_emb_dict[field]
+
+    def forward(self, inputs):
+        X = self.get_inputs(inputs)
+        feature_emb_dict = self.embedding_layer(X)
+        for idx, (target_field, sequence_field) in enumerate(zip(self.din_target_field, self.din_sequence_field)):
+            target_emb = self.get_embedding(target_field, feature_emb_dict)
+            sequence_emb = self.get_embedding(sequence_field, feature_emb_dict)
+            seq_fields = list(_flatten([sequence_field]))
+            mask = X[seq_fields[0]].long() != 0  # padding_idx = 0 required
+            pooling_emb = self.attention_layers[idx](target_emb, sequence_emb, mask)
+            for field, field_emb in zip(seq_fields, pooling_emb.split(self.embedding_dim, dim=-1)):
+                feature_emb_dict[field] = field_emb
+        feature_emb = self.embedding_layer.dict2tensor(feature_emb_dict, flatten_emb=True)
+        return {"y_pred": self.dnn(feature_emb)}
+
+
+class xDeepFM(RankModel):
+    def __init__(self, feature_map, model_id="xDeepFM", gpu=-1, learning_rate=1e-3, embedding_dim=10,
+                 dnn_hidden_units=[64, 64, 64], dnn_activations="ReLU", cin_hidden_units=[16, 16, 16],
+                 net_dropout=0, batch_norm=False, embedding_regularizer=None, net_regularizer=None,
+                 **kwargs):
+        super(xDeepFM, self).__init__(feature_map, model_id=model_id, gpu=gpu,
+                                      embedding_regularizer=embedding_regularizer,
+                                      net_regularizer=net_regularizer, **kwargs)
+        self.embedding_layer = FeatureEmbedding(feature_map, embedding_dim)
+        self.dnn = MLP_Block(input_dim=feature_map.sum_emb_out_dim(), output_dim=1,
+                             hidden_units=dnn_hidden_units, hidden_activations=dnn_activations,
+                             output_activation=None, dropout_rates=net_dropout, batch_norm=batch_norm) \
+            if dnn_hidden_units else None
+        self.lr_layer = LogisticRegression(feature_map, use_bias=False)
+        self.cin = CompressedInteractionNet(feature_map.num_fields, cin_hidden_units, output_dim=1)
+        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
+        self.reset_parameters()
+        self.model_to_device()
+
+    def forward_logits(self, inputs):
+        X = self.get_inputs(inputs)
+        feature_emb = self.embedding_layer(X)
+        terms = [self.lr_layer(X), self.cin(feature_emb)]
+        if self.dnn is not None:
+            terms.append(self.dnn(feature_emb.flatten(start_dim=1)))
+        return tuple(terms)
+
+    def forward(self, inputs):
+        terms = self.forward_logits(inputs)
+        y_pred = terms[0] + terms[1]
+        if len(terms) > 2:
+            y_pred = y_pred + terms[2]
+        return {"y_pred": self.output_activation(y_pred)}

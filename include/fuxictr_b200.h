@@ -1,0 +1,224 @@
+/*
+ * fuxictr_b200.h — C-ABI of the B200 (sm_100a) hot path for FuxiCTR models.
+ *
+ * The reference (reczoo/FuxiCTR v2.3.10) has no FFI: its hot path is a set of
+ * torch.nn.Module classes that dispatch to stock ATen ops.  Every entry point
+ * below replaces one of those ATen call sites; the citation beside each
+ * declaration is the reference file:line (relative to the reference root) whose
+ * arithmetic the kernel reproduces.  INTEGRATION.md shows the Python (ctypes)
+ * binding a FuxiCTR maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain C types only: raw DEVICE pointers, explicit sizes/strides, a
+ *    cudaStream_t passed as void* (0 = legacy default stream).
+ *  - every call is asynchronous on `stream`; nothing synchronises internally,
+ *    nothing is allocated; outputs/workspaces are caller-allocated.
+ *  - return value: 0 on success, negative B2_E_* on failure; the message for
+ *    the calling thread's last failure is b2_last_error().
+ *  - all matrices are row-major unless a stride argument says otherwise.
+ *  - "f32" everywhere means IEEE binary32 with round-to-nearest FMA
+ *    arithmetic; global atomics flush subnormals (PTX red.global.add.f32).
+ */
+#ifndef FUXICTR_B200_H_
+#define FUXICTR_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B2_API __attribute__((visibility("default")))
+#else
+#define B2_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------- */
+#define B2_OK 0
+#define B2_E_INVALID (-1)    /* bad argument (null pointer, unsupported size/dtype) */
+#define B2_E_CUDA (-2)       /* CUDA runtime/driver error; see b2_last_error() */
+#define B2_E_UNSUPPORTED (-3)/* valid request this build cannot serve */
+
+/* ---- dtype codes --------------------------------------------------------- */
+#define B2_F32 0
+#define B2_BF16 1
+#define B2_F64 2  /* index matrices arrive as float64 (npz_dataloader.py:63-66) */
+#define B2_I64 3
+#define B2_I32 4
+
+/* ---- pooling modes of a sequence field (feature_encoder) ---------------- */
+#define B2_POOL_NONE 0 /* emit (B, L, D) */
+#define B2_POOL_SUM 1  /* MaskedSumPooling, layers/pooling.py:62-73 */
+#define B2_POOL_MEAN 2 /* MaskedAveragePooling, layers/pooling.py:33-49 */
+
+/* ---- activation codes for fused GEMM epilogues --------------------------- */
+#define B2_ACT_NONE 0
+#define B2_ACT_RELU 1
+#define B2_ACT_SIGMOID 2
+
+#define B2_MAX_FIELDS 128
+
+/* Library/version probes (no GPU needed). */
+B2_API const char* b2_version(void);
+B2_API const char* b2_last_error(void);
+/* Returns the compute capability major*10+minor of `device`, or a negative
+ * error.  The library only contains sm_100a code. */
+B2_API int b2_device_cc(int device);
+
+/*
+ * One feature of the fused multi-field gather.  Mirrors one iteration of the
+ * per-feature loop in FeatureEmbeddingDict.forward
+ * (fuxictr/pytorch/layers/embeddings/feature_embedding.py:261-297): `idx` is
+ * the (B,) [or (B, L)] column view the BatchCollator produced
+ * (dataloaders/npz_dataloader.py:111-125), `table` is the nn.Embedding weight
+ * (feature_embedding.py:172-175), `out` is where the caller wants this
+ * feature's slice of the stacked (B,F,D) / concatenated (B,sum D) tensor that
+ * dict2tensor would build (feature_embedding.py:230-259), or a separate
+ * (B,L,D) buffer for an unpooled sequence.
+ */
+typedef struct b2_field {
+  const void* table;   /* (vocab, dim) row-major table, or its dense-grad twin in *_bwd */
+  const void* idx;     /* index of sample 0, position 0 */
+  void* out;           /* output element of sample 0 (fwd: written, bwd: grad read) */
+  int64_t vocab;       /* rows in table */
+  int64_t idx_stride;  /* index elements between consecutive samples */
+  int64_t out_stride;  /* output elements between consecutive samples */
+  int32_t dim;         /* embedding dim of this field */
+  int32_t seq_len;     /* 1 = categorical; L = sequence, positions contiguous */
+  int32_t pool;        /* B2_POOL_* (only meaningful when seq_len > 1) */
+  int32_t padding_idx; /* row that receives no gradient; -1 = none */
+} b2_field;
+
+/*
+ * Fused multi-field embedding gather, forward.
+ * Replaces, for all F features in one launch: the `.long()` cast + aten::embedding
+ * per feature (feature_embedding.py:283-288), the optional Masked{Sum,Average}Pooling
+ * encoder (layers/pooling.py:45-49,73) and the torch.stack/torch.cat of
+ * dict2tensor (feature_embedding.py:255-258).
+ *   fields     HOST array of nfields descriptors (copied into the launch)
+ *   idx_dtype  B2_F64 | B2_I64 | B2_I32 (f64 is truncated toward zero like .long())
+ *   elem_dtype B2_F32 (tables and outputs)
+ *   mean_count device f32[nfields * batch] or NULL; required when a field uses
+ *              B2_POOL_MEAN: receives at [f*batch + b] the MaskedAveragePooling
+ *              denominator (positions whose embedding vector sums to non-zero,
+ *              pooling.py:46-47) for the backward.
+ *   status     device int32[1], or NULL.  Set (atomicMax) to 1+field if an index is
+ *              outside [0, vocab) (the reference raises IndexError); the row is zero-filled.
+ */
+B2_API int b2_embed_gather_fwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype,
+                        int elem_dtype, float* mean_count, int32_t* status, void* stream);
+
+/*
+ * Backward of the fused gather: dense-gradient scatter-add with warp-level
+ * aggregation of duplicate rows.  Replaces F x aten::embedding_dense_backward
+ * (autograd of feature_embedding.py:285,288).  In each descriptor `table` is the
+ * (vocab, dim) f32 GRADIENT buffer (accumulated into: the caller zeroes it when it
+ * wants "=" semantics), `out` is the incoming gradient laid out exactly like the
+ * forward output; rows whose index equals padding_idx receive no gradient
+ * (nn.Embedding(padding_idx)).  mean_count is the buffer the forward filled
+ * (NULL when no field uses B2_POOL_MEAN).
+ */
+B2_API int b2_embed_scatter_bwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype,
+                         int elem_dtype, const float* mean_count, void* stream);
+
+/*
+ * LogisticRegression.forward (layers/blocks/logistic_regression.py:55-58):
+ * out[b] = sum over features (and sequence positions, MaskedSumPooling,
+ * feature_embedding.py:135-138) of table_f[idx] + bias[0].  Tables are
+ * (vocab,1) f32; `fields[i].out/out_stride/dim/pool` are ignored.
+ *   bias  device f32[1] or NULL;  out  device f32[batch]
+ */
+B2_API int b2_lr_fwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype, const float* bias,
+              float* out, int32_t* status, void* stream);
+/* Backward: table_f[idx] += gout[b] (skipping padding_idx); if gbias != NULL,
+ * gbias[0] += sum_b gout[b]. `table` fields point at the (vocab,1) gradient buffers. */
+B2_API int b2_lr_bwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype,
+              const float* gout, float* gbias, void* stream);
+
+/*
+ * InnerProductInteraction (layers/interactions/inner_product.py:55-70).
+ * emb is (B, F, D) f32 contiguous.
+ *   mode 0 "product_sum":    out (B,1)   = sum_d 0.5*((sum_f e)^2 - sum_f e^2)   (:56-62)
+ *   mode 1 "bi_interaction": out (B,D)   = 0.5*((sum_f e)^2 - sum_f e^2)         (:56-60)
+ *   mode 2 "inner_product":  out (B,F(F-1)/2) = triu(E E^T, 1), row-major pairs  (:64-66)
+ * *_bwd writes gemb (B,F,D) ("=" semantics).
+ */
+B2_API int b2_fm_fwd(const float* emb, int64_t batch, int nfields, int dim, int mode, float* out,
+              void* stream);
+B2_API int b2_fm_bwd(const float* emb, const float* gout, int64_t batch, int nfields, int dim, int mode,
+              float* gemb, void* stream);
+
+/*
+ * CrossNet (layers/interactions/cross_net.py:44-55,80-92), all layers in one
+ * launch: x_{i+1} = x_i + (w_i . x_i) * x_0 + b_i.
+ *   x0 (B,d); w (L,d); b (L,d); out (B,d); s (B,L) saved dot products w_i.x_i
+ * bwd: gx0 (B,d) "="; gw, gb (L,d) "+=" (caller zeroes).
+ */
+B2_API int b2_crossnet_fwd(const float* x0, const float* w, const float* b, int64_t batch, int d,
+                    int nlayers, float* out, float* s, void* stream);
+B2_API int b2_crossnet_bwd(const float* x0, const float* w, const float* b, const float* s,
+                    const float* gout, int64_t batch, int d, int nlayers, float* gx0, float* gw,
+                    float* gb, void* stream);
+
+/*
+ * Dense layer with fused epilogue; the GEMM behind MLP_Block
+ * (layers/blocks/mlp_block.py:74-85,96), CrossNetV2 (cross_net.py:126-129) and
+ * the 1x1 Conv1d of CIN (compressed_interaction_net.py:72).
+ *   C[m,n] = epi( sum_k A(m,k) * B(k,n) + bias[n] )
+ * A element (m,k) at a[m*a_rs + k*a_cs]; B element (k,n) at b[k*b_rs + n*b_cs];
+ * C row-major with leading dimension ldc.
+ *   act     B2_ACT_*
+ *   mul,add optional (M,N) row-major (ld = ldc): C = add + mul * (acc + bias)
+ *           (CrossNetV2: mul = x_0, add = x_i).  NULL = absent.
+ *   beta_accumulate != 0: C += result (used for gradient accumulation).
+ * math: B2_F32 = fp32 FMA (parity path); B2_BF16 = operands rounded to bf16,
+ * fp32 accumulate, on tcgen05 tensor cores when shapes allow.
+ */
+B2_API int b2_gemm_f32(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs,
+                int64_t b_cs, float* c, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                const float* bias, int act, const float* mul, const float* add,
+                int beta_accumulate, void* stream);
+
+/* Elementwise helpers used by the dense backward.
+ * b2_act_bwd: gx = gy * act'(y) where y is the activation OUTPUT (relu, sigmoid). */
+B2_API int b2_act_bwd(const float* y, const float* gy, float* gx, int64_t n, int act, void* stream);
+/* b2_colsum: out[n] (+)= sum_m x[m*ld + n]  (bias gradients). */
+B2_API int b2_colsum(const float* x, int64_t M, int64_t N, int64_t ld, float* out, int accumulate,
+              void* stream);
+
+/*
+ * Final glue of DeepFM.forward + BaseModel.add_loss (model_zoo/DeepFM/DeepFM_torch/
+ * src/DeepFM.py:84-86, fuxictr/pytorch/models/rank_model.py:120-131):
+ *   logit = sum of nterms per-sample terms; y_pred = sigmoid(logit);
+ *   loss  = mean_b BCE(y_pred, y) with torch's log clamp at -100.
+ * terms: device array... passed as up to 4 pointers (NULL = absent).
+ * Outputs: y_pred (B), loss (1, "=" semantics via two-stage reduction in ws),
+ * glogit (B) = (y_pred - y) / B  (NULL to skip).
+ */
+B2_API int b2_logit_bce_fwd(const float* t0, const float* t1, const float* t2, const float* t3,
+                     const float* label, int64_t batch, float* y_pred, float* loss,
+                     float* glogit, void* stream);
+
+/*
+ * Dense optimizer step over a flat fp32 arena, semantics of
+ * nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam
+ * (defaults betas=(0.9,0.999), eps=1e-8, weight_decay=0, amsgrad=False) as
+ * called by BaseModel.train_step (rank_model.py:321-322).
+ *   b2_sumsq: out[0] += sum g^2 over n elements (caller zeroes out).
+ *   b2_adam_step: clip_coef = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6));
+ *                 g' = g*clip_coef; m = b1*m + (1-b1)*g'; v = b2*v + (1-b2)*g'^2;
+ *                 p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps), with
+ *                 bc1 = 1-b1^step, bc2 = 1-b2^step, step read from step_dev[0]
+ *                 (device int64, already incremented by the caller).
+ *   If zero_grad != 0 the gradient arena is zeroed in the same pass.
+ */
+B2_API int b2_sumsq(const float* g, int64_t n, float* out, void* stream);
+B2_API int b2_adam_step(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq,
+                 float max_norm, float lr, float beta1, float beta2, float eps,
+                 const int64_t* step_dev, int zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUXICTR_B200_H_ */
