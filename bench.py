@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py — samples/sec of one DeepFM Criteo-shape training step on B200 (BASELINE.json
+configs[1]): 39 categorical fields x 25,641 rows (~1.0 M rows), emb_dim 16, MLP 300-300-300,
+batch 4096 per GPU.  A "step" is one pass of the hot path over one synthetic batch:
+zero_grad -> fused gather + LR + FM + MLP forward -> BCE -> backward (dense-gradient
+scatter-add, GEMM dgrad/wgrad) -> clip_grad_norm_(10) -> Adam  (the reference's
+BaseModel.train_step, fuxictr/pytorch/models/rank_model.py:307-323).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference ...                   # the reference's CPU path (oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NF, VOCAB, DIM, HIDDEN, BATCH = 39, 25641, 16, [300, 300, 300], 4096
+METRIC = "samples/sec DeepFM Criteo-shape train_step (fwd+bwd+clip+Adam)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--graph", type=int, default=1, help="capture the step in a CUDA graph")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nbatches", type=int, default=8, help="distinct synthetic batches rotated through")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "DeepFM Criteo-shape: %d fields x %d rows, emb_dim %d, MLP %s, fp32 Adam"
+                        % (NF, VOCAB, DIM, HIDDEN),
+            "global_batch": args.batch * n_gpus, "per_gpu_batch": args.batch,
+            "parallelism": "dp%d" % n_gpus if n_gpus > 1 else "single",
+            "cache": "working set (4 fp32 arenas x 68 MB: params, grads, Adam m/v) exceeds the 126 MB L2; "
+                     "%d distinct index batches are rotated" % args.nbatches}
+
+
+def make_specs():
+    return [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": VOCAB})
+            for i in range(NF)]
+
+
+def make_batches(n, batch, seed=0):
+    """uniform ids in [1, V), Bernoulli(0.25) labels, one (B, F+1) float64 matrix
+    per batch — exactly what the reference's BatchCollator hands to the model."""
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        ids = torch.randint(1, VOCAB, (batch, NF), generator=gen).double()
+        label = (torch.rand(batch, 1, generator=gen) < 0.25).double()
+        out.append(torch.cat([ids, label], dim=1))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# clocks / throttle sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.rows, self.proc, self.dev = [], None, device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU leg: the reference's own path (ATen ops on host cores), via the oracle restatement
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(batch, steps, warmup, seconds=None, threads=None):
+    """Times BaseModel.train_step as the reference executes it on CPU (oracle port: the same ATen
+    ops — F.embedding x39, stack, FM, LR, Linear/ReLU, BCE, autograd, clip_grad_norm_, Adam)."""
+    import torch
+    from oracle import fuxictr_oracle as O
+    from fuxictr_b200 import zoo
+    from fuxictr_b200.schema import FeatureMap
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    specs = make_specs()
+    fm = FeatureMap.from_specs(specs, embedding_dim=DIM)
+    torch.manual_seed(2019)
+    model = zoo.DeepFM(fm, gpu=-1, embedding_dim=DIM, hidden_units=HIDDEN)  # parameter container only
+    spec_map = OrderedDict(specs)
+    tr = O.OracleTrainer(model.state_dict(), lambda s, X: torch.sigmoid(O.deepfm_logit(spec_map, s, X, len(HIDDEN))),
+                         spec_map, ["label"])
+    batches = [fm.batch_dict(m) for m in make_batches(4, batch)]
+    for i in range(warmup):
+        tr.train_step(batches[i % len(batches)])
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        tr.train_step(batches[done % len(batches)])
+        done += 1
+        el = time.perf_counter() - t0
+        if seconds is not None:
+            if el >= seconds and done >= 3:
+                break
+        elif done >= steps:
+            break
+    return {"value": batch * done / el, "ms_per_step": 1e3 * el / done, "steps": done, "cores": threads}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded: each step is one 4096-sample batch; cap the run at a few minutes
+    steps = min(args.steps, 400)
+    r = cpu_reference_run(args.batch, steps, min(args.warmup, 5))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 5),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
+            "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                             "sample": "%d train steps of batch %d on %d host threads (oracle port of the "
+                                       "reference's ATen path)" % (r["steps"], args.batch, r["cores"])},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def time_kernel(fn, reps, stream_sync=None):
+    """Average device duration (ms) of `fn` over `reps` back-to-back launches.  The launches are
+    captured into one CUDA graph so that host-side (Python/ctypes) launch cost does not leak into
+    a microsecond-scale kernel time; CUDA events bracket the replay on the launching stream."""
+    import torch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def kernel_rooflines(model, fm, dev_batch, peaks, args):
+    """Per-kernel achieved bandwidth, measured live with CUDA events: the fused gather (north-star
+    kernel) and the dense clip+Adam pass (largest share of the step)."""
+    import ctypes
+    import torch
+    from fuxictr_b200 import _lib, functional as F2
+    out = {}
+    hbm = peaks["hbm_gbs"]
+    X = OrderedDict((k, v) for k, v in fm.batch_dict(dev_batch).items() if k != "label")
+    B = dev_batch.shape[0]
+    # fused multi-field gather, algorithmic bytes: F*8 (ids) + F*D*4 (rows) + F*D*4 (out)
+    fed = model.embedding_layer.embedding_layer
+    with torch.no_grad():
+        ms = time_kernel(lambda: fed.forward_tensor(X), 50, None)
+    gbytes = B * (NF * 8 + 2 * NF * DIM * 4)
+    out["embed_gather_fwd"] = {"ms": ms, "algorithmic_bytes": gbytes, "GBps": gbytes / ms / 1e6,
+                               "frac_of_measured_hbm": gbytes / ms / 1e6 / hbm,
+                               "note": "B=%d: tables (64 MB) are L2-resident and the launch is latency-bound" % B}
+    # dense optimizer pass over the arena: 4 reads (p,g,m,v) + 4 writes (p,m,v, g=0) of fp32
+    opt = model._fused_optimizer
+    a = model._arena
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    P, G, M, V = (ctypes.c_void_p(t.data_ptr()) for t in (a.P, a.G, opt.M, opt.V))
+    backup = (a.P.clone(), opt.M.clone(), opt.V.clone(), a.G.clone())
+    opt.step_dev.add_(1)
+    ms = time_kernel(lambda: _lib.call("b2_adam_step", P, G, M, V, a.numel, ctypes.c_void_p(opt.sumsq.data_ptr()),
+                                       10.0, 1e-3, 0.9, 0.999, 1e-8, ctypes.c_void_p(opt.step_dev.data_ptr()),
+                                       1, st()), 30, None)
+    abytes = a.numel * 4 * 8
+    out["adam_step"] = {"ms": ms, "algorithmic_bytes": abytes, "GBps": abytes / ms / 1e6,
+                        "frac_of_measured_hbm": abytes / ms / 1e6 / hbm}
+    ms = time_kernel(lambda: _lib.call("b2_sumsq", G, a.numel, ctypes.c_void_p(opt.sumsq.data_ptr()), st()), 30, None)
+    sbytes = a.numel * 4
+    out["grad_sumsq"] = {"ms": ms, "algorithmic_bytes": sbytes, "GBps": sbytes / ms / 1e6,
+                         "frac_of_measured_hbm": sbytes / ms / 1e6 / hbm}
+    a.P.copy_(backup[0]); opt.M.copy_(backup[1]); opt.V.copy_(backup[2]); a.G.copy_(backup[3])
+    opt.step_dev.sub_(1)
+    return out
+
+
+def gather_stress(peaks):
+    """The gather against a table set far larger than L2 (39 x 4 M rows x 64 B = 10 GB) at large
+    batch: the HBM-bound operating point BASELINE.md asks the 60 %-of-peak claim to be made on."""
+    import torch
+    from fuxictr_b200 import functional as F2
+    res = []
+    rows, F_, D = 4_000_000, NF, DIM
+    tables = [torch.empty(rows, D, device="cuda").normal_(0, 0.01) for _ in range(F_)]
+    plan = F2.GatherPlan([F2.GatherField("C%d" % i, i, D, padding_idx=0) for i in range(F_)])
+    for B in (4096, 65536, 524288):
+        gen = torch.Generator(device="cuda").manual_seed(B)
+        mat = torch.randint(1, rows, (B, F_ + 1), device="cuda", generator=gen).double()
+        idx = [mat[:, i] for i in range(F_)]
+        with torch.no_grad():
+            ms = time_kernel(lambda: F2.embed_gather(plan, idx, tables), 20, None)
+        nbytes = B * (F_ * 8 + 2 * F_ * D * 4)
+        res.append({"batch": B, "ms": ms, "GBps": nbytes / ms / 1e6,
+                    "frac_of_measured_hbm": nbytes / ms / 1e6 / peaks["hbm_gbs"]})
+        del mat, idx
+    del tables
+    torch.cuda.empty_cache()
+    return {"table_bytes": rows * D * 4 * F_, "points": res}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fd:
+            p = json.load(fd)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from fuxictr_b200 import zoo, _lib
+    from fuxictr_b200.schema import FeatureMap
+    _lib.load()
+    peaks = load_peaks()
+
+    fm = FeatureMap.from_specs(make_specs(), embedding_dim=DIM)
+    torch.manual_seed(2019)
+    model = zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
+    opt = model.use_fused_optimizer()
+    if world > 1:
+        opt.grad_allreduce = True
+    model.train()
+    host_batches = [m.pin_memory() for m in make_batches(args.nbatches, args.batch, seed=1000 + rank)]
+    dev_batches = [m.cuda(non_blocking=True) for m in host_batches]
+    static_in = torch.empty_like(dev_batches[0])
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    batch_views = fm.batch_dict(static_in)
+
+    def step_eager():
+        return model.fused_train_step(batch_views)
+
+    # launches per step (our kernels only): counted by wrapping the C-ABI call once
+    counter = {"n": 0}
+    orig_call = _lib.call
+
+    def counting_call(name, *a):
+        counter["n"] += 1
+        return orig_call(name, *a)
+
+    static_in.copy_(dev_batches[0])
+    _lib.call = counting_call
+    step_eager()
+    torch.cuda.synchronize()
+    launches = counter["n"]
+    _lib.call = orig_call
+
+    graph = None
+    loss_static = None
+    if args.graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss_static = step_eager()
+
+    def run_step(i, e2e):
+        if e2e:
+            static_in.copy_(host_batches[i % len(host_batches)], non_blocking=True)   # H2D from pinned
+        else:
+            static_in.copy_(dev_batches[i % len(dev_batches)], non_blocking=True)    # already in HBM
+        if graph is not None:
+            graph.replay()
+            loss = loss_static
+        else:
+            loss = step_eager()
+        if e2e:
+            loss_host.copy_(loss.detach(), non_blocking=True)                        # D2H of the result
+        return loss
+
+    def timed(e2e, steps, warmup):
+        for i in range(warmup):
+            run_step(i, e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            run_step(warmup + i, e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    warmup = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(False, args.steps, warmup)
+    ms_e2e = timed(True, args.steps, warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss_host.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    samples = args.batch * world * args.steps
+    value = samples / (ms_total / 1e3)
+    e2e_value = samples / (ms_e2e / 1e3)
+    kernels = kernel_rooflines(model, fm, dev_batches[0], peaks, args)
+    dom = max(("adam_step", "embed_gather_fwd", "grad_sumsq"), key=lambda k: kernels[k]["ms"])
+    step_ms = ms_total / args.steps
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": kernels[dom]["frac_of_measured_hbm"], "traffic": None,
+                "peak_source": peaks["source"], "share_of_step": kernels[dom]["ms"] / step_ms}
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": host_batches[0].numel() * 8 * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "cuda_graph": bool(args.graph), "final_loss": final_loss,
+            "roofline": roofline, "kernels": kernels}
+    if world == 1:
+        try:
+            line["gather_stress"] = gather_stress(peaks)
+        except Exception as exc:  # e.g. a smaller GPU: report, do not hide
+            line["gather_stress"] = {"error": str(exc)}
+        if not args.no_cpu_baseline:
+            r = cpu_reference_run(args.batch, 0, 3, seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                    "sample": "%d train steps of batch %d in %.0f s on %d host threads (oracle port of "
+                                              "the reference's ATen path)" % (r["steps"], args.batch, args.cpu_seconds,
+                                                                              r["cores"])}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)

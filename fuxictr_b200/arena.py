@@ -96,6 +96,7 @@ class FusedAdam(object):
         self.step_dev = torch.zeros((), dtype=torch.int64, device=dev)
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.zero_grad_in_step = zero_grad_in_step
+        self.grad_allreduce = False  # data-parallel replicas: average G across ranks before the step
 
     def zero_grad(self, set_to_none=True):
         self.arena.begin_step(grads_zeroed=self.zero_grad_in_step and self._stepped)
@@ -106,6 +107,10 @@ class FusedAdam(object):
         a = self.arena
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         self.step_dev.add_(1)
+        if self.grad_allreduce:
+            import torch.distributed as dist
+            dist.all_reduce(a.G, op=dist.ReduceOp.SUM)   # one NCCL collective over the whole arena
+            a.G.mul_(1.0 / dist.get_world_size())          # mean over the global batch (rank_model.py:130)
         sumsq_ptr = ctypes.c_void_p(0)
         if self.max_norm is not None:
             self.sumsq.zero_()

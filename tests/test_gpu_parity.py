@@ -1,0 +1,449 @@
+"""Parity of the sm_100a kernels (called through the C-ABI) against the reference goldens
+and the CPU oracle.  Bar (BASELINE.json north_star): index gather bit-exact; logits and
+gradients within 1e-5 relative fp32."""
+import ctypes
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, rel_err, close, ROOT
+
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__
+    __graft_entry__.build()
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from fuxictr_b200 import _lib
+    cc = _lib.load().b2_device_cc(0)
+    assert cc == 100, "library is sm_100a only (device reports cc %d)" % cc
+
+
+def fm_from(g, emb_dim=None):
+    from fuxictr_b200.schema import FeatureMap
+    return FeatureMap.from_specs(g.meta["specs"], labels=g.meta["labels"], embedding_dim=emb_dim)
+
+
+def cuda_batch(fm, mat, dtype=None):
+    mat = mat.cuda()
+    if dtype is not None:
+        mat = mat.to(dtype)
+    batch = fm.batch_dict(mat)
+    return batch, OrderedDict((k, v) for k, v in batch.items() if k not in fm.labels)
+
+
+def load_module(module, g, group="w"):
+    module.load_state_dict({k: v for k, v in g[group].items()})
+    return module.cuda()
+
+
+def check_param_grads(module, g, rtol=RTOL):
+    named = dict(module.named_parameters())
+    for k, ref in g["g"].items():
+        got = named[k].grad
+        assert got is not None, k
+        assert close(got, ref, rtol), (k, rel_err(got, ref))
+
+
+# ------------------------------------------------------------------ embeddings
+@pytest.mark.parametrize("idx_dtype", [torch.float64, torch.int64, torch.int32])
+def test_feature_embedding_bit_exact(idx_dtype):
+    from fuxictr_b200 import layers
+    g = Golden("feature_embedding_tiny_npz")
+    fm = fm_from(g, 4)
+    layer = load_module(layers.FeatureEmbedding(fm, 4), g)
+    _, X = cuda_batch(fm, g["in"]["matrix"], idx_dtype)
+    out = layer(X)
+    assert torch.equal(out.cpu(), g["out"]["stack"])                    # bit-exact gather
+    assert torch.equal(layer(X, flatten_emb=True).cpu(), g["out"]["flat"])
+    out.backward(g["in"]["gout"].cuda())
+    check_param_grads(layer, g)
+
+
+@pytest.mark.parametrize("tag", ["plain", "avgpool", "sumpool"])
+def test_feature_embedding_dict_sequence_shared(tag):
+    from fuxictr_b200 import layers
+    g = Golden("feature_embedding_dict_tiny_seq_" + tag)
+    fm = fm_from(g, 6)
+    layer = load_module(layers.FeatureEmbeddingDict(fm, 6), g)
+    _, X = cuda_batch(fm, g["in"]["matrix"])
+    emb = layer(X)
+    assert list(emb.keys()) == [k for k in fm.features.keys()]
+    loss = 0
+    for k, ref in g["out"].items():
+        if tag == "plain" or k != "click_sequence":
+            assert torch.equal(emb[k].cpu(), ref), k                    # pure copies stay bit-exact
+        else:
+            assert close(emb[k], ref, RTOL), k
+        loss = loss + (emb[k] * g["gout"][k].cuda()).sum()
+    loss.backward()
+    check_param_grads(layer, g)
+
+
+def test_logistic_regression():
+    from fuxictr_b200 import layers
+    g = Golden("logistic_regression_tiny_seq")
+    fm = fm_from(g, 6)
+    layer = load_module(layers.LogisticRegression(fm), g)
+    _, X = cuda_batch(fm, g["in"]["matrix"])
+    out = layer(X)
+    assert close(out, g["out"]["y"], RTOL)
+    out.backward(g["in"]["gout"].cuda())
+    check_param_grads(layer, g)
+
+
+def test_out_of_range_index_is_flagged_and_empty_batch_ok():
+    from fuxictr_b200 import functional as F2, _lib
+    table = torch.randn(10, 8, device="cuda")
+    plan = F2.GatherPlan([F2.GatherField("a", 0, 8, padding_idx=0)])
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    idx = torch.tensor([1.0, 12.0, 3.0, -1.0], dtype=torch.float64, device="cuda")
+    out = F2.embed_gather(plan, [idx], [table], status=status)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 1                                      # 1 + field index
+    assert torch.equal(out[0], table[1]) and torch.equal(out[2], table[3])
+    assert float(out[1].abs().sum()) == 0.0 and float(out[3].abs().sum()) == 0.0
+    empty = F2.embed_gather(plan, [idx[:0]], [table])
+    assert tuple(empty.shape) == (0, 8)
+
+
+def test_gather_f64_truncation_matches_long():
+    from fuxictr_b200 import functional as F2
+    table = torch.arange(40, dtype=torch.float32, device="cuda").view(10, 4)
+    idx = torch.tensor([2.9, 3.0, 0.2, 7.999999], dtype=torch.float64, device="cuda")
+    plan = F2.GatherPlan([F2.GatherField("a", 0, 4)])
+    out = F2.embed_gather(plan, [idx], [table])
+    assert torch.equal(out, table[idx.long()])
+
+
+# ------------------------------------------------------------------ interactions
+@pytest.mark.parametrize("name", ["inner_product_B16_F7_D10", "inner_product_B9_F39_D16",
+                                  "inner_product_B5_F27_D16"])
+def test_inner_product(name):
+    from fuxictr_b200 import layers
+    g = Golden(name)
+    for mode, ref in g["out"].items():
+        emb = g["in"]["emb"].cuda().requires_grad_(True)
+        layer = layers.InnerProductInteraction(g.meta["F"], output=mode).cuda()
+        out = layer(emb)
+        assert close(out, ref, RTOL), mode
+        out.backward(g["in"]["gout_" + mode].cuda())
+        assert close(emb.grad, g["gin"][mode], RTOL), mode
+
+
+@pytest.mark.parametrize("name", ["crossnet", "crossnet_v2"])
+def test_cross(name):
+    from fuxictr_b200 import layers
+    g = Golden(name)
+    cls = layers.CrossNet if name == "crossnet" else layers.CrossNetV2
+    layer = load_module(cls(g.meta["input_dim"], g.meta["num_layers"]), g)
+    x0 = g["in"]["x0"].cuda().requires_grad_(True)
+    out = layer(x0)
+    assert close(out, g["out"]["y"], RTOL)
+    out.backward(g["in"]["gout"].cuda())
+    check_param_grads(layer, g)
+    assert close(x0.grad, g["gin"]["x0"], RTOL)
+
+
+def test_cin():
+    from fuxictr_b200 import layers
+    g = Golden("cin")
+    layer = load_module(layers.CompressedInteractionNet(g.meta["F"], g.meta["cin_hidden_units"]), g)
+    emb = g["in"]["emb"].cuda().requires_grad_(True)
+    out = layer(emb)
+    assert close(out, g["out"]["y"], RTOL)
+    out.backward(g["in"]["gout"].cuda())
+    check_param_grads(layer, g)
+    assert close(emb.grad, g["gin"]["emb"], RTOL)
+
+
+def test_mlp_relu():
+    from fuxictr_b200 import layers
+    g = Golden("mlp_relu")
+    layer = load_module(layers.MLP_Block(input_dim=20, hidden_units=[16, 12], hidden_activations="ReLU",
+                                         output_dim=1), g)
+    x = g["in"]["x"].cuda().requires_grad_(True)
+    out = layer(x)
+    assert close(out, g["out"]["y"], RTOL)
+    out.backward(g["in"]["gout"].cuda())
+    check_param_grads(layer, g)
+    assert close(x.grad, g["gin"]["x"], RTOL)
+
+
+def test_dice_train_and_eval():
+    from fuxictr_b200 import layers
+    g = Golden("dice")
+    layer = load_module(layers.Dice(12), g)
+    layer.train()
+    x = g["in"]["x"].cuda().requires_grad_(True)
+    out = layer(x)
+    assert close(out, g["out"]["train"], RTOL)
+    out.backward(g["in"]["gout"].cuda())
+    check_param_grads(layer, g)
+    assert close(x.grad, g["gin"]["x"], RTOL)
+    assert close(layer.bn.running_mean, g["w1"]["bn.running_mean"], RTOL)
+    assert close(layer.bn.running_var, g["w1"]["bn.running_var"], RTOL)
+    layer.eval()
+    assert close(layer(x.detach()), g["out"]["eval"], RTOL)
+
+
+@pytest.mark.parametrize("softmax", [0, 1])
+def test_din_attention(softmax):
+    from fuxictr_b200 import layers
+    g = Golden("din_attention_softmax%d" % softmax)
+    layer = load_module(layers.DIN_Attention(embedding_dim=8, attention_units=[16], hidden_activations="Dice",
+                                             use_softmax=bool(softmax)), g)
+    layer.train()
+    target = g["in"]["target"].cuda().requires_grad_(True)
+    hist = g["in"]["history"].cuda().requires_grad_(True)
+    out = layer(target, hist, g["in"]["mask"].cuda())
+    assert close(out, g["out"]["y"], RTOL)
+    out.backward(g["in"]["gout"].cuda())
+    check_param_grads(layer, g)
+    assert close(target.grad, g["gin"]["target"], RTOL)
+    assert close(hist.grad, g["gin"]["history"], RTOL)
+
+
+# ------------------------------------------------------------------ dense primitives
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (64, 64, 16), (65, 63, 17), (333, 300, 624),
+                                   (4096, 1, 300), (300, 624, 4096), (129, 257, 1000)])
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_f32_layouts(M, N, K, a_t, b_t):
+    from fuxictr_b200 import functional as F2
+    gen = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn((K, M) if a_t else (M, K), generator=gen)
+    b = torch.randn((N, K) if b_t else (K, N), generator=gen)
+    ref = (a.t() if a_t else a).double() @ (b.t() if b_t else b).double()
+    out = torch.empty(M, N, device="cuda")
+    F2.gemm_f32(a.cuda(), b.cuda(), out, a_t=a_t, b_t=b_t)
+    assert close(out, ref, 2e-6 * max(1, K) ** 0.5, atol=1e-6)
+
+
+def test_gemm_f32_epilogues_and_accumulate():
+    from fuxictr_b200 import functional as F2
+    from fuxictr_b200._lib import B2_ACT_RELU, B2_ACT_SIGMOID
+    gen = torch.Generator().manual_seed(3)
+    M, N, K = 200, 130, 96
+    a, b = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen)
+    bias, mul, add = torch.randn(N, generator=gen), torch.randn(M, N, generator=gen), torch.randn(M, N, generator=gen)
+    z = a.double() @ b.double().t() + bias.double()
+    out = torch.empty(M, N, device="cuda")
+    F2.gemm_f32(a.cuda(), b.cuda(), out, b_t=True, bias=bias.cuda(), act=B2_ACT_RELU)
+    assert close(out, torch.relu(z), RTOL)
+    F2.gemm_f32(a.cuda(), b.cuda(), out, b_t=True, bias=bias.cuda(), act=B2_ACT_SIGMOID)
+    assert close(out, torch.sigmoid(z), RTOL)
+    F2.gemm_f32(a.cuda(), b.cuda(), out, b_t=True, bias=bias.cuda(), mul=mul.cuda(), add=add.cuda())
+    assert close(out, add.double() + mul.double() * z, RTOL)           # CrossNetV2 epilogue
+    base = torch.randn(M, N, generator=gen)
+    out = base.cuda().clone()
+    F2.gemm_f32(a.cuda(), b.cuda(), out, b_t=True, accumulate=True)
+    assert close(out, base.double() + a.double() @ b.double().t(), RTOL)
+    # strided output (a column slice of a wider matrix), split-K path (few tiles, long K)
+    wide = torch.zeros(40, 100, device="cuda")
+    a2, b2 = torch.randn(40, 2048, generator=gen), torch.randn(2048, 30, generator=gen)
+    F2.gemm_f32(a2.cuda(), b2.cuda(), wide[:, 10:40])
+    assert close(wide[:, 10:40], a2.double() @ b2.double(), RTOL)
+    assert float(wide[:, :10].abs().sum()) == 0 and float(wide[:, 40:].abs().sum()) == 0
+
+
+def test_colsum_actbwd_logit_bce():
+    from fuxictr_b200 import functional as F2, _lib
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(1000, 77, generator=gen)
+    out = torch.empty(77, device="cuda")
+    xc = x.cuda()
+    _lib.call("b2_colsum", F2._ptr(xc), 1000, 77, 77, F2._ptr(out), 0, F2._stream())
+    assert close(out, x.double().sum(0), RTOL)
+    # fused logit + BCE against torch
+    B = 513
+    t = [torch.randn(B, 1, generator=gen).requires_grad_(True) for _ in range(3)]
+    y = (torch.rand(B, 1, generator=gen) < 0.3).float()
+    ref_loss = torch.nn.functional.binary_cross_entropy(torch.sigmoid(t[0] + t[1] + t[2]), y)
+    ref_loss.backward()
+    tc = [v.detach().cuda().requires_grad_(True) for v in t]
+    loss, y_pred = F2.logit_bce(y.cuda(), *tc)
+    loss.backward()
+    assert close(loss, ref_loss, RTOL)
+    assert close(y_pred, torch.sigmoid(t[0] + t[1] + t[2]), RTOL)
+    for a, b in zip(tc, t):
+        assert close(a.grad, b.grad, RTOL)
+
+
+def test_fused_adam_matches_torch_clip_plus_adam():
+    from fuxictr_b200 import zoo, arena
+    gen = torch.Generator().manual_seed(5)
+    lin = torch.nn.Sequential(torch.nn.Linear(13, 7), torch.nn.Linear(7, 3))
+    ref = torch.nn.Sequential(torch.nn.Linear(13, 7), torch.nn.Linear(7, 3))
+    ref.load_state_dict(lin.state_dict())
+    lin = lin.cuda()
+    ar = arena.ParamArena(lin)
+    opt = arena.FusedAdam(ar, lr=1e-2, max_norm=0.5)
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    for step in range(4):
+        x = torch.randn(20, 13, generator=gen)
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        lin(x.cuda()).pow(2).sum().backward()
+        # hand the torch-computed grads to the arena (this test isolates the optimizer kernel)
+        for p in ar.params:
+            ar.grad_view(p._b2_slot).copy_(p.grad)
+        ref(x).pow(2).sum().backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5)
+        ref_opt.step()
+        opt.step()
+        for (k, a), (_, b) in zip(lin.state_dict().items(), ref.state_dict().items()):
+            assert close(a, b, RTOL), (step, k)
+    assert float(ar.G.abs().sum()) == 0.0  # zero_grad fused into the step
+
+
+# ------------------------------------------------------------------ whole models vs reference goldens
+def build_model(name, g, fused):
+    from fuxictr_b200 import zoo
+    fm = fm_from(g, g.meta["kwargs"]["embedding_dim"])
+    model = getattr(zoo, name)(fm, gpu=-1, **g.meta["kwargs"])
+    model.load_state_dict(g["w"])
+    model.device = torch.device("cuda:0")
+    model.model_to_device()
+    model.compile("adam", "binary_crossentropy", 1e-3)  # optimizer over the CUDA parameters
+    model.train()
+    if fused:
+        model.use_fused_optimizer()
+    return fm, model
+
+
+@pytest.mark.parametrize("name", ["DeepFM", "DCNv2", "DLRM", "xDeepFM", "DIN"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_model_matches_reference_trajectory(name, fused):
+    g = Golden("model_" + name)
+    fm, model = build_model(name, g, fused)
+    B = g.meta["batch"]
+    mat = g["in"]["matrix"].cuda()
+    batches = [fm.batch_dict(mat[i * B:(i + 1) * B]) for i in range(3)]
+    # forward, loss and every gradient on batch 0
+    ret = model.forward(batches[0])
+    assert close(ret["y_pred"], g["out"]["y_pred"], RTOL)
+    loss = model.compute_loss(ret, model.get_labels(batches[0]))
+    assert close(loss, g["out"]["loss"], RTOL)
+    if fused:
+        model._fused_optimizer.zero_grad()
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k, ref in g["g"].items():
+        assert close(named[k].grad, ref, RTOL), (k, rel_err(named[k].grad, ref))
+    if fused:
+        model._arena.zero_grads()
+    # three optimisation steps follow the reference's (clip_grad_norm_ + Adam) trajectory
+    losses = []
+    for i in range(3):
+        step = model.fused_train_step if fused else model.train_step
+        losses.append(float(step(batches[i])))
+        if i == 0:
+            sd = model.state_dict()
+            for k, ref in g["w1"].items():
+                if ref.is_floating_point():
+                    assert close(sd[k], ref, RTOL), (k, rel_err(sd[k], ref))
+    assert close(torch.tensor(losses), g["out"]["step_losses"], RTOL)
+    sd = model.state_dict()
+    for k, ref in g["w3"].items():
+        if ref.is_floating_point():
+            assert close(sd[k], ref, 2e-5), (k, rel_err(sd[k], ref))
+
+
+# ------------------------------------------------------------------ BASELINE sizes: oracle + properties
+def criteo_shape(nf=39, vocab=25641, batch=4096, seed=0, zipf=False):
+    from fuxictr_b200.schema import FeatureMap
+    specs = [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": vocab})
+             for i in range(nf)]
+    fm = FeatureMap.from_specs(specs, embedding_dim=16)
+    gen = torch.Generator().manual_seed(seed)
+    if zipf:
+        u = torch.rand(batch, nf, generator=gen, dtype=torch.float64)
+        ids = torch.clamp((u ** -4.0).floor(), 1, vocab - 1)            # heavy head: many duplicates
+    else:
+        ids = torch.randint(1, vocab, (batch, nf), generator=gen).double()
+    label = (torch.rand(batch, 1, generator=gen) < 0.25).double()
+    return fm, OrderedDict(specs), torch.cat([ids, label], dim=1)
+
+
+@pytest.mark.parametrize("zipf", [False, True])
+def test_criteo_shape_gather_scatter_vs_oracle(zipf):
+    from fuxictr_b200 import layers
+    from oracle import fuxictr_oracle as O
+    fm, specs, mat = criteo_shape(zipf=zipf)
+    torch.manual_seed(1)
+    layer = layers.FeatureEmbedding(fm, 16, embedding_initializer="partial(nn.init.normal_, std=0.1)")
+    state = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in layer.state_dict().items())
+    layer = layer.cuda()
+    _, X = cuda_batch(fm, mat)
+    out = layer(X)
+    Xc = OrderedDict((k, v) for k, v in fm.batch_dict(mat).items() if k != "label")
+    ref = O.feature_embedding(specs, state, "", Xc)
+    assert torch.equal(out.cpu(), ref)                                   # bit-exact at C2 size
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(2))
+    out.backward(gout.cuda())
+    ref.backward(gout)
+    named = dict(layer.named_parameters())
+    for k, v in state.items():
+        assert close(named[k].grad, v.grad, RTOL), k
+    # size-independent properties: total gradient mass is conserved, padding row untouched
+    total = sum(float(p.grad.double().sum()) for p in named.values())
+    assert abs(total - float(gout.double().sum())) <= 1e-3 * float(gout.double().abs().sum()) ** 0.5 + 1e-3
+    for p in named.values():
+        assert float(p.grad[0].abs().sum()) == 0.0
+
+
+def test_criteo_shape_deepfm_step_vs_oracle():
+    """C2 (39 fields x 25,641 rows, D=16, MLP 300-300-300, B=4096): one full training step
+    against the oracle restatement of the reference (fused path and module path)."""
+    from fuxictr_b200 import zoo
+    from oracle import fuxictr_oracle as O
+    fm, specs, mat = criteo_shape()
+    torch.manual_seed(2019)
+    model = zoo.DeepFM(fm, gpu=-1, embedding_dim=16, hidden_units=[300, 300, 300])
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.Embedding):
+                m.weight[1:].normal_(0, 0.05)
+    state0 = OrderedDict((k, v.detach().clone()) for k, v in model.state_dict().items())
+    tr = O.OracleTrainer(state0, lambda s, X: torch.sigmoid(O.deepfm_logit(specs, s, X, 3)), specs, ["label"])
+    ref_losses = [float(tr.train_step(fm.batch_dict(mat))) for _ in range(2)]
+    model.device = torch.device("cuda:0")
+    model.model_to_device()
+    model.compile("adam", "binary_crossentropy", 1e-3)
+    model.use_fused_optimizer()
+    batch = fm.batch_dict(mat.cuda())
+    losses = [float(model.fused_train_step(batch)) for _ in range(2)]
+    assert close(torch.tensor(losses), torch.tensor(ref_losses), RTOL)
+    for k, v in model.state_dict().items():
+        assert close(v, tr.state[k], 2e-5), (k, rel_err(v, tr.state[k]))
+
+
+def test_scatter_linearity_and_idempotent_gather():
+    """Properties that hold at any size: gather(x) twice is identical; scatter(a*g1 + g2) ==
+    a*scatter(g1) + scatter(g2) up to fp32 rounding."""
+    from fuxictr_b200 import layers
+    fm, specs, mat = criteo_shape(nf=26, vocab=100003, batch=8192, seed=9, zipf=True)
+    layer = layers.FeatureEmbedding(fm, 16).cuda()
+    _, X = cuda_batch(fm, mat)
+    o1, o2 = layer(X), layer(X)
+    assert torch.equal(o1, o2)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    g1 = torch.randn(o1.shape, device="cuda", generator=gen)
+    g2 = torch.randn(o1.shape, device="cuda", generator=gen)
+
+    def scat(gout):
+        for p in layer.parameters():
+            p.grad = None
+        layer(X).backward(gout)
+        return torch.cat([p.grad.flatten() for p in layer.parameters()])
+    lhs = scat(2.5 * g1 + g2)
+    rhs = 2.5 * scat(g1) + scat(g2)
+    assert close(lhs, rhs, RTOL)
