@@ -1,0 +1,450 @@
+// gemm_tc.cu — TMA-fed tcgen05 (5th-gen tensor core) GEMM with TMEM accumulator and a
+// fused epilogue, sm_100a.  The dense contraction behind MLP_Block
+// (fuxictr/pytorch/layers/blocks/mlp_block.py:74-85), CrossNetV2's d x d Linear
+// (fuxictr/pytorch/layers/interactions/cross_net.py:126-129) and CIN's 1x1 Conv1d
+// (fuxictr/pytorch/layers/interactions/compressed_interaction_net.py:72).
+//
+//   C[m, n] = epi( sum_k A[m, k] * B[n, k] )      A: (M, K) K-major fp32, B: (N, K) K-major fp32
+//
+// Arithmetic: tcgen05.mma kind::tf32 reads the fp32 operands straight from shared memory
+// (the tensor core ignores the low 13 mantissa bits) and accumulates in fp32 in TMEM.
+//   precision 1 ("tf32"):   one pass, ~1e-3 relative — at least the bf16 the config names.
+//   precision 3 ("tf32x3"): error-compensated 3xTF32: with x = big(x) + small(x),
+//        A.B ~= A_big.B_big + A_big.B_small + A_small.B_big
+//     where big() is the hardware truncation itself and small = x - big(x) is produced by
+//     b2_split_tf32 — fp32-class accuracy (the 1e-5 parity bar) on tensor cores.
+//
+// Structure (one 128 x BN output tile per CTA, optional split-K across gridDim.z):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles into a 4-stage ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias/act/mul/add -> global
+// Every mbarrier wait is bounded: a pipeline bug traps with a message instead of hanging the GPU.
+#include "b2_common.cuh"
+#include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time
+
+namespace tc {
+constexpr int BM = 128;          // UMMA M (cta_group::1): TMEM lane == output row
+constexpr int BK = 32;           // fp32 elements per k-block == one 128-byte swizzle row
+constexpr int UMMA_K_BYTES = 32; // kind::tf32: K = 8 elements of 4 bytes per instruction
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * 128;
+constexpr int NTHREADS = 192;
+constexpr int TMEM_COLS = 256;
+
+struct Params {
+  CUtensorMap map_a[3];
+  CUtensorMap map_b[3];
+  float* c;
+  int64_t ldc;
+  const float* bias;
+  const float* mul;
+  const float* add;
+  int M, N, K, bn, nseg, act, beta, kb_per_split;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: ~2 s at 2 GHz, then report and trap (never hang the device).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int which) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("b2 tc_gemm: mbarrier wait timed out (role %d, block %d,%d,%d)\n", which, blockIdx.x,
+             blockIdx.y, blockIdx.z);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// K-major, 128-byte swizzle, tile rows are 128 B apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t) ((addr & 0x3FFFFu) >> 4);  // start address  [0,14)
+  d |= (uint64_t) 0 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t) (1024 >> 4) << 32;         // stride byte offset [32,46)
+  d |= (uint64_t) 1 << 46;                   // descriptor version (sm_100)
+  d |= (uint64_t) 2 << 61;                   // layout: SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte aligned bases: align by hand (1 KB of slack is requested).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+  const uint32_t b_bytes = (uint32_t) p.bn * 128u;
+  const uint32_t stage_bytes = A_BYTES + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES),
+                 tmem_full = smem_u32(bars + 2 * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.bn;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+  const int iters = (kb_end - kb_begin) * p.nseg;  // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_a[s])) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_b[s])) : "memory");
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate TMEM columns for the accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t) TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1, 0);
+          const uint32_t a_dst = smem_base + stage * stage_bytes;
+          const uint32_t full = full0 + 8 * stage;
+          mbar_expect_tx(full, stage_bytes);
+          tma_load_2d(a_dst, &p.map_a[seg], full, kb * BK, m0);
+          tma_load_2d(a_dst + A_BYTES, &p.map_b[seg], full, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (one thread) ----------------
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (p.bn >> 3) << 17) |
+                             ((uint32_t) (BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full0 + 8 * stage, phase, 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * stage_bytes;
+        const uint64_t adesc = make_smem_desc(a_addr);
+        const uint64_t bdesc = make_smem_desc(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
+          // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_tf32(tmem_base, adesc + (uint64_t) (k * (UMMA_K_BYTES >> 4)),
+                    bdesc + (uint64_t) (k * (UMMA_K_BYTES >> 4)), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);  // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----------------
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0, 2);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
+    const bool split = gridDim.z > 1;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      uint32_t v[32];
+      __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
+      tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, v);
+      if (m >= p.M) continue;
+      const int nb = n0 + c0;
+      float* crow = p.c + (int64_t) m * p.ldc;
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = nb + j4 + j;
+          float x = __uint_as_float(v[j4 + j]);
+          if (n < p.N) {
+            if (p.bias != nullptr && blockIdx.z == 0) x += __ldg(p.bias + n);
+            if (!split) {
+              if (p.mul != nullptr) x *= __ldg(p.mul + (int64_t) m * p.ldc + n);
+              if (p.add != nullptr) x += __ldg(p.add + (int64_t) m * p.ldc + n);
+              if (p.act == B2_ACT_RELU) x = fmaxf(x, 0.f);
+              else if (p.act == B2_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+              if (p.beta) x += crow[n];
+            }
+          }
+          r[j] = x;
+        }
+        const int n = nb + j4;
+        if (split) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < p.N) b2_red_add(crow + n + j, r[j]);
+        } else if (vec_ok && n + 3 < p.N) {
+          *reinterpret_cast<float4*>(crow + n) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < p.N) crow[n + j] = r[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t) TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// small(x) = x - big(x), big(x) = x with the 13 low mantissa bits cleared (what kind::tf32 reads)
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, float* __restrict__ small, int64_t n) {
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t) gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float big = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    small[i] = v - big;
+  }
+}
+
+// out (cols, rows) = in (rows, cols)^T through a padded shared tile; optionally also the
+// small() part of the transposed values (for the 3xTF32 operands of dgrad / wgrad).
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
+                 float* __restrict__ out, int64_t ld_out, float* __restrict__ out_small) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t c0 = (int64_t) blockIdx.x * 32, r0 = (int64_t) blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t r = r0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (r < rows && c < cols) ? __ldg(in + r * ld_in + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t c = c0 + ty + i, r = r0 + tx;  // out[c, r]
+    if (c < cols && r < rows) {
+      const float v = tile[tx][ty + i];
+      out[c * ld_out + r] = v;
+      if (out_small != nullptr)
+        out_small[c * ld_out + r] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    }
+  }
+}
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------
+typedef CUresult (*b2_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                       const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static b2_encode_tiled_fn b2_get_encode() {
+  static b2_encode_tiled_fn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<b2_encode_tiled_fn>(ptr);
+  }
+  return fn;
+}
+
+// (rows, K) fp32, K contiguous, leading dimension ld; box = 32 columns (128 B) x box_rows rows.
+static int encode_kmajor(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld,
+                         int box_rows) {
+  b2_encode_tiled_fn enc = b2_get_encode();
+  if (enc == nullptr) return b2_fail(B2_E_CUDA, "cuTensorMapEncodeTiled is unavailable in this driver");
+  cuuint64_t dims[2] = {(cuuint64_t) K, (cuuint64_t) rows};
+  cuuint64_t strides[1] = {(cuuint64_t) ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t) tc::BK, (cuuint32_t) box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return b2_fail(B2_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
+  return B2_OK;
+}
+
+static bool tma_ok(const float* p, int64_t ld) {
+  return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0);
+}
+
+extern "C" B2_API int b2_gemm_tc_supported(const float* a, int64_t lda, const float* b, int64_t ldb,
+                                           int64_t M, int64_t N, int64_t K) {
+  return (tma_ok(a, lda) && tma_ok(b, ldb) && M >= 1 && N >= 1 && K >= 1 && M < (1ll << 31) &&
+          N < (1ll << 31) && K < (1ll << 31)) ? 1 : 0;
+}
+
+extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
+                                 int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int act,
+                                 const float* mul, const float* add, int beta_accumulate,
+                                 const float* a_small, const float* b_small, void* stream) {
+  B2_REQUIRE(a && b && c, "NULL operand");
+  B2_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N && lda >= K && ldb >= K, "bad shape");
+  B2_REQUIRE(act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad activation code %d", act);
+  B2_REQUIRE((a_small == nullptr) == (b_small == nullptr), "3xTF32 needs both small operands");
+  if (!b2_gemm_tc_supported(a, lda, b, ldb, M, N, K) ||
+      (a_small != nullptr && !(tma_ok(a_small, lda) && tma_ok(b_small, ldb))))
+    return b2_fail(B2_E_UNSUPPORTED, "operands are not TMA-addressable (16-byte base, ld %% 4 == 0)");
+  cudaStream_t st = (cudaStream_t) stream;
+
+  // Tile-shape choice: BN in {32..256 step 32}; the kernel is bound by L2->SM operand traffic,
+  // so minimise waves x per-CTA operand bytes, where one wave = 148 CTAs (one per SM).
+  const int64_t tiles_m = b2_ceil_div(M, tc::BM);
+  const int64_t num_kb = b2_ceil_div(K, tc::BK);
+  const bool linear = (act == B2_ACT_NONE && mul == nullptr && add == nullptr);
+  int best_bn = 32, best_split = 1;
+  double best_cost = 1e300;
+  for (int bn = 32; bn <= 256; bn += 32) {
+    const int64_t tiles_n = b2_ceil_div(N, bn);
+    for (int split = 1; split <= 32; split *= 2) {
+      if (split > 1 && (!linear || num_kb / split < 8)) break;
+      const int64_t ctas = tiles_m * tiles_n * split;
+      const int64_t waves = b2_ceil_div(ctas, B2_NUM_SMS);
+      const double kb = (double) b2_ceil_div(num_kb, split);
+      // per-CTA time ~ fixed prologue/epilogue + k-blocks x bytes per k-block
+      const double cost = (double) waves * (24.0 * 160.0 + kb * (double) (tc::BM + bn));
+      if (cost < best_cost) { best_cost = cost; best_bn = bn; best_split = split; }
+    }
+  }
+  tc::Params p;
+  const int nseg = (a_small != nullptr) ? 3 : 1;
+  const float* as[3] = {a, a, a_small};   // A_big.B_big, A_big.B_small, A_small.B_big
+  const float* bs[3] = {b, b_small, b};
+  for (int s = 0; s < nseg; ++s) {
+    int rc = encode_kmajor(&p.map_a[s], as[s], M, K, lda, tc::BM);
+    if (rc != B2_OK) return rc;
+    rc = encode_kmajor(&p.map_b[s], bs[s], N, K, ldb, best_bn);
+    if (rc != B2_OK) return rc;
+  }
+  p.c = c; p.ldc = ldc; p.bias = bias; p.mul = mul; p.add = add;
+  p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.act = act;
+  p.beta = beta_accumulate ? 1 : 0;
+  p.kb_per_split = (int) b2_ceil_div(num_kb, best_split);
+  const int splits = (int) b2_ceil_div(num_kb, p.kb_per_split);
+  if (splits > 1 && !p.beta) {
+    cudaError_t e = cudaMemset2DAsync(c, (size_t) ldc * 4, 0, (size_t) N * 4, (size_t) M, st);
+    if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
+  }
+  const size_t smem = (size_t) tc::STAGES * (tc::A_BYTES + (size_t) best_bn * 128) + 1024 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) (tc::STAGES * (tc::A_BYTES + 256 * 128) + 1024 + 128));
+    if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned) tiles_m, (unsigned) b2_ceil_div(N, best_bn), (unsigned) splits);
+  B2_REQUIRE(grid.y <= 65535, "N too large for this launch geometry");
+  tc::gemm_tf32_kernel<<<grid, tc::NTHREADS, smem, st>>>(p);
+  B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_split_tf32(const float* x, float* small, int64_t n, void* stream) {
+  B2_REQUIRE(x && small, "NULL pointer");
+  if (n <= 0) return B2_OK;
+  int64_t blocks = b2_ceil_div(n, 256);
+  if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
+  tc::split_tf32_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(x, small, n);
+  B2_CUDA_LAUNCH_CHECK("b2_split_tf32");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in,
+                                       float* out, int64_t ld_out, float* out_small, void* stream) {
+  B2_REQUIRE(in && out, "NULL pointer");
+  B2_REQUIRE(rows >= 0 && cols >= 0 && ld_in >= cols && ld_out >= rows, "bad shape");
+  if (rows == 0 || cols == 0) return B2_OK;
+  dim3 grid((unsigned) b2_ceil_div(cols, 32), (unsigned) b2_ceil_div(rows, 32));
+  B2_REQUIRE(grid.y <= 65535, "too many rows for this launch geometry");
+  tc::transpose_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(in, rows, cols, ld_in, out, ld_out, out_small);
+  B2_CUDA_LAUNCH_CHECK("b2_transpose_f32");
+  return B2_OK;
+}

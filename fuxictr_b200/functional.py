@@ -360,6 +360,70 @@ def gemm_f32(a, b, out, a_t=False, b_t=False, bias=None, act=B2_ACT_NONE, mul=No
     return out
 
 
+# Matmul arithmetic of the dense layers:
+#   "fp32"   FFMA SIMT kernel (b2_gemm_f32)                       — bit-for-bit the reference's class
+#   "tf32x3" tcgen05 tensor cores, error-compensated 3xTF32       — fp32-class accuracy (1e-5 parity)
+#   "tf32"   tcgen05 tensor cores, single TF32 pass (10-bit mantissa, >= the bf16 of BASELINE configs[1])
+_MATMUL = {"mode": "fp32"}
+
+
+def set_matmul_precision(mode):
+    if mode not in ("fp32", "tf32x3", "tf32"):
+        raise ValueError("matmul precision must be 'fp32', 'tf32x3' or 'tf32'")
+    _MATMUL["mode"] = mode
+
+
+def get_matmul_precision():
+    return _MATMUL["mode"]
+
+
+def _tc_operand_ok(t):
+    return t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 \
+        and t.stride(0) >= t.shape[1]
+
+
+def split_tf32(t):
+    """small part of a contiguous fp32 tensor for 3xTF32."""
+    small = torch.empty_like(t)
+    _lib.call("b2_split_tf32", _ptr(t), _ptr(small), t.numel(), _stream())
+    return small
+
+
+def transpose_f32(t, want_small):
+    """(rows, cols) -> contiguous (cols, rows) [+ its 3xTF32 small part]."""
+    rows, cols = t.shape
+    out = torch.empty((cols, rows), dtype=torch.float32, device=t.device)
+    small = torch.empty_like(out) if want_small else None
+    _lib.call("b2_transpose_f32", _ptr(t), rows, cols, t.stride(0), _ptr(out), rows, _ptr(small), _stream())
+    return out, small
+
+
+def gemm_nt(a, b, out, bias=None, act=B2_ACT_NONE, mul=None, add=None, accumulate=False,
+            a_small=None, b_small=None):
+    """out (M,N) = epi(a (M,K) @ b (N,K)^T) in the configured matmul precision."""
+    mode = _MATMUL["mode"]
+    M, K = a.shape
+    N = b.shape[0]
+    use_tc = (mode != "fp32" and N >= 16 and _tc_operand_ok(a) and _tc_operand_ok(b) and out.stride(1) == 1)
+    if use_tc and mode == "tf32x3":
+        if a_small is None:
+            if not a.is_contiguous():
+                a = a.contiguous()
+            a_small = split_tf32(a)
+        if b_small is None:
+            if not b.is_contiguous():
+                b = b.contiguous()
+            b_small = split_tf32(b)
+    if not use_tc:
+        return gemm_f32(a, b, out, b_t=True, bias=bias, act=act, mul=mul, add=add, accumulate=accumulate)
+    if mode == "tf32":
+        a_small = b_small = None
+    _lib.call("b2_gemm_tc", _ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K,
+              _ptr(bias), act, _ptr(mul), _ptr(add), 1 if accumulate else 0, _ptr(a_small), _ptr(b_small),
+              _stream())
+    return out
+
+
 class _LinearAct(torch.autograd.Function):
     """y = act(x W^T + b): nn.Linear (+ReLU/Sigmoid) of MLP_Block (mlp_block.py:74-80)."""
 
@@ -369,7 +433,7 @@ class _LinearAct(torch.autograd.Function):
         M, K = x.shape
         N = weight.shape[0]
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        gemm_f32(x, weight, y, b_t=True, bias=bias, act=act)
+        gemm_nt(x, weight, y, bias=bias, act=act)
         ctx.act = act
         ctx.save_for_backward(x, weight, y if act != B2_ACT_NONE else None)
         ctx.has_bias = bias is not None
@@ -387,13 +451,26 @@ class _LinearAct(torch.autograd.Function):
             _lib.call("b2_act_bwd", _ptr(y), _ptr(gy), _ptr(gz), gy.numel(), ctx.act, _stream())
         else:
             gz = gy
+        mode = _MATMUL["mode"]
+        # tensor-core path needs K-major operands: dgrad contracts over N, wgrad over M
+        tc = mode != "fp32" and N % 4 == 0 and M % 4 == 0 and K % 4 == 0 and N >= 16 and K >= 16
+        x3 = mode == "tf32x3"
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty((M, K), dtype=torch.float32, device=x.device)
-            gemm_f32(gz, weight, gx)                      # dX = dZ W        (M,N)x(N,K)
+            if tc:
+                wt, wt_small = transpose_f32(weight, x3)                      # (K, N)
+                gemm_nt(gz, wt, gx, b_small=wt_small)                         # dX = dZ W
+            else:
+                gemm_f32(gz, weight, gx)
         if ctx.needs_input_grad[1]:
             gw = _grad_buffer(weight, zero=False)
-            gemm_f32(gz, x, gw, a_t=True)                 # dW = dZ^T X      (N,M)x(M,K)
+            if tc:
+                gzt, gzt_small = transpose_f32(gz, x3)                        # (N, M)
+                xt, xt_small = transpose_f32(x, x3)                           # (K, M)
+                gemm_nt(gzt, xt, gw, a_small=gzt_small, b_small=xt_small)     # dW = dZ^T X
+            else:
+                gemm_f32(gz, x, gw, a_t=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = _grad_buffer(ctx.bias, zero=False)
             _lib.call("b2_colsum", _ptr(gz), M, N, gz.stride(0), _ptr(gb), 0, _stream())

@@ -180,6 +180,29 @@ B2_API int b2_gemm_f32(const float* a, int64_t a_rs, int64_t a_cs, const float* 
                 const float* bias, int act, const float* mul, const float* add,
                 int beta_accumulate, void* stream);
 
+/*
+ * Tensor-core dense layer: same contract as b2_gemm_f32 for the K-major case
+ *   C[m,n] = epi( sum_k A[m,k] * B[n,k] + bias[n] ),  A (M,K) ld=lda, B (N,K) ld=ldb, fp32,
+ * computed by a TMA-fed tcgen05.mma kind::tf32 kernel with the accumulator in TMEM.
+ *   a_small == b_small == NULL : single-pass TF32 (operand mantissas truncated to 10 bits).
+ *   a_small, b_small given      : error-compensated 3xTF32 (fp32-class accuracy); they hold
+ *                                 x - tf32_trunc(x) of A and B (same shapes/lds), see b2_split_tf32.
+ * Operands must be TMA-addressable (16-byte aligned base, ld % 4 == 0): b2_gemm_tc_supported()
+ * says whether they are; otherwise B2_E_UNSUPPORTED is returned and the caller uses b2_gemm_f32.
+ */
+B2_API int b2_gemm_tc_supported(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t M,
+                                int64_t N, int64_t K);
+B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
+                      int64_t M, int64_t N, int64_t K, const float* bias, int act, const float* mul,
+                      const float* add, int beta_accumulate, const float* a_small,
+                      const float* b_small, void* stream);
+/* small[i] = x[i] - (x[i] with the 13 low mantissa bits cleared). */
+B2_API int b2_split_tf32(const float* x, float* small, int64_t n, void* stream);
+/* out (cols, rows; ld_out) = in (rows, cols; ld_in)^T; if out_small != NULL it also receives the
+ * 3xTF32 small part of the transposed values. */
+B2_API int b2_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                            int64_t ld_out, float* out_small, void* stream);
+
 /* Elementwise helpers used by the dense backward.
  * b2_act_bwd: gx = gy * act'(y) where y is the activation OUTPUT (relu, sigmoid). */
 B2_API int b2_act_bwd(const float* y, const float* gy, float* gx, int64_t n, int act, void* stream);

@@ -50,7 +50,7 @@ def rel_err(a, b):
     return float((a - b).abs().max()) / denom
 
 
-def close(a, b, rtol, atol=2e-7):
+def close(a, b, rtol, atol=1e-6):
     """|a-b|_inf <= rtol * |b|_inf + atol.  atol covers quantities that are mathematically zero
     (e.g. the last-bias gradient under a softmax) where only rounding noise remains."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
