@@ -107,6 +107,14 @@ class FusedAdam(object):
         a = self.arena
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         self.step_dev.add_(1)
+        # Gradients produced by stock autograd ops (parameters our kernels do not own, e.g. Dice's
+        # alpha or a Conv1d weight reached through a view) live in p.grad, not in the arena: bring
+        # them in.  Kernel-written gradients already alias their arena slot and are skipped.
+        g_base = a.G.data_ptr()
+        for p in a.params:
+            g = p.grad
+            if g is not None and g.data_ptr() != g_base + p._b2_slot.offset * 4:
+                a.grad_view(p._b2_slot).copy_(g)
         if self.grad_allreduce:
             import torch.distributed as dist
             dist.all_reduce(a.G, op=dist.ReduceOp.SUM)   # one NCCL collective over the whole arena

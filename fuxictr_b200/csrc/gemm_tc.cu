@@ -277,14 +277,21 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   }
 }
 
-// small(x) = x - big(x), big(x) = x with the 13 low mantissa bits cleared (what kind::tf32 reads)
+// small(x) = rna_tf32(x - big(x)), big(x) = x with the 13 low mantissa bits cleared (what
+// kind::tf32 reads from a raw fp32 operand).  x - big(x) is exact; rounding it to a
+// tf32-representable value HERE (round-to-nearest) makes the hardware truncation of the small
+// operand a no-op, so the residual of the split is unbiased instead of always toward zero.
+__device__ __forceinline__ float tf32_small(float v) {
+  const float big = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - big));
+  return __uint_as_float(r);
+}
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, float* __restrict__ small, int64_t n) {
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t) gridDim.x * blockDim.x) {
-    const float v = x[i];
-    const float big = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-    small[i] = v - big;
+    small[i] = tf32_small(x[i]);
   }
 }
 
@@ -309,7 +316,7 @@ transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64
       const float v = tile[tx][ty + i];
       out[c * ld_out + r] = v;
       if (out_small != nullptr)
-        out_small[c * ld_out + r] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        out_small[c * ld_out + r] = tf32_small(v);
     }
   }
 }
