@@ -29,7 +29,6 @@ constexpr int UMMA_K_BYTES = 32; // kind::tf32: K = 8 elements of 4 bytes per in
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * 128;
 constexpr int NTHREADS = 192;
-constexpr int TMEM_COLS = 256;
 
 struct Params {
   CUtensorMap map_a[3];
@@ -40,6 +39,8 @@ struct Params {
   const float* mul;
   const float* add;
   int M, N, K, bn, nseg, act, beta, kb_per_split;
+  int nmain;      // TMEM accumulators for the main (big x big) product: its K range is cut in nmain chunks
+  int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -150,7 +151,8 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   const int num_kb_total = (p.K + BK - 1) / BK;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
-  const int iters = (kb_end - kb_begin) * p.nseg;  // >= 1 by construction of the grid
+  // a short last K split may hold fewer k-blocks than accumulation chains
+  const int nmain = min(p.nmain, kb_end - kb_begin);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -167,7 +169,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   }
   if (warp == 1) {  // whole warp: allocate TMEM columns for the accumulator
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t) TMEM_COLS)
+                 "r"((uint32_t) p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -199,22 +201,39 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (p.bn >> 3) << 17) |
                              ((uint32_t) (BM >> 4) << 24);
+      // The tensor core adds each instruction's 8 products into the fp32 accumulator with
+      // truncation, so rounding error grows with the length of one accumulation chain and with
+      // the magnitude of the accumulator.  For 3xTF32 the K range of the main product is
+      // therefore cut into `nmain` chains held in separate TMEM column ranges, and the two small
+      // correction products get a range of their own; the epilogue adds the ranges in fp32 RN.
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(full0 + 8 * stage, phase, 1);
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + stage * stage_bytes;
-        const uint64_t adesc = make_smem_desc(a_addr);
-        const uint64_t bdesc = make_smem_desc(a_addr + A_BYTES);
+      const int nkb = kb_end - kb_begin;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(full0 + 8 * stage, phase, 1);
+          tc_fence_after();
+          int slot, first;
+          if (seg == 0) {
+            slot = (int) (((long long) i * nmain) / nkb);
+            first = (i == (int) (((long long) slot * nkb + nmain - 1) / nmain));
+          } else {
+            slot = nmain;
+            first = (seg == 1 && i == 0);
+          }
+          const uint32_t d_tmem = tmem_base + (uint32_t) (slot * p.bn);
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
-          // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_tf32(tmem_base, adesc + (uint64_t) (k * (UMMA_K_BYTES >> 4)),
-                    bdesc + (uint64_t) (k * (UMMA_K_BYTES >> 4)), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
+            // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_tf32(d_tmem, adesc + (uint64_t) (k * (UMMA_K_BYTES >> 4)),
+                      bdesc + (uint64_t) (k * (UMMA_K_BYTES >> 4)), idesc, (!first || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full);  // accumulator complete
     }
@@ -226,10 +245,17 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     const int m = m0 + q * 32 + lane;
     const bool split = gridDim.z > 1;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+    const int nslots = nmain + (p.nseg > 1 ? 1 : 0);
     for (int c0 = 0; c0 < p.bn; c0 += 32) {
       uint32_t v[32];
       __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
       tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, v);
+      for (int sl = 1; sl < nslots; ++sl) {  // fp32 round-to-nearest sum of the accumulation chains
+        uint32_t w[32];
+        tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (sl * p.bn + c0), w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
       if (m >= p.M) continue;
       const int nb = n0 + c0;
       float* crow = p.c + (int64_t) m * p.ldc;
@@ -272,7 +298,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t) TMEM_COLS)
+                 "r"((uint32_t) p.tmem_cols)
                  : "memory");
   }
 }
@@ -388,7 +414,8 @@ extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, in
   const bool linear = (act == B2_ACT_NONE && mul == nullptr && add == nullptr);
   int best_bn = 32, best_split = 1;
   double best_cost = 1e300;
-  for (int bn = 32; bn <= 256; bn += 32) {
+  const int bn_max = (a_small != nullptr) ? 128 : 256;  // 3xTF32 keeps >= 4 accumulator ranges in TMEM
+  for (int bn = 32; bn <= bn_max; bn += 32) {
     const int64_t tiles_n = b2_ceil_div(N, bn);
     for (int split = 1; split <= 32; split *= 2) {
       if (split > 1 && (!linear || num_kb / split < 8)) break;
@@ -414,6 +441,19 @@ extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, in
   p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.act = act;
   p.beta = beta_accumulate ? 1 : 0;
   p.kb_per_split = (int) b2_ceil_div(num_kb, best_split);
+  if (nseg == 1) {
+    p.nmain = 1;
+  } else {
+    p.nmain = 512 / best_bn - 1;                       // all of TMEM: nmain main chains + 1 correction
+    if (p.nmain > 4) p.nmain = 4;
+    if (p.nmain > p.kb_per_split) p.nmain = p.kb_per_split;
+  }
+  {
+    const int need = (p.nmain + (nseg > 1 ? 1 : 0)) * best_bn;
+    int cols = 32;
+    while (cols < need) cols <<= 1;
+    p.tmem_cols = cols;
+  }
   const int splits = (int) b2_ceil_div(num_kb, p.kb_per_split);
   if (splits > 1 && !p.beta) {
     cudaError_t e = cudaMemset2DAsync(c, (size_t) ldc * 4, 0, (size_t) N * 4, (size_t) M, st);
