@@ -564,3 +564,100 @@ def din_attention(module, target_item, history_sequence, mask=None):
             attention_weight = attention_weight + -1.e9 * (1 - mask.float())
         attention_weight = attention_weight.softmax(dim=-1)
     return (attention_weight.unsqueeze(-1) * history_sequence).sum(dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# Fused sparse front: embedding gather + FM product_sum + LogisticRegression in one launch
+# --------------------------------------------------------------------------------------
+class _Front(torch.autograd.Function):
+    """(emb (B, F*D), logit (B,1)) = b2_front_fwd; backward = b2_front_bwd (one launch each).
+
+    Reference: FeatureEmbedding.forward (feature_embedding.py:73-88) + FactorizationMachine.forward
+    (factorization_machine.py:56-59) = InnerProductInteraction product_sum (inner_product.py:56-62)
+    + LogisticRegression (logistic_regression.py:55-58)."""
+
+    @staticmethod
+    def forward(ctx, plan, lr_plan, idx_list, status, want_fm, bias, n_emb, *tables):
+        emb_tables, lr_tables = tables[:n_emb], tables[n_emb:]
+        batch = idx_list[0].shape[0]
+        dev = emb_tables[0].device
+        arena = torch.empty((batch, plan.width), dtype=torch.float32, device=dev)
+        logit = torch.empty((batch, 1), dtype=torch.float32, device=dev)
+        dim = plan.fields[0].dim
+        sums = torch.empty((batch, dim), dtype=torch.float32, device=dev) if want_fm else None
+        descs = plan.fill(emb_tables, idx_list, arena, batch)
+        lr_descs = None
+        if lr_plan is not None:
+            lr_descs = lr_plan._descs
+            for d, f, idx in zip(lr_descs, lr_plan.fields, idx_list):
+                t = lr_tables[f.table_slot]
+                d.table, d.vocab = t.data_ptr(), t.shape[0]
+                d.idx, d.idx_stride = idx.data_ptr(), (idx.stride(0) if batch > 0 else 0)
+                d.out, d.out_stride = 0, 0
+        _lib.call("b2_front_fwd", descs, lr_descs, len(plan.fields), batch, ctx_code(idx_list),
+                  1 if want_fm else 0, _ptr(bias), _ptr(logit), _ptr(sums), _ptr(status), _stream())
+        ctx.plan, ctx.lr_plan, ctx.idx_list, ctx.want_fm = plan, lr_plan, idx_list, want_fm
+        ctx.emb_tables, ctx.lr_tables, ctx.bias = emb_tables, lr_tables, bias
+        ctx.save_for_backward(arena, sums)
+        return arena, logit
+
+    @staticmethod
+    def backward(ctx, garena, glogit):
+        arena, sums = ctx.saved_tensors
+        plan, lr_plan, idx_list = ctx.plan, ctx.lr_plan, ctx.idx_list
+        batch = idx_list[0].shape[0]
+        garena = torch.zeros_like(arena) if garena is None else _f32c(garena)
+        glogit = (torch.zeros((batch,), dtype=torch.float32, device=arena.device) if glogit is None
+                  else _f32c(glogit).view(-1))
+        egrads = [(_grad_buffer(t, zero=True) if t.requires_grad else None) for t in ctx.emb_tables]
+        lgrads = [(_grad_buffer(t, zero=True) if t.requires_grad else None) for t in ctx.lr_tables]
+        bias = ctx.bias
+        gbias = _grad_buffer(bias, zero=True) if (bias is not None and bias.requires_grad) else None
+        if batch > 0:
+            descs = (b2_field * len(plan.fields))()
+            base = garena.data_ptr()
+            for d, f, idx in zip(descs, plan.fields, idx_list):
+                g = egrads[f.table_slot]
+                d.table = g.data_ptr() if g is not None else 0
+                d.vocab = ctx.emb_tables[f.table_slot].shape[0]
+                d.idx, d.idx_stride = idx.data_ptr(), idx.stride(0)
+                d.out, d.out_stride = base + f.out_offset * 4, plan.width
+                d.dim, d.seq_len, d.pool, d.padding_idx = f.dim, 1, 0, f.padding_idx
+            lr_descs = None
+            if lr_plan is not None:
+                lr_descs = (b2_field * len(lr_plan.fields))()
+                for d, f, idx in zip(lr_descs, lr_plan.fields, idx_list):
+                    g = lgrads[f.table_slot]
+                    d.table = g.data_ptr() if g is not None else 0
+                    d.vocab = ctx.lr_tables[f.table_slot].shape[0]
+                    d.idx, d.idx_stride = idx.data_ptr(), idx.stride(0)
+                    d.dim, d.seq_len, d.pool, d.padding_idx = 1, 1, 0, f.padding_idx
+            _lib.call("b2_front_bwd", descs, lr_descs, len(plan.fields), batch, ctx_code(idx_list),
+                      1 if ctx.want_fm else 0, _ptr(arena), _ptr(garena), _ptr(sums), _ptr(glogit),
+                      _ptr(gbias), _stream())
+        return (None, None, None, None, None, gbias, None) + tuple(egrads) + tuple(lgrads)
+
+
+def front_supported(plan, lr_plan):
+    """The fused front handles categorical-only fields of one common dim (% 4, <= 128)."""
+    dims = set(f.dim for f in plan.fields)
+    if len(dims) != 1 or any(f.seq_len != 1 for f in plan.fields):
+        return False
+    dim = plan.fields[0].dim
+    if dim % 4 != 0 or dim > 128:
+        return False
+    if lr_plan is not None:
+        if [f.name for f in lr_plan.fields] != [f.name for f in plan.fields]:
+            return False
+        if any(f.seq_len != 1 for f in lr_plan.fields):
+            return False
+    return True
+
+
+def front(plan, lr_plan, idx_list, emb_tables, lr_tables, bias, want_fm, status=None):
+    """Returns (emb arena (B, F*D), logit (B,1) = [FM product_sum] + [LR + bias])."""
+    _require_cuda(*emb_tables)
+    _require_cuda(*idx_list)
+    idx_list, _ = _prep_indices(list(idx_list), plan.fields)
+    return _Front.apply(plan, lr_plan, idx_list, status, bool(want_fm), bias, len(emb_tables),
+                        *(tuple(emb_tables) + tuple(lr_tables)))

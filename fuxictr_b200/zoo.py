@@ -18,7 +18,7 @@ same RNG consumption) and nothing else.
 import torch
 from torch import nn
 
-from .layers import (FeatureEmbedding, FeatureEmbeddingDict, MLP_Block, FactorizationMachine,
+from .layers import (fused_front, FeatureEmbedding, FeatureEmbeddingDict, MLP_Block, FactorizationMachine,
                      CrossNetV2, InnerProductInteraction, DIN_Attention, Dice,
                      CompressedInteractionNet, LogisticRegression, not_in_whitelist)
 from .arena import ParamArena, FusedAdam
@@ -197,15 +197,19 @@ class DeepFM(RankModel):
 
     def forward_logits(self, inputs):
         X = self.get_inputs(inputs)
+        fused = fused_front(self.embedding_layer, self.fm.lr_layer, X, want_fm=True)
+        if fused is not None:     # gather + FM + LR in one launch
+            feature_emb, fm_lr = fused
+            return (fm_lr, self.mlp(feature_emb.flatten(start_dim=1)))
         feature_emb = self.embedding_layer(X)
         return (self.fm.fm_layer(feature_emb), self.fm.lr_layer(X),
                 self.mlp(feature_emb.flatten(start_dim=1)))
 
     def forward(self, inputs):
-        X = self.get_inputs(inputs)
-        feature_emb = self.embedding_layer(X)
-        y_pred = self.fm(X, feature_emb)
-        y_pred = y_pred + self.mlp(feature_emb.flatten(start_dim=1))
+        terms = self.forward_logits(inputs)
+        y_pred = terms[0]
+        for t in terms[1:]:
+            y_pred = y_pred + t
         return {"y_pred": self.output_activation(y_pred)}
 
 
@@ -393,8 +397,13 @@ class xDeepFM(RankModel):
 
     def forward_logits(self, inputs):
         X = self.get_inputs(inputs)
-        feature_emb = self.embedding_layer(X)
-        terms = [self.lr_layer(X), self.cin(feature_emb)]
+        fused = fused_front(self.embedding_layer, self.lr_layer, X, want_fm=False)
+        if fused is not None:     # gather + LR in one launch
+            feature_emb, lr_logit = fused
+            terms = [lr_logit, self.cin(feature_emb)]
+        else:
+            feature_emb = self.embedding_layer(X)
+            terms = [self.lr_layer(X), self.cin(feature_emb)]
         if self.dnn is not None:
             terms.append(self.dnn(feature_emb.flatten(start_dim=1)))
         return tuple(terms)

@@ -137,6 +137,30 @@ B2_API int b2_lr_bwd(const b2_field* fields, int nfields, int64_t batch, int idx
               const float* gout, float* gbias, void* stream);
 
 /*
+ * The sparse front of an FM-style model in one launch each way (DeepFM, xDeepFM's LR term):
+ *   emb   = FeatureEmbedding.forward  (feature_embedding.py:73-88)      -> written through emb_fields[i].out
+ *   logit = InnerProductInteraction "product_sum" (inner_product.py:56-62, if want_fm)
+ *         + LogisticRegression (logistic_regression.py:55-58, if lr_fields != NULL) + bias
+ * Requirements: categorical fields only (seq_len 1), one common emb dim with dim % 4 == 0 and
+ * dim <= 128, 16-byte aligned rows; lr_fields[i] shares idx/idx_stride with emb_fields[i] and
+ * points at the (vocab,1) tables.  sum_out (B, dim) receives sum_f e (saved for the backward).
+ */
+B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* lr_fields, int nfields, int64_t batch,
+                        int idx_dtype, int want_fm, const float* bias, float* logit_out, float* sum_out,
+                        int32_t* status, void* stream);
+/*
+ * Backward of b2_front_fwd.  In emb_fields, `table` is the (vocab, dim) gradient buffer (NULL =
+ * no gradient wanted) and `out` addresses the incoming gradient arena gx (same layout as the
+ * forward output); emb_saved is the forward output itself.  Per row:
+ *   g = gx[b,f,:] + glogit[b] * (sums[b,:] - emb_saved[b,f,:])      (second term only if want_fm)
+ * is scatter-added (warp-aggregated) into the gradient table, rows equal to padding_idx skipped;
+ * lr_fields[i].table (vocab,1) += glogit[b]; gbias[0] += sum_b glogit[b].
+ */
+B2_API int b2_front_bwd(const b2_field* emb_fields, const b2_field* lr_fields, int nfields, int64_t batch,
+                        int idx_dtype, int want_fm, const float* emb_saved, const float* gx,
+                        const float* sums, const float* glogit, float* gbias, void* stream);
+
+/*
  * InnerProductInteraction (layers/interactions/inner_product.py:55-70).
  * emb is (B, F, D) f32 contiguous.
  *   mode 0 "product_sum":    out (B,1)   = sum_d 0.5*((sum_f e)^2 - sum_f e^2)   (:56-62)
