@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nbatches", type=int, default=8, help="distinct synthetic batches rotated through")
+    ap.add_argument("--steps-only", action="store_true", help="skip the per-kernel / stress / CPU legs (profiling)")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the dense GEMMs: fp32 FFMA, 3xTF32 (fp32-class) or 1xTF32 on tcgen05")
     return ap.parse_args()
@@ -408,6 +409,10 @@ def run_b200_arm(args):
     samples = args.batch * world * args.steps
     value = samples / (ms_total / 1e3)
     e2e_value = samples / (ms_e2e / 1e3)
+    if args.steps_only:
+        print(json.dumps({"value": value, "ms_per_step": ms_total / args.steps, "e2e": e2e_value,
+                          "gpu_launches_per_step": launches, "precision": args.precision}))
+        return
     kernels = kernel_rooflines(model, fm, dev_batches[0], peaks, args)
     dom = max(("adam_step", "embed_gather_fwd", "grad_sumsq"), key=lambda k: kernels[k]["ms"])
     step_ms = ms_total / args.steps
