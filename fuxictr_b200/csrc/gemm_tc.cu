@@ -41,6 +41,7 @@ struct Params {
   int M, N, K, bn, nseg, act, beta, kb_per_split;
   int nmain;      // TMEM accumulators for the main (big x big) product: its K range is cut in nmain chunks
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
+  long long* dbg; // diagnostic: 8 globaltimer stamps of CTA (0,0,0), or NULL
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -133,9 +134,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void stamp(const Params& p, int slot) {
+  if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.dbg[slot] = (long long) t;
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) stamp(p, 0);
   // 128B-swizzled tiles need 1024-byte aligned bases: align by hand (1 KB of slack is requested).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
   const uint32_t b_bytes = (uint32_t) p.bn * 128u;
@@ -177,6 +187,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(p, 1);
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -191,6 +202,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
           mbar_expect_tx(full, stage_bytes);
           tma_load_2d(a_dst, &p.map_a[seg], full, kb * BK, m0);
           tma_load_2d(a_dst + A_BYTES, &p.map_b[seg], full, kb * BK, n0);
+          if (seg == 0 && kb == kb_begin) stamp(p, 2);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -213,6 +225,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(full0 + 8 * stage, phase, 1);
           tc_fence_after();
+          if (seg == 0 && i == 0) stamp(p, 3);
           int slot, first;
           if (seg == 0) {
             slot = (int) (((long long) i * nmain) / nkb);
@@ -236,12 +249,14 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         }
       }
       umma_commit(tmem_full);  // accumulator complete
+      stamp(p, 4);
     }
   } else {
     // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----------------
     const int q = warp & 3;
     mbar_wait(tmem_full, 0, 2);
     tc_fence_after();
+    if (warp == 2 && lane == 0) stamp(p, 5);
     const int m = m0 + q * 32 + lane;
     const bool split = gridDim.z > 1;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
@@ -293,8 +308,10 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       }
     }
   }
+  if (warp == 2 && lane == 0) stamp(p, 6);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(p, 7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -384,6 +401,15 @@ static int encode_kmajor(CUtensorMap* map, const float* base, int64_t rows, int6
   return B2_OK;
 }
 
+static long long* g_tc_debug = nullptr;
+// Diagnostic hook: subsequent b2_gemm_tc launches write 8 globaltimer stamps (ns) of CTA (0,0,0)
+// into buf: 0 entry, 1 setup done, 2 first TMA issued, 3 first tile landed, 4 last MMA committed,
+// 5 accumulator visible to the epilogue, 6 epilogue stored, 7 all warps done.  NULL disables.
+extern "C" B2_API int b2_gemm_tc_set_debug(long long* buf) {
+  g_tc_debug = buf;
+  return B2_OK;
+}
+
 static bool tma_ok(const float* p, int64_t ld) {
   return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0);
 }
@@ -441,6 +467,7 @@ extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, in
   p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.act = act;
   p.beta = beta_accumulate ? 1 : 0;
   p.kb_per_split = (int) b2_ceil_div(num_kb, best_split);
+  p.dbg = g_tc_debug;
   if (nseg == 1) {
     p.nmain = 1;
   } else {

@@ -220,6 +220,9 @@ B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, int64_t ldb, 
                       int64_t M, int64_t N, int64_t K, const float* bias, int act, const float* mul,
                       const float* add, int beta_accumulate, const float* a_small,
                       const float* b_small, void* stream);
+/* Diagnostic: later b2_gemm_tc launches record 8 %globaltimer stamps (ns) of CTA (0,0,0) in buf
+ * (device int64[8]); NULL disables. */
+B2_API int b2_gemm_tc_set_debug(long long* buf);
 /* small[i] = x[i] - (x[i] with the 13 low mantissa bits cleared). */
 B2_API int b2_split_tf32(const float* x, float* small, int64_t n, void* stream);
 /* out (cols, rows; ld_out) = in (rows, cols; ld_in)^T; if out_small != NULL it also receives the
