@@ -448,16 +448,17 @@ def test_criteo_shape_deepfm_step_vs_oracle():
     loss.backward()
 
     def qerr(a, truth):
-        """max-norm relative error over all but the worst 1e-4 of the elements, and over all"""
+        """max-norm relative error over all but the worst 1% of the elements, and over all"""
         d = (a.detach().double().cpu() - truth.double()).abs().flatten()
         scale = max(float(truth.abs().max()), 1e-30)
-        k = max(1, int(d.numel() * (1 - 1e-4)))
+        k = max(1, int(d.numel() * 0.99))
         return float(d.kthvalue(k).values) / scale, float(d.max()) / scale
 
     def bar(ours, ref32, truth, what):
         # A ReLU whose pre-activation is within rounding of zero may fall on either side of it in
-        # two correct fp32 programs; such a flip moves the gradient rows of ONE sample (<= 1e-4 of
-        # any tensor here) by up to ~1e-3.  Those elements are bounded separately.
+        # two correct fp32 programs; a flip at (sample b, unit h) perturbs sample b's embedding rows
+        # and the whole row h of that layer's weight gradient (1/300 of the tensor) by up to ~1e-3.
+        # Those elements (< 1 % of any tensor for a handful of flips) are bounded separately.
         (q_ours, m_ours), (q_ref, _) = qerr(ours, truth), qerr(ref32, truth)
         assert q_ours <= max(RTOL, 3 * q_ref), (what, q_ours, q_ref)
         assert m_ours <= 1e-2, (what, m_ours)
