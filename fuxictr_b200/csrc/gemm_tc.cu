@@ -147,7 +147,8 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   if (threadIdx.x == 0) stamp(p, 0);
   // 128B-swizzled tiles need 1024-byte aligned bases: align by hand (1 KB of slack is requested).
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+  // (pointer arithmetic on smem_raw keeps the shared address space visible to the compiler)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t b_bytes = (uint32_t) p.bn * 128u;
   const uint32_t stage_bytes = A_BYTES + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
@@ -280,22 +281,44 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       const int n = n0 + c0 + lane;  // this lane's output column for the whole chunk
       const bool n_ok = n < p.N;
       const float bv = (n_ok && p.bias != nullptr && blockIdx.z == 0) ? __ldg(p.bias + n) : 0.f;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int m = m0 + q * 32 + r;
-        if (m >= p.M) break;  // warp-uniform
-        if (!n_ok) continue;
-        float x = patch[r * 33 + lane] + bv;
-        float* cp = p.c + (int64_t) m * p.ldc + n;
+      float t[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t[r] = patch[r * 33 + lane] + bv;  // 32 independent LDS in flight
+      const int mrow0 = m0 + q * 32;
+      if (n_ok) {
+        float* cp = p.c + (int64_t) mrow0 * p.ldc + n;
         if (split) {
-          b2_red_add(cp, x);
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if (mrow0 + r < p.M) b2_red_add(cp + (int64_t) r * p.ldc, t[r]);
         } else {
-          if (p.mul != nullptr) x *= __ldg(p.mul + (int64_t) m * p.ldc + n);
-          if (p.add != nullptr) x += __ldg(p.add + (int64_t) m * p.ldc + n);
-          if (p.act == B2_ACT_RELU) x = fmaxf(x, 0.f);
-          else if (p.act == B2_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
-          if (p.beta) x += *cp;
-          *cp = x;
+          if (p.mul != nullptr) {
+            const float* mp = p.mul + (int64_t) mrow0 * p.ldc + n;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (mrow0 + r < p.M) t[r] *= __ldg(mp + (int64_t) r * p.ldc);
+          }
+          if (p.add != nullptr) {
+            const float* ap = p.add + (int64_t) mrow0 * p.ldc + n;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (mrow0 + r < p.M) t[r] += __ldg(ap + (int64_t) r * p.ldc);
+          }
+          if (p.act == B2_ACT_RELU) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) t[r] = fmaxf(t[r], 0.f);
+          } else if (p.act == B2_ACT_SIGMOID) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) t[r] = 1.f / (1.f + expf(-t[r]));
+          }
+          if (p.beta) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (mrow0 + r < p.M) t[r] += cp[(int64_t) r * p.ldc];
+          }
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if (mrow0 + r < p.M) cp[(int64_t) r * p.ldc] = t[r];   // 128 contiguous bytes per row
         }
       }
     }
