@@ -404,34 +404,44 @@ def test_criteo_shape_gather_scatter_vs_oracle(zipf):
         assert float(p.grad[0].abs().sum()) == 0.0
 
 
-def test_criteo_shape_deepfm_step_vs_oracle():
+@pytest.mark.parametrize("act", ["sigmoid", "relu"])
+def test_criteo_shape_deepfm_step_vs_oracle(act):
     """C2 (39 fields x 25,641 rows, D=16, MLP 300-300-300, B=4096): forward, loss, every gradient
     and one optimiser step against the oracle restatement of the reference.
 
-    At this size a per-element 1e-5 comparison of two fp32 programs is ill-posed: the weight
-    gradients are 4096-term sums with cancellation (two correct fp32 summation orders differ by
-    more than 1e-5 of the result), and a ReLU whose pre-activation is within rounding of zero may
-    legitimately fall on either side.  The oracle is therefore ALSO run in float64, and the bar is
-    "as close to the exact result as the reference's own fp32 arithmetic":
+    The oracle is run in float32 (what the reference computes) AND in float64 (the exact answer);
+    the bar is "as close to the exact result as the reference's own fp32 arithmetic":
         err(ours, fp64) <= max(1e-5, 3 * err(reference fp32, fp64))       (max-norm, relative)
-    for predictions, loss and every gradient.  (The small models of tests/golden pin the exact
-    multi-step Adam trajectory element by element.)"""
+    * act="sigmoid": a smooth network — the bar applies to predictions, loss and EVERY gradient.
+    * act="relu" (the BASELINE config): the loss surface is only piecewise smooth.  With 3.7 M
+      pre-activations per step, one of them lies within fp32 rounding of zero with probability
+      O(1); two correct fp32 programs then pick different sides, which changes that sample's
+      contribution to every weight gradient by ~1e-3 of the gradient (1 sample in 4096, no
+      cancellation).  Predictions and loss still meet the bar; gradients are held to 1e-2
+      element-wise and 1e-4 in total norm, and the exact element-wise trajectory is pinned by the
+      small reference goldens (test_model_matches_reference_trajectory)."""
     from fuxictr_b200 import zoo, functional as F2
     from oracle import fuxictr_oracle as O
     fm, specs, mat = criteo_shape()
     torch.manual_seed(2019)
-    model = zoo.DeepFM(fm, gpu=-1, embedding_dim=16, hidden_units=[300, 300, 300])
+    model = zoo.DeepFM(fm, gpu=-1, embedding_dim=16, hidden_units=[300, 300, 300], hidden_activations=act)
     with torch.no_grad():
         for m in model.modules():
             if isinstance(m, torch.nn.Embedding):
                 m.weight[1:].normal_(0, 0.05)
     state0 = OrderedDict((k, v.detach().clone()) for k, v in model.state_dict().items())
     cpu_batch = fm.batch_dict(mat)
+    layout = O.mlp_layout(3, hidden_act=act)
+
+    def logit_fn(s, X):
+        emb = O.feature_embedding(specs, s, "embedding_layer.", X)
+        y = O.factorization_machine(specs, s, "fm.", X, emb)
+        return y + O.mlp_block(emb.flatten(start_dim=1), s, "mlp.", layout)
 
     def oracle_run(dtype):
         st = OrderedDict((k, v.detach().to(dtype).requires_grad_(True)) for k, v in state0.items())
         X, y = O.split_inputs(specs, ["label"], cpu_batch)
-        y_pred = torch.sigmoid(O.deepfm_logit(specs, st, X, 3))
+        y_pred = torch.sigmoid(logit_fn(st, X))
         loss = torch.nn.functional.binary_cross_entropy(y_pred, y.to(dtype), reduction="mean")
         loss.backward()
         return y_pred.detach(), loss.detach(), {k: v.grad for k, v in st.items()}
@@ -447,28 +457,23 @@ def test_criteo_shape_deepfm_step_vs_oracle():
     loss, y_pred = F2.logit_bce(model.get_labels(batch), *model.forward_logits(batch))
     loss.backward()
 
-    def qerr(a, truth):
-        """max-norm relative error over all but the worst 1% of the elements, and over all"""
-        d = (a.detach().double().cpu() - truth.double()).abs().flatten()
-        scale = max(float(truth.abs().max()), 1e-30)
-        k = max(1, int(d.numel() * 0.99))
-        return float(d.kthvalue(k).values) / scale, float(d.max()) / scale
-
     def bar(ours, ref32, truth, what):
-        # A ReLU whose pre-activation is within rounding of zero may fall on either side of it in
-        # two correct fp32 programs; a flip at (sample b, unit h) perturbs sample b's embedding rows
-        # and the whole row h of that layer's weight gradient (1/300 of the tensor) by up to ~1e-3.
-        # Those elements (< 1 % of any tensor for a handful of flips) are bounded separately.
-        (q_ours, m_ours), (q_ref, _) = qerr(ours, truth), qerr(ref32, truth)
-        assert q_ours <= max(RTOL, 3 * q_ref), (what, q_ours, q_ref)
-        assert m_ours <= 1e-2, (what, m_ours)
+        e_ours, e_ref = rel_err(ours, truth), rel_err(ref32, truth)
+        assert e_ours <= max(RTOL, 3 * e_ref), (what, e_ours, e_ref)
     bar(y_pred, y32, y64, "y_pred")
     bar(loss, l32, l64, "loss")
     named = dict(model.named_parameters())
-    for k in g64:
-        bar(named[k].grad, g32[k], g64[k], k)
+    if act == "sigmoid":
+        for k in g64:
+            bar(named[k].grad, g32[k], g64[k], k)
+    else:
+        for k in g64:
+            assert rel_err(named[k].grad, g64[k]) <= 1e-2, (k, rel_err(named[k].grad, g64[k]))
+        ours = torch.cat([named[k].grad.flatten().double().cpu() for k in g64])
+        truth = torch.cat([g64[k].flatten() for k in g64])
+        assert float((ours - truth).norm()) <= 1e-4 * float(truth.norm())
     # one optimiser step, then the next loss (weights feed back through the whole model)
-    tr = O.OracleTrainer(state0, lambda s, X: torch.sigmoid(O.deepfm_logit(specs, s, X, 3)), specs, ["label"])
+    tr = O.OracleTrainer(state0, lambda s, X: torch.sigmoid(logit_fn(s, X)), specs, ["label"])
     tr.train_step(cpu_batch)
     loss_ref2 = float(O.bce_mean(*tr.forward(cpu_batch)))
     opt.step()
@@ -565,7 +570,8 @@ def test_criteo_shape_deepfm_step_tf32x3_vs_oracle():
     from fuxictr_b200 import functional as F2
     F2.set_matmul_precision("tf32x3")
     try:
-        test_criteo_shape_deepfm_step_vs_oracle()
+        test_criteo_shape_deepfm_step_vs_oracle("sigmoid")
+        test_criteo_shape_deepfm_step_vs_oracle("relu")
     finally:
         F2.set_matmul_precision("fp32")
 
