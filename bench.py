@@ -416,8 +416,16 @@ def run_b200_arm(args):
     kernels = kernel_rooflines(model, fm, dev_batches[0], peaks, args)
     dom = max(("adam_step", "embed_gather_fwd", "grad_sumsq"), key=lambda k: kernels[k]["ms"])
     step_ms = ms_total / args.steps
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_step_kernels_traffic.json")
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
+        with open(tpath) as fd:
+            cap = json.load(fd).get({"adam_step": "adam_kernel", "grad_sumsq": "sumsq_kernel"}.get(dom, dom))
+        if cap:
+            traffic = (cap["dram_read_MB"] + cap["dram_write_MB"]) * 1e6
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": kernels[dom]["frac_of_measured_hbm"], "traffic": None,
+                "unit": "GB/s", "frac": kernels[dom]["frac_of_measured_hbm"], "traffic": traffic,
+                "algorithmic_bytes": kernels[dom]["algorithmic_bytes"],
                 "peak_source": peaks["source"], "share_of_step": kernels[dom]["ms"] / step_ms}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
