@@ -338,6 +338,8 @@ def run_b200_arm(args):
         counter["n"] += 1
         return orig_call(name, *a)
 
+    if os.environ.get("B2_BENCH_VERBOSE"):
+        sys.stderr.write("[bench r%d] model built\n" % rank); sys.stderr.flush()
     static_in.copy_(dev_batches[0])
     _lib.call = counting_call
     step_eager()
@@ -358,6 +360,9 @@ def run_b200_arm(args):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             loss_static = step_eager()
+
+    if os.environ.get("B2_BENCH_VERBOSE"):
+        sys.stderr.write("[bench r%d] graph captured\n" % rank); sys.stderr.flush()
 
     def run_step(i, e2e):
         if e2e:
@@ -402,8 +407,14 @@ def run_b200_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss_host.item())
 
+    def note(msg):
+        if os.environ.get("B2_BENCH_VERBOSE"):
+            sys.stderr.write("[bench r%d] %s\n" % (rank, msg))
+            sys.stderr.flush()
+    note("timed regions done")
     if rank != 0:
         if world > 1:
+            dist.barrier()          # rank 0 still has single-rank measurements to take
             dist.destroy_process_group()
         return
     samples = args.batch * world * args.steps
@@ -411,7 +422,11 @@ def run_b200_arm(args):
     e2e_value = samples / (ms_e2e / 1e3)
     if args.steps_only:
         print(json.dumps({"value": value, "ms_per_step": ms_total / args.steps, "e2e": e2e_value,
-                          "gpu_launches_per_step": launches, "precision": args.precision}))
+                          "gpu_launches_per_step": launches, "precision": args.precision, "n_gpus": world}))
+        sys.stdout.flush()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     kernels = kernel_rooflines(model, fm, dev_batches[0], peaks, args)
     dom = max(("adam_step", "embed_gather_fwd", "grad_sumsq"), key=lambda k: kernels[k]["ms"])
@@ -451,7 +466,9 @@ def run_b200_arm(args):
                                               "setting; oracle port of the reference's ATen path)"
                                               % (r["steps"], args.batch, args.cpu_seconds, r["cores"], r["host_cpus"])}
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
