@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nbatches", type=int, default=8, help="distinct synthetic batches rotated through")
+    ap.add_argument("--dp-only", action="store_true",
+                    help="N>1: replicate the tables and all-reduce the whole gradient arena instead of row-sharding")
     ap.add_argument("--steps-only", action="store_true", help="skip the per-kernel / stress / CPU legs (profiling)")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the dense GEMMs: fp32 FFMA, 3xTF32 (fp32-class) or 1xTF32 on tcgen05")
@@ -48,7 +50,9 @@ def workload_config(args, n_gpus):
     return {"workload": "DeepFM Criteo-shape: %d fields x %d rows, emb_dim %d, MLP %s, fp32 Adam"
                         % (NF, VOCAB, DIM, HIDDEN),
             "global_batch": args.batch * n_gpus, "per_gpu_batch": args.batch,
-            "parallelism": "dp%d" % n_gpus if n_gpus > 1 else "single",
+            "parallelism": ("single" if n_gpus == 1 else
+                            ("dp%d (replicated tables, all-reduce of the gradient arena)" % n_gpus if args.dp_only else
+                             "tables row-sharded over %d GPUs (P2P push/pull over NVLink) + dense dp all-reduce" % n_gpus)),
             "cache": "working set (4 fp32 arenas x 68 MB: params, grads, Adam m/v) exceeds the 126 MB L2; "
                      "%d distinct index batches are rotated" % args.nbatches}
 
@@ -219,7 +223,7 @@ def time_kernel(fn, reps, stream_sync=None):
     return e0.elapsed_time(e1) / reps
 
 
-def kernel_rooflines(model, fm, dev_batch, peaks, args):
+def kernel_rooflines(model, fm, dev_batch, peaks, args, with_gather=True):
     """Per-kernel achieved bandwidth, measured live with CUDA events: the fused gather (north-star
     kernel) and the dense clip+Adam pass (largest share of the step)."""
     import ctypes
@@ -231,12 +235,13 @@ def kernel_rooflines(model, fm, dev_batch, peaks, args):
     B = dev_batch.shape[0]
     # fused multi-field gather, algorithmic bytes: F*8 (ids) + F*D*4 (rows) + F*D*4 (out)
     fed = model.embedding_layer.embedding_layer
-    with torch.no_grad():
-        ms = time_kernel(lambda: fed.forward_tensor(X), 50, None)
-    gbytes = B * (NF * 8 + 2 * NF * DIM * 4)
-    out["embed_gather_fwd"] = {"ms": ms, "algorithmic_bytes": gbytes, "GBps": gbytes / ms / 1e6,
-                               "frac_of_measured_hbm": gbytes / ms / 1e6 / hbm,
-                               "note": "B=%d: tables (64 MB) are L2-resident and the launch is latency-bound" % B}
+    if with_gather:
+        with torch.no_grad():
+            ms = time_kernel(lambda: fed.forward_tensor(X), 50, None)
+        gbytes = B * (NF * 8 + 2 * NF * DIM * 4)
+        out["embed_gather_fwd"] = {"ms": ms, "algorithmic_bytes": gbytes, "GBps": gbytes / ms / 1e6,
+                                   "frac_of_measured_hbm": gbytes / ms / 1e6 / hbm,
+                                   "note": "B=%d: tables (64 MB) are L2-resident and the launch is latency-bound" % B}
     # dense optimizer pass over the arena: 4 reads (p,g,m,v) + 4 writes (p,m,v, g=0) of fp32
     opt = model._fused_optimizer
     a = model._arena
@@ -317,8 +322,12 @@ def run_b200_arm(args):
     fm = FeatureMap.from_specs(make_specs(), embedding_dim=DIM)
     torch.manual_seed(2019)
     model = zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
+    sharded = world > 1 and not args.dp_only
+    if sharded:
+        from fuxictr_b200.sharded import SymmPeerGroup
+        model.enable_sharding(SymmPeerGroup(), args.batch, NF + 1, torch.float64)
     opt = model.use_fused_optimizer()
-    if world > 1:
+    if world > 1 and not sharded:
         opt.grad_allreduce = True
     model.train()
     host_batches = [m.pin_memory() for m in make_batches(args.nbatches, args.batch, seed=1000 + rank)]
@@ -413,10 +422,10 @@ def run_b200_arm(args):
             sys.stderr.flush()
     note("timed regions done")
     if rank != 0:
-        if world > 1:
-            dist.barrier()          # rank 0 still has single-rank measurements to take
-            dist.destroy_process_group()
-        return
+        # Last collective done.  Leave without NCCL teardown: rank 0 still captures CUDA graphs for
+        # its single-rank kernel measurements, and a concurrent communicator finalize hung here.
+        sys.stdout.flush()
+        os._exit(0)
     samples = args.batch * world * args.steps
     value = samples / (ms_total / 1e3)
     e2e_value = samples / (ms_e2e / 1e3)
@@ -425,11 +434,11 @@ def run_b200_arm(args):
                           "gpu_launches_per_step": launches, "precision": args.precision, "n_gpus": world}))
         sys.stdout.flush()
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            os._exit(0)
         return
-    kernels = kernel_rooflines(model, fm, dev_batches[0], peaks, args)
-    dom = max(("adam_step", "embed_gather_fwd", "grad_sumsq"), key=lambda k: kernels[k]["ms"])
+    kernels = kernel_rooflines(model, fm, dev_batches[0], peaks, args, with_gather=not sharded)
+    dom = max([k for k in ("adam_step", "embed_gather_fwd", "grad_sumsq") if k in kernels],
+              key=lambda k: kernels[k]["ms"])
     step_ms = ms_total / args.steps
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_step_kernels_traffic.json")
@@ -468,8 +477,7 @@ def run_b200_arm(args):
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -28,13 +28,16 @@ class ParamArena(object):
 
     ALIGN = 4  # floats (16 bytes): every slice is float4-addressable
 
-    def __init__(self, module):
-        params = [p for p in module.parameters() if p.requires_grad]
+    def __init__(self, module, first=()):
+        """`first`: parameters to place at the front of the arena (e.g. the row-sharded tables of a
+        multi-GPU run, so that the replicated dense parameters form one contiguous tail slice)."""
+        params = list(first) + [p for p in module.parameters() if p.requires_grad]
         seen, uniq = set(), []
         for p in params:
             if id(p) not in seen:
                 seen.add(id(p))
                 uniq.append(p)
+        n_first = len(set(id(p) for p in first))
         if not uniq:
             raise ValueError("module has no trainable parameters")
         dev = uniq[0].device
@@ -45,9 +48,14 @@ class ParamArena(object):
                 raise RuntimeError("ParamArena supports float32 parameters on one device")
         off = 0
         slots = []
-        for p in uniq:
+        self.tail_offset = 0           # first element of the non-`first` (dense, replicated) slice
+        for i, p in enumerate(uniq):
+            if i == n_first:
+                self.tail_offset = off
             slots.append((p, off))
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if n_first >= len(uniq):
+            self.tail_offset = off
         self.numel = off
         self.P = torch.zeros(off, dtype=torch.float32, device=dev)
         self.G = torch.zeros(off, dtype=torch.float32, device=dev)
@@ -97,6 +105,7 @@ class FusedAdam(object):
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.zero_grad_in_step = zero_grad_in_step
         self.grad_allreduce = False  # data-parallel replicas: average G across ranks before the step
+        self.sharded = False         # row-sharded tables in G[:tail_offset], replicated dense params after
 
     def zero_grad(self, set_to_none=True):
         self.arena.begin_step(grads_zeroed=self.zero_grad_in_step and self._stepped)
@@ -120,7 +129,25 @@ class FusedAdam(object):
             dist.all_reduce(a.G, op=dist.ReduceOp.SUM)   # one NCCL collective over the whole arena
             a.G.mul_(1.0 / dist.get_world_size())          # mean over the global batch (rank_model.py:130)
         sumsq_ptr = ctypes.c_void_p(0)
-        if self.max_norm is not None:
+        if self.sharded:
+            import torch.distributed as dist
+            world = dist.get_world_size()
+            dense = a.G[a.tail_offset:]
+            if dense.numel() > 0:
+                dist.all_reduce(dense, op=dist.ReduceOp.SUM)     # dense grads: mean over the global batch
+                dense.mul_(1.0 / world)
+            if self.max_norm is not None:
+                # global norm^2 = sum over ranks of the shard parts + the (replicated) dense part once
+                self.sumsq.zero_()
+                if a.tail_offset > 0:
+                    _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr()), a.tail_offset,
+                              ctypes.c_void_p(self.sumsq.data_ptr()), st)
+                dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM)
+                if dense.numel() > 0:
+                    _lib.call("b2_sumsq", ctypes.c_void_p(dense.data_ptr()), dense.numel(),
+                              ctypes.c_void_p(self.sumsq.data_ptr()), st)
+                sumsq_ptr = ctypes.c_void_p(self.sumsq.data_ptr())
+        elif self.max_norm is not None:
             self.sumsq.zero_()
             _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr()), a.numel,
                       ctypes.c_void_p(self.sumsq.data_ptr()), st)

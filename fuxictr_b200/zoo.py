@@ -137,13 +137,58 @@ class RankModel(nn.Module):
         return loss
 
     # -- B200 extension: flat arenas + 2-kernel clip/Adam -------------------------------------
+    def enable_sharding(self, group, batch_local, matrix_width, idx_dtype=torch.float64, want_fm=True):
+        """Row-shard every embedding / LR table over `group` (fuxictr_b200.sharded) and route the
+        sparse front through the peer-memory push/pull kernels.  Call after model_to_device() and
+        before use_fused_optimizer().  Models: the FM-style fronts (DeepFM, xDeepFM)."""
+        from . import sharded as SH
+        fed = self.embedding_layer.embedding_layer
+        lr_layer = self.fm.lr_layer if hasattr(self, "fm") else getattr(self, "lr_layer", None)
+        names = [f for f in self.feature_map.features.keys() if f in fed.embedding_layers]
+        if not all(fed._is_fusable(f) and self.feature_map.features[f]["type"] == "categorical" for f in names):
+            raise NotImplementedError("sharded front needs categorical features only")
+        lfed = lr_layer.embedding_layer.embedding_layer if lr_layer is not None else None
+        vocabs, cols, pads, etabs, ltabs = [], [], [], [], []
+        with torch.no_grad():
+            for f in names:
+                emb = fed.embedding_layers[f]
+                vocabs.append(emb.num_embeddings)
+                cols.append(self.feature_map.get_column_index(f))
+                pads.append(emb.padding_idx)
+                if not getattr(emb, "_b2_sharded", False):
+                    emb.weight.data = SH.shard_rows(emb.weight.data, group.rank, group.world)
+                    emb._b2_sharded = True
+                etabs.append(emb.weight)
+                if lfed is not None:
+                    lemb = lfed.embedding_layers[f]
+                    if not getattr(lemb, "_b2_sharded", False):
+                        lemb.weight.data = SH.shard_rows(lemb.weight.data, group.rank, group.world)
+                        lemb._b2_sharded = True
+                    ltabs.append(lemb.weight)
+        dim = fed.embedding_layers[names[0]].embedding_dim
+        self._sharded_front = SH.ShardedFront(group, names, etabs, ltabs or None, vocabs, cols, pads, dim,
+                                              batch_local, matrix_width, idx_dtype,
+                                              bias=(lr_layer.bias if lr_layer is not None else None),
+                                              want_fm=want_fm)
+        self._sharded_params = etabs + ltabs
+        return self._sharded_front
+
+    def _batch_matrix(self, inputs):
+        """The (B, W) matrix the collator sliced `inputs` from (the views' common base)."""
+        first = next(iter(inputs.values()))
+        base = first._base if first._base is not None else None
+        if base is None or base.dim() != 2:
+            raise RuntimeError("sharded front needs the batch dict to be column views of one matrix")
+        return base.to(self.device)
+
     def use_fused_optimizer(self):
         """Re-home parameters into one HBM arena and replace clip_grad_norm_ + torch Adam by
         the two-kernel FusedAdam (same arithmetic; see arena.py).  Call after model_to_device()."""
         if self._optimizer_name != "Adam":
             raise NotImplementedError("the fused optimizer implements Adam only")
-        self._arena = ParamArena(self)
+        self._arena = ParamArena(self, first=getattr(self, "_sharded_params", ()))
         self._fused_optimizer = FusedAdam(self._arena, lr=self._lr, max_norm=self._max_gradient_norm)
+        self._fused_optimizer.sharded = bool(getattr(self, "_sharded_params", None))
         self.optimizer = None
         return self._fused_optimizer
 
@@ -196,6 +241,10 @@ class DeepFM(RankModel):
         self.model_to_device()
 
     def forward_logits(self, inputs):
+        if getattr(self, "_sharded_front", None) is not None:   # row-sharded tables, P2P push/pull
+            from .sharded import sharded_front
+            feature_emb, fm_lr = sharded_front(self._sharded_front, self._batch_matrix(inputs))
+            return (fm_lr, self.mlp(feature_emb.flatten(start_dim=1)))
         X = self.get_inputs(inputs)
         fused = fused_front(self.embedding_layer, self.fm.lr_layer, X, want_fm=True)
         if fused is not None:     # gather + FM + LR in one launch

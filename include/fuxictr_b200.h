@@ -161,6 +161,36 @@ B2_API int b2_front_bwd(const b2_field* emb_fields, const b2_field* lr_fields, i
                         const float* sums, const float* glogit, float* gbias, void* stream);
 
 /*
+ * Row-sharded tables across the GPUs of one NVSwitch box: row r of every table
+ * lives on rank r % world at local row r / world.  The lookup and its exchange are one kernel
+ * over NVLink peer memory.  In emb_fields/lr_fields: `table` = this rank's shard (or its gradient
+ * shard in b2_shard_pull), `vocab` = GLOBAL vocabulary, `idx_stride` = COLUMN of the field in the
+ * batch matrix, `padding_idx` = global padding row; `idx`/`out` are unused.
+ *   peer_ids[p]   (B_local, ids_stride) batch matrix of rank p       (peer-mapped, read)
+ *   peer_emb[p]   (B_local, F*D) fp32 embedding output of rank p     (peer-mapped, written)
+ *   peer_lrw[p]   (B_local, F)   fp32 LR weights of rank p's samples (peer-mapped, written)
+ * b2_shard_push gathers the rows THIS rank owns for every rank's samples and stores them into the
+ * requester's buffers; b2_shard_pull reads the requester's gradient rows peer_gemb[p] (B_local,
+ * F*D) / peer_glogit[p] (B_local) for the rows this rank owns and scatter-adds `scale *` them
+ * into the local gradient shards.  Cross-rank ordering is the caller's barrier.  world <= 16.
+ */
+B2_API int b2_shard_push(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
+                         int64_t batch_local, int world, int rank, const void* const* peer_ids,
+                         int idx_dtype, int64_t ids_stride, float* const* peer_emb,
+                         float* const* peer_lrw, int32_t* status, void* stream);
+B2_API int b2_shard_pull(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
+                         int64_t batch_local, int world, int rank, const void* const* peer_ids,
+                         int idx_dtype, int64_t ids_stride, const float* const* peer_gemb,
+                         const float* const* peer_glogit, float scale, void* stream);
+/* After the push: logit[b] = [FM product_sum of emb[b]] (if want_fm) + sum_f lrw[b,f] + bias;
+ * sums[b,:] = sum_f emb[b,f,:] (saved for the backward). */
+B2_API int b2_front_reduce(const float* emb, const float* lrw, const float* bias, int64_t batch,
+                           int nfields, int dim, int want_fm, float* logit, float* sums, void* stream);
+/* Before the pull: gemb[b,f,:] = gx[b,f,:] + glogit[b] * (sums[b,:] - emb[b,f,:]) (2nd term if want_fm). */
+B2_API int b2_front_gprep(const float* gx, const float* emb, const float* sums, const float* glogit,
+                          int64_t batch, int nfields, int dim, int want_fm, float* gemb, void* stream);
+
+/*
  * InnerProductInteraction (layers/interactions/inner_product.py:55-70).
  * emb is (B, F, D) f32 contiguous.
  *   mode 0 "product_sum":    out (B,1)   = sum_d 0.5*((sum_f e)^2 - sum_f e^2)   (:56-62)
