@@ -230,7 +230,9 @@ class FeatureEmbeddingDict(nn.Module):
             return False
         if feature in self.feature_encoders:
             enc = self.feature_encoders[feature]
-            if not (spec["type"] == "sequence" and type(enc) in (MaskedSumPooling, MaskedAveragePooling)):
+            # by name: the reference's own pooling classes qualify too (fuxictr_b200.patch)
+            if not (spec["type"] == "sequence" and
+                    type(enc).__name__ in ("MaskedSumPooling", "MaskedAveragePooling")):
                 return False
         return True
 
@@ -250,7 +252,8 @@ class FeatureEmbeddingDict(nn.Module):
             seq_len = spec["max_len"] if spec["type"] == "sequence" else 1
             pool = B2_POOL_NONE
             if feature in self.feature_encoders:
-                pool = B2_POOL_SUM if type(self.feature_encoders[feature]) == MaskedSumPooling else B2_POOL_MEAN
+                pool = B2_POOL_SUM if type(self.feature_encoders[feature]).__name__ == "MaskedSumPooling" \
+                    else B2_POOL_MEAN
             fields.append(F2.GatherField(feature, slot_of[id(emb)], emb.embedding_dim, seq_len, pool,
                                          emb.padding_idx))
         plan = (F2.GatherPlan(fields), tables)

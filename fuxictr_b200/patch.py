@@ -1,0 +1,104 @@
+"""enable(): route the UNMODIFIED reference's hot-path layers through the B200 kernels.
+
+On a machine that has reczoo/FuxiCTR installed, ``import fuxictr_b200.patch as p; p.enable()``
+(before or after building a model) swaps the ``forward`` of the reference's own layer classes —
+class identity, parameters, ``state_dict`` keys, initialisation order and the
+``type(module) == FeatureEmbeddingDict`` test of the regulariser (rank_model.py:107) are untouched,
+so any ``model_zoo`` model keeps running from its YAML config.  A patched forward uses the kernels
+when its tensors are CUDA tensors and the configuration is one the kernels cover; otherwise it
+calls the reference's original forward (the reference's own code, not a fallback of ours).
+
+Patched: FeatureEmbedding, FeatureEmbeddingDict, LogisticRegression, InnerProductInteraction,
+CrossNet, CrossNetV2, CompressedInteractionNet, DIN_Attention, Dice, MLP_Block
+(fuxictr/pytorch/layers/**).
+"""
+import functools
+
+import torch
+
+from . import layers as M
+
+_ORIGINALS = {}
+_STATE = {"enabled": False, "calls": {}}
+
+
+def _tensors(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            yield a
+        elif isinstance(a, dict):
+            for v in a.values():
+                if isinstance(v, torch.Tensor):
+                    yield v
+
+
+def _on_cuda(args, kwargs):
+    ts = list(_tensors(args, kwargs))
+    return bool(ts) and all(t.is_cuda for t in ts)
+
+
+def _wrap(ref_cls, mirror_forward, supported=None):
+    name = ref_cls.__name__
+    original = ref_cls.forward
+    _ORIGINALS[ref_cls] = original
+
+    @functools.wraps(original)
+    def forward(self, *args, **kwargs):
+        if _STATE["enabled"] and _on_cuda(args, kwargs) and (supported is None or supported(self)):
+            _STATE["calls"][name] = _STATE["calls"].get(name, 0) + 1
+            return mirror_forward(self, *args, **kwargs)
+        return original(self, *args, **kwargs)
+    ref_cls.forward = forward
+
+
+def _graft_methods(ref_cls, mirror_cls, names):
+    for n in names:
+        setattr(ref_cls, n, getattr(mirror_cls, n))
+
+
+def _fed_supported(self):
+    if not hasattr(self, "_plans"):
+        self._plans = {}
+    return True
+
+
+def _mlp_supported(self):
+    return True
+
+
+def enable():
+    """Patch the reference classes in place (idempotent).  Raises ImportError when the reference
+    package is not importable — this module is only meaningful next to it."""
+    import fuxictr.pytorch.layers as R
+    if _ORIGINALS:
+        _STATE["enabled"] = True
+        return
+    # helper methods the mirrored forwards call on `self`
+    _graft_methods(R.FeatureEmbeddingDict, M.FeatureEmbeddingDict,
+                   ["_active_features", "_is_fusable", "_plan", "_fused_arena", "forward_tensor"])
+    _wrap(R.FeatureEmbeddingDict, M.FeatureEmbeddingDict.forward, _fed_supported)
+    _wrap(R.FeatureEmbedding, M.FeatureEmbedding.forward, lambda s: _fed_supported(s.embedding_layer))
+
+    def lr_ok(self):
+        if not hasattr(self, "_lr_plans"):
+            self._lr_plans = {}
+        return _fed_supported(self.embedding_layer.embedding_layer)
+    _wrap(R.LogisticRegression, M.LogisticRegression.forward, lr_ok)
+    _wrap(R.InnerProductInteraction, M.InnerProductInteraction.forward)
+    _wrap(R.CrossNet, M.CrossNet.forward)
+    _wrap(R.CrossNetV2, M.CrossNetV2.forward)
+    _wrap(R.CompressedInteractionNet, M.CompressedInteractionNet.forward)
+    _wrap(R.DIN_Attention, M.DIN_Attention.forward)
+    _wrap(R.Dice, M.Dice.forward)
+    _wrap(R.MLP_Block, M.MLP_Block.forward, _mlp_supported)
+    _STATE["enabled"] = True
+
+
+def disable():
+    """Back to the reference's own forwards (the patches stay installed but inert)."""
+    _STATE["enabled"] = False
+
+
+def call_counts():
+    """How many times each patched forward took the kernel path (for tests / diagnostics)."""
+    return dict(_STATE["calls"])

@@ -1,0 +1,84 @@
+"""fuxictr_b200.patch.enable() on the REAL reference (only where /root/reference exists, i.e. in the
+build container; the GPU box has no reference checkout): class identity, state_dict and CPU
+behaviour are untouched, and CUDA tensors would be routed to the kernels."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+from conftest import Golden, rel_err
+
+REF = os.environ.get("FUXICTR_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "fuxictr")),
+                                reason="reference checkout not present on this machine")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    for name in ["h5py", "polars", "keras_preprocessing", "keras_preprocessing.sequence"]:
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["keras_preprocessing.sequence"].pad_sequences = lambda *a, **k: None
+    sys.modules["keras_preprocessing"].sequence = sys.modules["keras_preprocessing.sequence"]
+    sys.path.insert(0, REF)
+    import fuxictr.pytorch.layers as L
+    from fuxictr.features import FeatureMap
+    for name in ["h5py", "polars"]:
+        sys.modules.pop(name, None)
+    sys.path.insert(0, os.path.join(REF, "model_zoo", "DeepFM", "DeepFM_torch"))
+    from src.DeepFM import DeepFM
+    return types.SimpleNamespace(L=L, FeatureMap=FeatureMap, DeepFM=DeepFM)
+
+
+def build_ref_deepfm(ref, g):
+    from collections import OrderedDict
+    fm = ref.FeatureMap("synthetic", "/tmp")
+    fm.features = OrderedDict((k, dict(v)) for k, v in g.meta["specs"])
+    fm.labels = g.meta["labels"]
+    fm.default_emb_dim = g.meta["kwargs"]["embedding_dim"]
+    fm.num_fields = fm.get_num_fields()
+    fm.set_column_index()
+    model = ref.DeepFM(fm, model_root="/tmp/b2_patch/", metrics=["AUC"], verbose=0, optimizer="adam",
+                       loss="binary_crossentropy", task="binary_classification", gpu=-1, **g.meta["kwargs"])
+    model.load_state_dict(g["w"])
+    return fm, model
+
+
+def test_enable_keeps_identity_and_cpu_results(ref):
+    from fuxictr_b200 import patch
+    g = Golden("model_DeepFM")
+    cls_before = ref.L.FeatureEmbeddingDict
+    patch.enable()
+    try:
+        assert ref.L.FeatureEmbeddingDict is cls_before                       # same class object
+        fm, model = build_ref_deepfm(ref, g)
+        assert list(model.state_dict().keys()) == list(g["w"].keys())
+        assert type(model.embedding_layer.embedding_layer) == ref.L.FeatureEmbeddingDict   # rank_model.py:107
+        B = g.meta["batch"]
+        mat = g["in"]["matrix"][:B]
+        batch = {c: mat[:, fm.get_column_index(c)] for c in list(fm.features.keys()) + fm.labels}
+        y = model.forward(batch)["y_pred"]                                    # CPU tensors -> original forwards
+        assert rel_err(y, g["out"]["y_pred"]) <= 1e-6
+        assert patch.call_counts() == {}
+    finally:
+        patch.disable()
+
+
+def test_cuda_tensors_are_routed_to_the_kernels(ref, monkeypatch):
+    """No GPU here: pretend the tensors are CUDA and check that the patched forwards reach the
+    kernel entry points (which then refuse the CPU tensors loudly)."""
+    from fuxictr_b200 import patch
+    g = Golden("model_DeepFM")
+    patch.enable()
+    try:
+        fm, model = build_ref_deepfm(ref, g)
+        B = g.meta["batch"]
+        mat = g["in"]["matrix"][:B]
+        batch = {c: mat[:, fm.get_column_index(c)] for c in list(fm.features.keys()) + fm.labels}
+        monkeypatch.setattr(patch, "_on_cuda", lambda a, k: True)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            model.forward(batch)
+        assert patch.call_counts().get("FeatureEmbedding", 0) >= 1
+    finally:
+        patch.disable()
