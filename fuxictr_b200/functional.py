@@ -543,27 +543,121 @@ def cin_forward(feature_emb, conv_layers, fc):
     return linear_act(torch.cat(pools, dim=-1), fc.weight, fc.bias, B2_ACT_NONE)
 
 
+class _Dice(torch.autograd.Function):
+    """Dice.forward (activations.py:49-50) on (M, C): column statistics + gate, one C-ABI call each way."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, bn, training):
+        x = _f32c(x)
+        M, C = x.shape
+        dev = x.device
+        out = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        rstd = torch.empty(C, dtype=torch.float32, device=dev)
+        ws = torch.empty(3 * C, dtype=torch.float64, device=dev)
+        track = bn.track_running_stats and bn.running_mean is not None
+        use_batch_stats = training or not track
+        momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+        _lib.call("b2_dice_fwd", _ptr(x), _ptr(alpha), M, C, float(bn.eps), momentum, 1 if use_batch_stats else 0,
+                  _ptr(bn.running_mean) if (track and training) or not use_batch_stats else None,
+                  _ptr(bn.running_var) if (track and training) or not use_batch_stats else None,
+                  _ptr(mean), _ptr(rstd), _ptr(ws), _ptr(out), _stream())
+        if training and track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(x, alpha, mean, rstd)
+        ctx.batch_stats = use_batch_stats
+        ctx.alpha_param = alpha
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, alpha, mean, rstd = ctx.saved_tensors
+        gout = _f32c(gout)
+        M, C = x.shape
+        gx = torch.empty_like(x)
+        galpha = _grad_buffer(ctx.alpha_param, zero=False)
+        ws = torch.empty(3 * C, dtype=torch.float64, device=x.device)
+        _lib.call("b2_dice_bwd", _ptr(x), _ptr(gout), _ptr(alpha), _ptr(mean), _ptr(rstd), M, C,
+                  1 if ctx.batch_stats else 0, _ptr(ws), _ptr(gx), _ptr(galpha), _stream())
+        return gx, galpha, None, None
+
+
 def dice_forward(X, bn, alpha, training):
     """Dice.forward (activations.py:49-50)."""
-    p = torch.sigmoid(bn(X))
-    return p * X + alpha * (1 - p) * X
+    _require_cuda(X, alpha)
+    if X.dim() != 2:
+        lead = X.shape[:-1]
+        return _Dice.apply(X.reshape(-1, X.shape[-1]), alpha, bn, training).view(*lead, -1)
+    return _Dice.apply(X, alpha, bn, training)
+
+
+class _DinInput(torch.autograd.Function):
+    """att_in ((B*L), 4d) = [t, h, t-h, t*h]  (target_attention.py:80-82) in one launch."""
+
+    @staticmethod
+    def forward(ctx, target, hist):
+        target, hist = _f32c(target), _f32c(hist)
+        B, L, d = hist.shape
+        out = torch.empty((B * L, 4 * d), dtype=torch.float32, device=hist.device)
+        _lib.call("b2_din_input_fwd", _ptr(target), _ptr(hist), B, L, d, _ptr(out), _stream())
+        ctx.save_for_backward(target, hist)
+        return out
+
+    @staticmethod
+    def backward(ctx, gin):
+        target, hist = ctx.saved_tensors
+        B, L, d = hist.shape
+        gin = _f32c(gin)
+        gt = torch.empty_like(target)
+        gh = torch.empty_like(hist)
+        _lib.call("b2_din_input_bwd", _ptr(target), _ptr(hist), _ptr(gin), B, L, d, _ptr(gt), _ptr(gh), 0, _stream())
+        return gt, gh
+
+
+class _DinWeightedSum(torch.autograd.Function):
+    """out (B,d) = sum_l (w*mask)[b,l] * hist[b,l,:]  (target_attention.py:85-86,91)."""
+
+    @staticmethod
+    def forward(ctx, w, mask_u8, hist):
+        w, hist = _f32c(w), _f32c(hist)
+        B, L, d = hist.shape
+        out = torch.empty((B, d), dtype=torch.float32, device=hist.device)
+        _lib.call("b2_din_wsum_fwd", _ptr(w), _ptr(mask_u8), _ptr(hist), B, L, d, _ptr(out), _stream())
+        ctx.save_for_backward(w, hist)
+        ctx.mask = mask_u8
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        w, hist = ctx.saved_tensors
+        B, L, d = hist.shape
+        gout = _f32c(gout)
+        gw = torch.empty_like(w)
+        gh = torch.empty_like(hist)
+        _lib.call("b2_din_wsum_bwd", _ptr(w), _ptr(ctx.mask), _ptr(hist), _ptr(gout), B, L, d, _ptr(gw), _ptr(gh),
+                  _stream())
+        return gw, None, gh
 
 
 def din_attention(module, target_item, history_sequence, mask=None):
-    """DIN_Attention.forward (target_attention.py:79-92)."""
-    seq_len = history_sequence.size(1)
-    target_item = target_item.unsqueeze(1).expand(-1, seq_len, -1)
-    attention_input = torch.cat([target_item, history_sequence, target_item - history_sequence,
-                                 target_item * history_sequence], dim=-1)
-    attention_weight = module.attention_layer(attention_input.view(-1, 4 * module.embedding_dim))
-    attention_weight = attention_weight.view(-1, seq_len)
+    """DIN_Attention.forward (target_attention.py:79-92): input construction, mask and weighted sum
+    are single launches; the attention MLP runs on the b2 GEMM + Dice kernels."""
+    _require_cuda(target_item, history_sequence)
+    B, L, d = history_sequence.shape
+    att_in = _DinInput.apply(target_item, history_sequence)
+    weight = module.attention_layer(att_in).view(B, L)
+    mask_u8 = None
     if mask is not None:
-        attention_weight = attention_weight * mask.float()
+        mask_u8 = mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
     if module.use_softmax:
+        # softmax variant (:87-90): mask, additive -1e9 fill and softmax stay stock ops
         if mask is not None:
-            attention_weight = attention_weight + -1.e9 * (1 - mask.float())
-        attention_weight = attention_weight.softmax(dim=-1)
-    return (attention_weight.unsqueeze(-1) * history_sequence).sum(dim=1)
+            mf = mask.float()
+            weight = weight * mf
+            weight = weight + -1.e9 * (1 - mf)
+        weight = weight.softmax(dim=-1)
+        mask_u8 = None
+    return _DinWeightedSum.apply(weight, mask_u8, history_sequence)
 
 
 # --------------------------------------------------------------------------------------

@@ -216,6 +216,35 @@ B2_API int b2_crossnet_bwd(const float* x0, const float* w, const float* b, cons
                     float* gb, void* stream);
 
 /*
+ * Dice (layers/activations.py:37,49-50): p = sigmoid(BatchNorm1d(affine=False, eps, momentum)(x));
+ * out = p*x + alpha*(1-p)*x on x (M, C).  training != 0: batch statistics over the M rows (and
+ * running_mean/var updated in place like nn.BatchNorm1d, unbiased variance); else running stats.
+ * mean/rstd (C) are outputs saved for the backward; stats_ws is a device workspace of 3*C doubles.
+ * b2_dice_bwd: gx (M,C) "=", galpha (C) "=" (stats_ws is clobbered).
+ */
+B2_API int b2_dice_fwd(const float* x, const float* alpha, int64_t M, int C, float eps, float momentum,
+                       int training, float* running_mean, float* running_var, float* mean, float* rstd,
+                       double* stats_ws, float* out, void* stream);
+B2_API int b2_dice_bwd(const float* x, const float* gout, const float* alpha, const float* mean,
+                       const float* rstd, int64_t M, int C, int training, double* stats_ws, float* gx,
+                       float* galpha, void* stream);
+/*
+ * DIN_Attention glue (layers/attentions/target_attention.py:79-92).
+ * b2_din_input_fwd: out ((B*L), 4d) = [t, h, t-h, t*h] with t = target (B,d) broadcast over L, h = hist (B,L,d).
+ * b2_din_input_bwd: from gin ((B*L),4d): gtarget (B,d) "=", ghist (B,L,d) "=" or "+=" (accumulate_hist).
+ * b2_din_wsum_fwd:  out (B,d) = sum_l w[b,l]*mask[b,l]*hist[b,l,:]  (mask uint8 or NULL)   (:85-86,91)
+ * b2_din_wsum_bwd:  gw (B,L) = mask * <gout[b], hist[b,l]>;  ghist (B,L,d) = w*mask*gout[b].
+ */
+B2_API int b2_din_input_fwd(const float* target, const float* hist, int64_t B, int L, int d, float* out,
+                            void* stream);
+B2_API int b2_din_input_bwd(const float* target, const float* hist, const float* gin, int64_t B, int L, int d,
+                            float* gtarget, float* ghist, int accumulate_hist, void* stream);
+B2_API int b2_din_wsum_fwd(const float* w, const unsigned char* mask, const float* hist, int64_t B, int L,
+                           int d, float* out, void* stream);
+B2_API int b2_din_wsum_bwd(const float* w, const unsigned char* mask, const float* hist, const float* gout,
+                           int64_t B, int L, int d, float* gw, float* ghist, void* stream);
+
+/*
  * Dense layer with fused epilogue; the GEMM behind MLP_Block
  * (layers/blocks/mlp_block.py:74-85,96), CrossNetV2 (cross_net.py:126-129) and
  * the 1x1 Conv1d of CIN (compressed_interaction_net.py:72).
