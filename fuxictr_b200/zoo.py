@@ -174,12 +174,16 @@ class RankModel(nn.Module):
         return self._sharded_front
 
     def _batch_matrix(self, inputs):
-        """The (B, W) matrix the collator sliced `inputs` from (the views' common base)."""
-        first = next(iter(inputs.values()))
-        base = first._base if first._base is not None else None
-        if base is None or base.dim() != 2:
+        """The (B, W) matrix the collator sliced `inputs` from, rebuilt from one column view's
+        storage offset and row stride (the views' `_base` may be a larger tensor)."""
+        name = next(iter(self.feature_map.features.keys()))
+        v = inputs[name]
+        col = self.feature_map.get_column_index(name)
+        width = self.feature_map.input_length + len(self.feature_map.labels)
+        if v.dim() != 1 or v.stride(0) < width or v.storage_offset() < col:
             raise RuntimeError("sharded front needs the batch dict to be column views of one matrix")
-        return base.to(self.device)
+        mat = v.as_strided((v.shape[0], width), (v.stride(0), 1), v.storage_offset() - col)
+        return mat.to(self.device)
 
     def use_fused_optimizer(self):
         """Re-home parameters into one HBM arena and replace clip_grad_norm_ + torch Adam by
