@@ -14,14 +14,32 @@
 // Field descriptors travel as a __grid_constant__ launch parameter (no H2D
 // copy, CUDA-graph friendly) and are staged once per CTA in shared memory.
 #include "embed_common.cuh"
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------------
 // Forward, fast path: no pooled field, every row fits one pass of its LPR lanes.
 // ---------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ typename VecT<VEC>::type b2_ld_row(const typename VecT<VEC>::type* p, bool stream) {
+  return __ldg(p);
+}
+template <>
+__device__ __forceinline__ float4 b2_ld_row<4>(const float4* p, bool stream) {
+  return stream ? b2_ldg_stream(p) : __ldg(p);
+}
+template <int VEC>
+__device__ __forceinline__ void b2_st_row(typename VecT<VEC>::type* p, const typename VecT<VEC>::type& v, bool stream) {
+  *p = v;
+}
+template <>
+__device__ __forceinline__ void b2_st_row<4>(float4* p, const float4& v, bool stream) {
+  if (stream) b2_stg_stream(p, v); else *p = v;
+}
+
 template <typename IdxT, int VEC, int UNROLL>
 __global__ void __launch_bounds__(256)
 gather_fast_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int lpr_log2,
-                   int32_t* __restrict__ status) {
+                   int32_t* __restrict__ status, bool stream) {
   using V = typename VecT<VEC>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemFields sf = b2_stage_fields(pack, smem_raw);
@@ -80,12 +98,12 @@ gather_fast_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int 
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       val[u] = b2_vzero<VEC>();
-      if (live[u]) val[u] = __ldg(src[u]);
+      if (live[u]) val[u] = b2_ld_row<VEC>(src[u], stream);
     }
     // Phase 3: coalesced stores of the stacked/concatenated tensor.
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
-      if (dst[u] != nullptr) *dst[u] = val[u];
+      if (dst[u] != nullptr) b2_st_row<VEC>(dst[u], val[u], stream);
   }
 }
 
@@ -331,11 +349,24 @@ static int launch_gather(const B2FieldPack& pack, int64_t batch, int vec, int ma
   const bool one_pass = ((1 << lpr_log2) * vec) >= max_dim;
   const int64_t nitems = batch * (int64_t) pack.nslots;
   if (!any_pooled && one_pass) {
-    constexpr int UNROLL = 4;
-    const int grid = grid_for(b2_ceil_div(nitems, UNROLL) << lpr_log2, block);
-    if (vec == 4) gather_fast_kernel<IdxT, 4, UNROLL><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status);
-    else if (vec == 2) gather_fast_kernel<IdxT, 2, UNROLL><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status);
-    else gather_fast_kernel<IdxT, 1, UNROLL><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status);
+    // Large launches stream: rows are touched once, so keep them out of L1 and unroll deeper
+    // (8 independent 16-byte row loads per lane); small launches stay L2-friendly and shallow.
+    static const int env_unroll = getenv("B2_GATHER_UNROLL") ? atoi(getenv("B2_GATHER_UNROLL")) : 0;
+    static const int env_stream = getenv("B2_GATHER_STREAM") ? atoi(getenv("B2_GATHER_STREAM")) : -1;
+    const bool big = nitems >= (int64_t) 1 << 20;
+    const int unroll = env_unroll ? env_unroll : (big ? 8 : 4);
+    const bool stream = env_stream >= 0 ? (env_stream != 0) : big;
+    if (unroll == 8) {
+      const int grid = grid_for(b2_ceil_div(nitems, 8) << lpr_log2, block);
+      if (vec == 4) gather_fast_kernel<IdxT, 4, 8><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
+      else if (vec == 2) gather_fast_kernel<IdxT, 2, 8><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
+      else gather_fast_kernel<IdxT, 1, 8><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
+    } else {
+      const int grid = grid_for(b2_ceil_div(nitems, 4) << lpr_log2, block);
+      if (vec == 4) gather_fast_kernel<IdxT, 4, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
+      else if (vec == 2) gather_fast_kernel<IdxT, 2, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
+      else gather_fast_kernel<IdxT, 1, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
+    }
   } else {
     const int grid = grid_for(nitems << lpr_log2, block);
     if (vec == 4) gather_general_kernel<IdxT, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, mean_count, status);

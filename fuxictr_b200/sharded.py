@@ -50,7 +50,8 @@ class PeerGroup(object):
     rank = 0
 
     def alloc(self, name, shape, dtype):
-        """Returns (local tensor, [device pointer of that buffer on every rank])."""
+        """Returns (local tensor, [device pointer of that buffer on every rank], peer_view) where
+        peer_view(r) is a tensor aliasing rank r's copy of the buffer."""
         raise NotImplementedError
 
     def barrier(self):
@@ -73,7 +74,8 @@ class SymmPeerGroup(PeerGroup):
         hdl = self._symm.rendezvous(t, self.group.group_name)
         self._handles.append(hdl)
         t.zero_()
-        return t, [int(p) for p in hdl.buffer_ptrs]
+        shape = tuple(shape)
+        return t, [int(p) for p in hdl.buffer_ptrs], (lambda r: hdl.get_buffer(r, shape, dtype))
 
     def barrier(self):
         self._handles[0].barrier()      # device-side signal-pad barrier on the current stream
@@ -89,7 +91,7 @@ class VirtualPeerGroup(PeerGroup):
     def alloc(self, name, shape, dtype):
         bufs = self._reg.setdefault(name, {})
         bufs[self.rank] = torch.zeros(tuple(shape), dtype=dtype, device="cuda")
-        return bufs[self.rank], _LazyPtrs(bufs, self.world)
+        return bufs[self.rank], _LazyPtrs(bufs, self.world), (lambda r: bufs[r])
 
     def barrier(self):
         pass
@@ -103,6 +105,9 @@ class _LazyPtrs(object):
 
     def __iter__(self):
         return iter([self._bufs[r].data_ptr() for r in range(self._world)])
+
+    def __getitem__(self, r):
+        return self._bufs[r].data_ptr()
 
 
 def _ptr_array(ptrs):
@@ -130,11 +135,15 @@ class ShardedFront(object):
         self.idx_dtype = idx_dtype
         self.idx_code = F2._IDX_CODE[idx_dtype]
         g = group
-        self.ids, self.ids_ptrs = g.alloc("ids", (batch_local, matrix_width), idx_dtype)
-        self.emb, self.emb_ptrs = g.alloc("emb", (batch_local, self.F * dim), torch.float32)
-        self.lrw, self.lrw_ptrs = g.alloc("lrw", (batch_local, self.F), torch.float32)
-        self.gemb, self.gemb_ptrs = g.alloc("gemb", (batch_local, self.F * dim), torch.float32)
-        self.glogit, self.glogit_ptrs = g.alloc("glogit", (batch_local,), torch.float32)
+        # ids_all[p] = batch matrix of rank p: every rank BROADCASTS its ids into slot `rank` of all
+        # peers (bulk P2P copies), so the push/pull kernels walk local memory only.
+        self.ids_all, _, self._ids_peer = g.alloc("ids_all", (g.world, batch_local, matrix_width), idx_dtype)
+        esz = self.ids_all.element_size()
+        self.ids_ptrs = [self.ids_all.data_ptr() + p * batch_local * matrix_width * esz for p in range(g.world)]
+        self.emb, self.emb_ptrs, _ = g.alloc("emb", (batch_local, self.F * dim), torch.float32)
+        self.lrw, self.lrw_ptrs, _ = g.alloc("lrw", (batch_local, self.F), torch.float32)
+        self.gemb, self.gemb_ptrs, _ = g.alloc("gemb", (batch_local, self.F * dim), torch.float32)
+        self.glogit, self.glogit_ptrs, _ = g.alloc("glogit", (batch_local,), torch.float32)
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     # -- descriptors --------------------------------------------------------------------------
@@ -149,7 +158,8 @@ class ShardedFront(object):
 
     # -- forward phases -------------------------------------------------------------------------
     def phase_ids(self, batch_matrix):
-        self.ids.copy_(batch_matrix)
+        for p in range(self.group.world):
+            self._ids_peer(p)[self.group.rank].copy_(batch_matrix)      # P2P store of 8*B*W bytes per peer
 
     def phase_push(self):
         g = self.group
