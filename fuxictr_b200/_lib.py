@@ -60,6 +60,10 @@ SIGNATURES = {
     "b2_crossnet_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_crossnet_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2_cin_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
+                           c_void_p]),
+    "b2_cin_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
+                           c_int, c_void_p, c_void_p, c_void_p]),
     "b2_dice_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2_dice_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,

@@ -528,17 +528,62 @@ def logit_bce(label, *terms):
 # elementwise/outer-product pieces are stock torch ops until their fused kernels land
 # (tracked in DESIGN.md "kernel status").
 # --------------------------------------------------------------------------------------
+class _CinLayer(torch.autograd.Function):
+    """X_next (B,H',D) = Conv1x1(outer(X_0, X_i)) with the outer product kept in registers
+    (compressed_interaction_net.py:70-73)."""
+
+    @staticmethod
+    def forward(ctx, x0, xk, weight, bias):
+        x0, xk = _f32c(x0), _f32c(xk)
+        B, F, D = x0.shape
+        H = xk.shape[1]
+        HO = weight.shape[0]
+        out = torch.empty((B, HO, D), dtype=torch.float32, device=x0.device)
+        _lib.call("b2_cin_fwd", _ptr(x0), _ptr(xk), _ptr(weight), _ptr(bias), B, F, H, HO, D, _ptr(out), _stream())
+        ctx.save_for_backward(x0, xk, weight)
+        ctx.w_param, ctx.b_param = weight, bias
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x0, xk, weight = ctx.saved_tensors
+        g = _f32c(g)
+        B, F, D = x0.shape
+        H = xk.shape[1]
+        HO = weight.shape[0]
+        gx0 = torch.empty_like(x0)
+        gxk = torch.empty_like(xk)
+        gw = _grad_buffer(ctx.w_param, zero=False)
+        _lib.call("b2_cin_bwd", _ptr(x0), _ptr(xk), _ptr(weight), _ptr(g), B, F, H, HO, D, _ptr(gx0), 0, _ptr(gxk),
+                  _ptr(gw), _stream())
+        gb = None
+        if ctx.b_param is not None and ctx.b_param.requires_grad:
+            gb = g.sum(dim=(0, 2))
+        return gx0, gxk, gw, gb
+
+
+def cin_supported(num_fields, hidden_units):
+    hs = [num_fields] + list(hidden_units)
+    return all(h <= 32 for h in hidden_units) and all(h <= 64 for h in hs[:-1])
+
+
 def cin_forward(feature_emb, conv_layers, fc):
     """CompressedInteractionNet.forward (compressed_interaction_net.py:64-76)."""
+    _require_cuda(feature_emb)
     X0 = feature_emb
-    B, _, D = X0.shape
+    B, F, D = X0.shape
     Xi = X0
     pools = []
+    fused = cin_supported(F, [c.out_channels for c in conv_layers])
     for conv in conv_layers:
-        had = torch.einsum("bhd,bmd->bhmd", X0, Xi).reshape(B, -1, D)          # (B, F*H, D)
-        w = conv.weight.view(conv.out_channels, -1)                              # 1x1 conv == GEMM
-        rows = had.transpose(1, 2).reshape(B * D, -1)                            # (B*D, F*H)
-        Xi = linear_act(rows, w, conv.bias, B2_ACT_NONE).view(B, D, -1).transpose(1, 2)
+        if fused:
+            Xi = _CinLayer.apply(X0, Xi, conv.weight, conv.bias)       # weight (H', F*H, 1): contiguous (H', F*H)
+        else:
+            # shapes beyond the fused kernel's register budget: materialise like the reference does
+            had = torch.einsum("bhd,bmd->bhmd", X0, Xi).reshape(B, -1, D)
+            w = conv.weight.view(conv.out_channels, -1)
+            rows = had.transpose(1, 2).reshape(B * D, -1)
+            Xi = linear_act(rows, w, conv.bias, B2_ACT_NONE).view(B, D, -1).transpose(1, 2)
         pools.append(Xi.sum(dim=-1))
     return linear_act(torch.cat(pools, dim=-1), fc.weight, fc.bias, B2_ACT_NONE)
 

@@ -216,6 +216,20 @@ B2_API int b2_crossnet_bwd(const float* x0, const float* w, const float* b, cons
                     float* gb, void* stream);
 
 /*
+ * One CompressedInteractionNet layer (layers/interactions/compressed_interaction_net.py:70-73)
+ * without the (B, F*H, D) Hadamard tensor:
+ *   out[b,h',d] = bias[h'] + sum_{f,m} w[h', f*H + m] * x0[b,f,d] * xk[b,m,d]
+ * x0 (B,F,D), xk (B,H,D), w (H', F*H) = Conv1d weight with kernel_size 1, out (B,H',D); H' <= 32.
+ * b2_cin_bwd: g (B,H',D) -> gx0 (B,F,D) ("=" or "+=" with accumulate_x0), gxk (B,H,D) "=",
+ * gw (H', F*H) "=" (H <= 64).  The bias gradient is the plain sum of g over (b,d).
+ */
+B2_API int b2_cin_fwd(const float* x0, const float* xk, const float* w, const float* bias, int64_t batch,
+                      int F, int H, int HO, int D, float* out, void* stream);
+B2_API int b2_cin_bwd(const float* x0, const float* xk, const float* w, const float* g, int64_t batch, int F,
+                      int H, int HO, int D, float* gx0, int accumulate_x0, float* gxk, float* gw,
+                      void* stream);
+
+/*
  * Dice (layers/activations.py:37,49-50): p = sigmoid(BatchNorm1d(affine=False, eps, momentum)(x));
  * out = p*x + alpha*(1-p)*x on x (M, C).  training != 0: batch statistics over the M rows (and
  * running_mean/var updated in place like nn.BatchNorm1d, unbiased variance); else running stats.

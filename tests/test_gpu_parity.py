@@ -622,3 +622,33 @@ def test_fused_front_matches_separate_modules(want_fm, dim, nf):
     scale = max(float(g.abs().max()) for g in g0)
     for a, b in zip(g1, g0):
         assert close(a, b, RTOL, atol=RTOL * scale)
+
+
+@pytest.mark.parametrize("F_,D,units,B", [(39, 16, [16, 16, 16], 130), (26, 10, [32, 8], 77), (5, 4, [3], 9)])
+def test_cin_fused_vs_oracle(F_, D, units, B):
+    """Fused CIN layers (Hadamard tensor never materialised) at xDeepFM shapes against the oracle's
+    einsum + Conv1d restatement (compressed_interaction_net.py:64-76)."""
+    from fuxictr_b200 import layers
+    from oracle import fuxictr_oracle as O
+    torch.manual_seed(F_ + D)
+    layer = layers.CompressedInteractionNet(F_, units)
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.normal_(0, 0.2)
+    state = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in layer.state_dict().items())
+    gen = torch.Generator().manual_seed(B)
+    emb = torch.randn(B, F_, D, generator=gen) * 0.5
+    gout = torch.randn(B, 1, generator=gen)
+    e_ref = emb.clone().requires_grad_(True)
+    y_ref = O.compressed_interaction_net(e_ref, state, "", units)
+    y_ref.backward(gout)
+    layer = layer.cuda()
+    e = emb.cuda().requires_grad_(True)
+    y = layer(e)
+    y.backward(gout.cuda())
+    assert close(y, y_ref, RTOL)
+    assert close(e.grad, e_ref.grad, RTOL)
+    named = dict(layer.named_parameters())
+    scale = max(float(v.grad.abs().max()) for v in state.values())
+    for k, v in state.items():
+        assert close(named[k].grad, v.grad, RTOL, atol=RTOL * scale), k
