@@ -47,7 +47,7 @@ cin_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const
   extern __shared__ float sm[];
   float* sx0 = sm;                       // F * PITCH
   float* sxk = sx0 + F * PITCH;          // H * PITCH
-  float* sw = sxk + H * PITCH;           // 2 buffers of H * HP  (W[:, f, :] transposed to [m][h'])
+  float* sw = sm + (((F + H) * PITCH + 3) & ~3);  // 16-byte aligned: 2 buffers of H * HP (W[:, f, :] as [m][h'])
   const int64_t ncols = batch * (int64_t) D;
   const int tid = threadIdx.x;
   for (int64_t col0 = (int64_t) blockIdx.x * COLS; col0 < ncols; col0 += (int64_t) gridDim.x * COLS) {
@@ -99,7 +99,7 @@ cin_bwd_x_kernel(const float* __restrict__ x0, const float* __restrict__ xk, con
   extern __shared__ float sm[];
   float* sx0 = sm;
   float* sxk = sx0 + F * PITCH;
-  float* sw = sxk + H * PITCH;
+  float* sw = sm + (((F + H) * PITCH + 3) & ~3);
   const int64_t ncols = batch * (int64_t) D;
   const int tid = threadIdx.x;
   for (int64_t col0 = (int64_t) blockIdx.x * COLS; col0 < ncols; col0 += (int64_t) gridDim.x * COLS) {
@@ -164,7 +164,7 @@ cin_bwd_w_kernel(const float* __restrict__ x0, const float* __restrict__ xk, con
   extern __shared__ float sm[];
   float* sx0 = sm;
   float* sxk = sx0 + F * PITCH;
-  float* sg = sxk + H * PITCH;           // COLS * HP   (column-major: sg[c*HP + h'])
+  float* sg = sm + (((F + H) * PITCH + 3) & ~3);  // 16-byte aligned: COLS * HP (sg[c*HP + h'])
   const int64_t ncols = batch * (int64_t) D;
   const int tid = threadIdx.x;
   const int K = F * H;
@@ -245,7 +245,7 @@ extern "C" B2_API int b2_cin_fwd(const float* x0, const float* xk, const float* 
   B2_REQUIRE(F >= 1 && H >= 1 && HO >= 1 && HO <= 32 && D >= 1, "unsupported CIN shape (H' must be <= 32)");
   if (batch <= 0) return B2_OK;
   const int hp = round_hp(HO);
-  const size_t smem = sizeof(float) * ((size_t) (F + H) * PITCH + 2 * (size_t) H * hp);
+  const size_t smem = sizeof(float) * ((size_t) (F + H) * PITCH + 4 + 2 * (size_t) H * hp);
   B2_REQUIRE(smem <= 220 * 1024, "CIN tile (F=%d, H=%d) exceeds shared memory", F, H);
   const int64_t tiles = b2_ceil_div(batch * (int64_t) D, COLS);
   const int grid = (int) (tiles < 2 * B2_NUM_SMS ? tiles : 2 * B2_NUM_SMS);
@@ -268,7 +268,7 @@ extern "C" B2_API int b2_cin_bwd(const float* x0, const float* xk, const float* 
   const int hp = round_hp(HO);
   const int64_t tiles = b2_ceil_div(batch * (int64_t) D, COLS);
   {
-    const size_t smem = sizeof(float) * ((size_t) (F + H) * PITCH + 2 * (size_t) H * hp);
+    const size_t smem = sizeof(float) * ((size_t) (F + H) * PITCH + 4 + 2 * (size_t) H * hp);
     B2_REQUIRE(smem <= 220 * 1024, "CIN tile (F=%d, H=%d) exceeds shared memory", F, H);
     const int grid = (int) (tiles < 2 * B2_NUM_SMS ? tiles : 2 * B2_NUM_SMS);
 #define B2_LAUNCH_BX(HPV, HKV)                                                                     \
@@ -286,7 +286,7 @@ extern "C" B2_API int b2_cin_bwd(const float* x0, const float* xk, const float* 
   }
   {
     constexpr int PAIRS = 2;
-    const size_t smem = sizeof(float) * ((size_t) (F + H) * PITCH + (size_t) COLS * hp);
+    const size_t smem = sizeof(float) * ((size_t) (F + H) * PITCH + 4 + (size_t) COLS * hp);
     B2_REQUIRE(smem <= 220 * 1024, "CIN tile (F=%d, H=%d) exceeds shared memory", F, H);
     const int K = F * H;
     const int kslices = (int) b2_ceil_div(K, COLS * PAIRS);
