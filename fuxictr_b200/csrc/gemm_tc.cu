@@ -26,7 +26,7 @@ namespace tc {
 constexpr int BM = 128;          // UMMA M (cta_group::1): TMEM lane == output row
 constexpr int BK = 32;           // fp32 elements per k-block == one 128-byte swizzle row
 constexpr int UMMA_K_BYTES = 32; // kind::tf32: K = 8 elements of 4 bytes per instruction
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;  // 4 stages of (A,B) for one pass; 3 stages of (A,As,B,Bs) for 3xTF32
 constexpr int A_BYTES = BM * 128;
 constexpr int NTHREADS = 192;
 
@@ -150,12 +150,15 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   // (pointer arithmetic on smem_raw keeps the shared address space visible to the compiler)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t b_bytes = (uint32_t) p.bn * 128u;
-  const uint32_t stage_bytes = A_BYTES + b_bytes;
+  const bool x3 = p.nseg > 1;
+  const int STAGES = x3 ? 3 : 4;
+  const uint32_t stage_bytes = (x3 ? 2u : 1u) * (A_BYTES + b_bytes);
+  const uint32_t off_as = A_BYTES, off_b = (x3 ? 2u : 1u) * A_BYTES, off_bs = off_b + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES),
-                 tmem_full = smem_u32(bars + 2 * STAGES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES),
+                 tmem_full = smem_u32(bars + 2 * MAX_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.bn;
@@ -166,11 +169,11 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   const int nmain = min(p.nmain, kb_end - kb_begin);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nseg; ++s) {
+    for (int s = 0; s < (x3 ? 2 : 1); ++s) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_a[s])) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_b[s])) : "memory");
     }
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
@@ -195,17 +198,20 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int seg = 0; seg < p.nseg; ++seg) {
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(empty0 + 8 * stage, phase ^ 1, 0);
-          const uint32_t a_dst = smem_base + stage * stage_bytes;
-          const uint32_t full = full0 + 8 * stage;
-          mbar_expect_tx(full, stage_bytes);
-          tma_load_2d(a_dst, &p.map_a[seg], full, kb * BK, m0);
-          tma_load_2d(a_dst + A_BYTES, &p.map_b[seg], full, kb * BK, n0);
-          if (seg == 0 && kb == kb_begin) stamp(p, 2);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(empty0 + 8 * stage, phase ^ 1, 0);
+        const uint32_t a_dst = smem_base + stage * stage_bytes;
+        const uint32_t full = full0 + 8 * stage;
+        mbar_expect_tx(full, stage_bytes);
+        // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products
+        tma_load_2d(a_dst, &p.map_a[0], full, kb * BK, m0);
+        tma_load_2d(a_dst + off_b, &p.map_b[0], full, kb * BK, n0);
+        if (x3) {
+          tma_load_2d(a_dst + off_as, &p.map_a[1], full, kb * BK, m0);
+          tma_load_2d(a_dst + off_bs, &p.map_b[1], full, kb * BK, n0);
         }
+        if (kb == kb_begin) stamp(p, 2);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -222,32 +228,31 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       int stage = 0;
       uint32_t phase = 0;
       const int nkb = kb_end - kb_begin;
-      for (int seg = 0; seg < p.nseg; ++seg) {
-        for (int i = 0; i < nkb; ++i) {
-          mbar_wait(full0 + 8 * stage, phase, 1);
-          tc_fence_after();
-          if (seg == 0 && i == 0) stamp(p, 3);
-          int slot, first;
-          if (seg == 0) {
-            slot = (int) (((long long) i * nmain) / nkb);
-            first = (i == (int) (((long long) slot * nkb + nmain - 1) / nmain));
-          } else {
-            slot = nmain;
-            first = (seg == 1 && i == 0);
-          }
-          const uint32_t d_tmem = tmem_base + (uint32_t) (slot * p.bn);
-          const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t adesc = make_smem_desc(a_addr);
-          const uint64_t bdesc = make_smem_desc(a_addr + A_BYTES);
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full0 + 8 * stage, phase, 1);
+        tc_fence_after();
+        if (i == 0) stamp(p, 3);
+        const int slot = (int) (((long long) i * nmain) / nkb);
+        const bool first = (i == (int) (((long long) slot * nkb + nmain - 1) / nmain));
+        const uint32_t d_main = tmem_base + (uint32_t) (slot * p.bn);
+        const uint32_t d_corr = tmem_base + (uint32_t) (nmain * p.bn);
+        const uint32_t a_addr = smem_base + stage * stage_bytes;
+        const uint64_t adesc = make_smem_desc(a_addr);
+        const uint64_t bdesc = make_smem_desc(a_addr + off_b);
+        const uint64_t asdesc = make_smem_desc(a_addr + off_as);
+        const uint64_t bsdesc = make_smem_desc(a_addr + off_bs);
 #pragma unroll
-          for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
-            // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_tf32(d_tmem, adesc + (uint64_t) (k * (UMMA_K_BYTES >> 4)),
-                      bdesc + (uint64_t) (k * (UMMA_K_BYTES >> 4)), idesc, (!first || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
+          // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          const uint64_t ko = (uint64_t) (k * (UMMA_K_BYTES >> 4));
+          umma_tf32(d_main, adesc + ko, bdesc + ko, idesc, (!first || k > 0) ? 1u : 0u);      // A_big . B_big
+          if (x3) {
+            umma_tf32(d_corr, adesc + ko, bsdesc + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);   // A_big . B_small
+            umma_tf32(d_corr, asdesc + ko, bdesc + ko, idesc, 1u);                            // A_small . B_big
           }
-          umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full);  // accumulator complete
       stamp(p, 4);
@@ -378,6 +383,136 @@ transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64
     }
   }
 }
+
+// ---------------------------------------------------------------------------------
+// Operand preparation for the K-major tensor-core GEMMs, one pass over a (R, C) matrix:
+//   v      = act'(y) * x          (act-backward fused when y != NULL; y is the activation OUTPUT)
+//   out    = v            (R, C)            out_small  = tf32_small(v)
+//   outT   = v^T          (C, R)            outT_small = tf32_small(v^T)
+//   colsum[c] += sum_r v[r, c]              (bias gradient)
+// Any output pointer may be NULL.  32 x 32 tiles through padded shared memory.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_operand_kernel(const float* __restrict__ x, const float* __restrict__ y, int act, int64_t R,
+                    int64_t C, int64_t ld_in, float* __restrict__ out, float* __restrict__ out_small,
+                    float* __restrict__ outT, float* __restrict__ outT_small, float* __restrict__ colsum) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t c0 = (int64_t) blockIdx.x * 32, r0 = (int64_t) blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t r = r0 + ty + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = __ldg(x + r * ld_in + c);
+      if (y != nullptr) {
+        const float yv = __ldg(y + r * ld_in + c);
+        if (act == B2_ACT_RELU) v = (yv > 0.f) ? v : 0.f;
+        else if (act == B2_ACT_SIGMOID) v = v * ((1.f - yv) * yv);
+      }
+      if (out != nullptr) out[r * C + c] = v;
+      if (out_small != nullptr) out_small[r * C + c] = tf32_small(v);
+    }
+    tile[ty + i][tx] = v;
+  }
+  __syncthreads();
+  if (outT != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      const int64_t c = c0 + ty + i, r = r0 + tx;  // outT[c, r]
+      if (c < C && r < R) {
+        const float v = tile[tx][ty + i];
+        outT[c * R + r] = v;
+        if (outT_small != nullptr) outT_small[c * R + r] = tf32_small(v);
+      }
+    }
+  }
+  if (colsum != nullptr && ty == 0) {
+    const int64_t c = c0 + tx;
+    if (c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t += tile[i][tx];
+      b2_red_add(colsum + c, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// The N = 1 output head of an MLP (Linear(K, 1)): TMA cannot address a 4-byte row and a 128-wide
+// MMA tile would be 1/128 full, so it is a warp-per-row GEMV forward and one fused backward:
+//   fwd: y[m] = act(<x[m,:], w> + b)
+//   bwd: gz = act'(y) * gy;  gx[m,:] = gz[m] * w;  gw += sum_m gz[m] * x[m,:];  gb += sum_m gz[m]
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                int64_t M, int K, int act, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  const float bv = (b != nullptr) ? __ldg(b) : 0.f;
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(x + m * K + k), __ldg(w + k), acc);
+    acc = b2_warp_sum(acc);
+    if (lane == 0) {
+      float v = acc + bv;
+      if (act == B2_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (act == B2_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+      y[m] = v;
+    }
+  }
+}
+
+// CTA = 256 threads = 8 warps; each CTA owns a contiguous block of rows; lane k-strided columns.
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ y,
+                const float* __restrict__ gy, int64_t M, int K, int act, int64_t rows_per_cta,
+                float* __restrict__ gx, float* __restrict__ gw, float* __restrict__ gb) {
+  extern __shared__ float sgw[];  // K partial sums
+  __shared__ float red[32];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sgw[k] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t) blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
+  float gb_acc = 0.f;
+  // each warp keeps per-lane partials of gw for its k-strided columns over its rows
+  for (int kb = 0; kb < K; kb += 32 * 8) {       // 8 columns per lane per pass
+    float part[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[j] = 0.f;
+    for (int64_t m = r0 + warp; m < r1; m += 8) {
+      float gz = __ldg(gy + m);
+      if (y != nullptr) {
+        const float yv = __ldg(y + m);
+        if (act == B2_ACT_RELU) gz = (yv > 0.f) ? gz : 0.f;
+        else if (act == B2_ACT_SIGMOID) gz = gz * ((1.f - yv) * yv);
+      }
+      if (kb == 0 && lane == 0) gb_acc += gz;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = kb + j * 32 + lane;
+        if (k < K) {
+          if (gx != nullptr) gx[m * K + k] = gz * __ldg(w + k);
+          part[j] = fmaf(gz, __ldg(x + m * K + k), part[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kb + j * 32 + lane;
+      if (k < K) atomicAdd(sgw + k, part[j]);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    if (sgw[k] != 0.f) b2_red_add(gw + k, sgw[k]);
+  if (gb != nullptr) {
+    const float t = b2_block_sum(gb_acc, red);
+    if (threadIdx.x == 0 && t != 0.f) b2_red_add(gb, t);
+  }
+}
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------
@@ -470,9 +605,9 @@ extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, in
   }
   tc::Params p;
   const int nseg = (a_small != nullptr) ? 3 : 1;
-  const float* as[3] = {a, a, a_small};   // A_big.B_big, A_big.B_small, A_small.B_big
-  const float* bs[3] = {b, b_small, b};
-  for (int s = 0; s < nseg; ++s) {
+  const float* as[2] = {a, a_small};
+  const float* bs[2] = {b, b_small};
+  for (int s = 0; s < (nseg > 1 ? 2 : 1); ++s) {
     int rc = encode_kmajor(&p.map_a[s], as[s], M, K, lda, tc::BM);
     if (rc != B2_OK) return rc;
     rc = encode_kmajor(&p.map_b[s], bs[s], N, K, ldb, best_bn);
@@ -501,11 +636,11 @@ extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, in
     cudaError_t e = cudaMemset2DAsync(c, (size_t) ldc * 4, 0, (size_t) N * 4, (size_t) M, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
-  const size_t smem = (size_t) tc::STAGES * (tc::A_BYTES + (size_t) best_bn * 128) + 1024 + 128;
+  const size_t smem = (nseg > 1 ? (size_t) 3 * 2 : (size_t) 4) * (tc::A_BYTES + (size_t) best_bn * 128) + 1024 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) (tc::STAGES * (tc::A_BYTES + 256 * 128) + 1024 + 128));
+                                         (int) (4 * (tc::A_BYTES + 256 * 128) + 1024 + 128));
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -535,5 +670,56 @@ extern "C" B2_API int b2_transpose_f32(const float* in, int64_t rows, int64_t co
   B2_REQUIRE(grid.y <= 65535, "too many rows for this launch geometry");
   tc::transpose_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(in, rows, cols, ld_in, out, ld_out, out_small);
   B2_CUDA_LAUNCH_CHECK("b2_transpose_f32");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_prep_operand(const float* x, const float* y, int act, int64_t R, int64_t C,
+                                      float* out, float* out_small, float* outT, float* outT_small,
+                                      float* colsum, void* stream) {
+  B2_REQUIRE(x != nullptr, "NULL input");
+  B2_REQUIRE(R >= 0 && C >= 0, "bad shape");
+  B2_REQUIRE(act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad activation code %d", act);
+  cudaStream_t st = (cudaStream_t) stream;
+  if (colsum != nullptr) {
+    cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t) C, st);
+    if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_prep_operand: memset: %s", cudaGetErrorString(e));
+  }
+  if (R == 0 || C == 0) return B2_OK;
+  dim3 grid((unsigned) b2_ceil_div(C, 32), (unsigned) b2_ceil_div(R, 32));
+  B2_REQUIRE(grid.y <= 65535, "too many rows for this launch geometry");
+  tc::prep_operand_kernel<<<grid, 256, 0, st>>>(x, y, act, R, C, C, out, out_small, outT, outT_small, colsum);
+  B2_CUDA_LAUNCH_CHECK("b2_prep_operand");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_head_fwd(const float* x, const float* w, const float* b, int64_t M, int K, int act,
+                                  float* y, void* stream) {
+  B2_REQUIRE(x && w && y, "NULL pointer");
+  B2_REQUIRE(K >= 1 && act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad K/act");
+  if (M <= 0) return B2_OK;
+  int64_t blocks = b2_ceil_div(M * 32, 256);
+  if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
+  tc::head_fwd_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(x, w, b, M, K, act, y);
+  B2_CUDA_LAUNCH_CHECK("b2_head_fwd");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_head_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M,
+                                  int K, int act, float* gx, float* gw, float* gb, void* stream) {
+  B2_REQUIRE(x && w && gy && gw, "NULL pointer");
+  B2_REQUIRE(K >= 1 && K <= 12288 && act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad K/act");
+  B2_REQUIRE(act == B2_ACT_NONE || y != nullptr, "activation backward needs y");
+  cudaStream_t st = (cudaStream_t) stream;
+  cudaError_t e = cudaMemsetAsync(gw, 0, sizeof(float) * (size_t) K, st);
+  if (e == cudaSuccess && gb != nullptr) e = cudaMemsetAsync(gb, 0, sizeof(float), st);
+  if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_head_bwd: memset: %s", cudaGetErrorString(e));
+  if (M <= 0) return B2_OK;
+  int64_t ctas = 2 * B2_NUM_SMS;
+  if (ctas > b2_ceil_div(M, 8)) ctas = b2_ceil_div(M, 8);
+  const int64_t rows_per_cta = b2_ceil_div(M, ctas);
+  ctas = b2_ceil_div(M, rows_per_cta);
+  tc::head_bwd_kernel<<<(int) ctas, 256, sizeof(float) * (size_t) K, st>>>(x, w, (act == B2_ACT_NONE) ? nullptr : y,
+                                                                         gy, M, K, act, rows_per_cta, gx, gw, gb);
+  B2_CUDA_LAUNCH_CHECK("b2_head_bwd");
   return B2_OK;
 }

@@ -424,20 +424,59 @@ def gemm_nt(a, b, out, bias=None, act=B2_ACT_NONE, mul=None, add=None, accumulat
     return out
 
 
+def prep_operand(x, y=None, act=B2_ACT_NONE, want_out=False, want_small=False, want_t=False,
+                 want_t_small=False, colsum=None):
+    """One pass over x (R, C): [act-backward with y] -> out / out_small / out^T / out^T_small / column sums."""
+    R, C = x.shape
+    dev = x.device
+    out = torch.empty((R, C), dtype=torch.float32, device=dev) if want_out else None
+    small = torch.empty((R, C), dtype=torch.float32, device=dev) if want_small else None
+    out_t = torch.empty((C, R), dtype=torch.float32, device=dev) if want_t else None
+    t_small = torch.empty((C, R), dtype=torch.float32, device=dev) if want_t_small else None
+    _lib.call("b2_prep_operand", _ptr(x), _ptr(y), act, R, C, _ptr(out), _ptr(small), _ptr(out_t), _ptr(t_small),
+              _ptr(colsum), _stream())
+    return out, small, out_t, t_small
+
+
 class _LinearAct(torch.autograd.Function):
-    """y = act(x W^T + b): nn.Linear (+ReLU/Sigmoid) of MLP_Block (mlp_block.py:74-80)."""
+    """y = act(x W^T + b): nn.Linear (+ReLU/Sigmoid) of MLP_Block (mlp_block.py:74-80).
+
+    Three arithmetic paths: the N = 1 output head (GEMV kernels), the tcgen05 tensor-core GEMM
+    (TF32 / 3xTF32; operands are prepared K-major by ONE b2_prep_operand pass each), and the fp32
+    SIMT GEMM.  The backward fuses activation-backward, the transposes/splits and the bias gradient
+    into a single pass over dY."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         x = _f32c(x)
         M, K = x.shape
         N = weight.shape[0]
+        mode = _MATMUL["mode"]
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        gemm_nt(x, weight, y, bias=bias, act=act)
-        ctx.act = act
+        ctx.act, ctx.bias, ctx.has_bias = act, bias, bias is not None
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)
+        if N == 1 and weight.is_contiguous():
+            ctx.kind = "head"
+            _lib.call("b2_head_fwd", _ptr(x), _ptr(weight), _ptr(bias), M, K, act, _ptr(y), _stream())
+            ctx.save_for_backward(x, weight, y if act != B2_ACT_NONE else None)
+            return y
+        tc = (mode != "fp32" and N >= 16 and K >= 16 and N % 4 == 0 and K % 4 == 0 and M % 4 == 0
+              and _tc_operand_ok(x) and weight.is_contiguous() and weight.data_ptr() % 16 == 0)
+        if tc:
+            ctx.kind = "tc"
+            x3 = mode == "tf32x3"
+            # one pass per operand: 3xTF32 small parts now, K-major transposes for the backward
+            _, w_small, w_t, w_t_small = prep_operand(weight, want_small=x3, want_t=need_grad,
+                                                      want_t_small=need_grad and x3)
+            _, x_small, x_t, x_t_small = prep_operand(x, want_small=x3, want_t=need_grad,
+                                                      want_t_small=need_grad and x3)
+            gemm_nt(x, weight, y, bias=bias, act=act, a_small=x_small, b_small=w_small)
+            ctx.extra = (w_t, w_t_small, x_t, x_t_small)
+            ctx.save_for_backward(x, weight, y if act != B2_ACT_NONE else None)
+            return y
+        ctx.kind = "simt"
+        gemm_f32(x, weight, y, b_t=True, bias=bias, act=act)
         ctx.save_for_backward(x, weight, y if act != B2_ACT_NONE else None)
-        ctx.has_bias = bias is not None
-        ctx.bias = bias
         return y
 
     @staticmethod
@@ -446,34 +485,51 @@ class _LinearAct(torch.autograd.Function):
         gy = _f32c(gy)
         M, K = x.shape
         N = weight.shape[0]
-        if ctx.act != B2_ACT_NONE:
-            gz = torch.empty_like(gy)
-            _lib.call("b2_act_bwd", _ptr(y), _ptr(gy), _ptr(gz), gy.numel(), ctx.act, _stream())
-        else:
-            gz = gy
-        mode = _MATMUL["mode"]
-        # tensor-core path needs K-major operands: dgrad contracts over N, wgrad over M
-        tc = mode != "fp32" and N % 4 == 0 and M % 4 == 0 and K % 4 == 0 and N >= 16 and K >= 16
-        x3 = mode == "tf32x3"
+        act = ctx.act
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = torch.empty((M, K), dtype=torch.float32, device=x.device)
-            if tc:
-                wt, wt_small = transpose_f32(weight, x3)                      # (K, N)
-                gemm_nt(gz, wt, gx, b_small=wt_small)                         # dX = dZ W
-            else:
-                gemm_f32(gz, weight, gx)
-        if ctx.needs_input_grad[1]:
+        if ctx.kind == "head":
+            gx = torch.empty((M, K), dtype=torch.float32, device=x.device) if need_x else None
             gw = _grad_buffer(weight, zero=False)
-            if tc:
-                gzt, gzt_small = transpose_f32(gz, x3)                        # (N, M)
-                xt, xt_small = transpose_f32(x, x3)                           # (K, M)
-                gemm_nt(gzt, xt, gw, a_small=gzt_small, b_small=xt_small)     # dW = dZ^T X
-            else:
-                gemm_f32(gz, x, gw, a_t=True)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = _grad_buffer(ctx.bias, zero=False)
-            _lib.call("b2_colsum", _ptr(gz), M, N, gz.stride(0), _ptr(gb), 0, _stream())
+            gb = _grad_buffer(ctx.bias, zero=False) if need_b else None
+            _lib.call("b2_head_bwd", _ptr(x), _ptr(weight), _ptr(y), _ptr(gy), M, K, act, _ptr(gx), _ptr(gw),
+                      _ptr(gb), _stream())
+            return gx, gw, gb, None
+        gb = _grad_buffer(ctx.bias, zero=False) if need_b else None
+        if ctx.kind == "tc":
+            x3 = _MATMUL["mode"] == "tf32x3"
+            w_t, w_t_small, x_t, x_t_small = ctx.extra
+            if w_t is None:   # forward ran without grad bookkeeping (should not happen under autograd)
+                _, _, w_t, w_t_small = prep_operand(weight, want_t=True, want_t_small=x3)
+                _, _, x_t, x_t_small = prep_operand(x, want_t=True, want_t_small=x3)
+            fused = act != B2_ACT_NONE
+            # dZ = act'(Y) * dY, its small part, its transpose (+small) and the bias gradient: one pass
+            gz, gz_small, gz_t, gz_t_small = prep_operand(gy, y if fused else None, act, want_out=fused,
+                                                          want_small=x3 and need_x, want_t=need_w,
+                                                          want_t_small=x3 and need_w, colsum=gb)
+            if not fused:
+                gz = gy
+            if need_x:
+                gx = torch.empty((M, K), dtype=torch.float32, device=x.device)
+                gemm_nt(gz, w_t, gx, a_small=gz_small, b_small=w_t_small)            # dX = dZ W
+            if need_w:
+                gw = _grad_buffer(weight, zero=False)
+                gemm_nt(gz_t, x_t, gw, a_small=gz_t_small, b_small=x_t_small)        # dW = dZ^T X
+            return gx, gw, gb, None
+        # fp32 SIMT path
+        fused = act != B2_ACT_NONE
+        gz = gy
+        if fused or gb is not None:
+            out, _, _, _ = prep_operand(gy, y if fused else None, act, want_out=fused, colsum=gb)
+            if fused:
+                gz = out
+        if need_x:
+            gx = torch.empty((M, K), dtype=torch.float32, device=x.device)
+            gemm_f32(gz, weight, gx)
+        if need_w:
+            gw = _grad_buffer(weight, zero=False)
+            gemm_f32(gz, x, gw, a_t=True)
         return gx, gw, gb, None
 
 

@@ -303,6 +303,23 @@ B2_API int b2_split_tf32(const float* x, float* small, int64_t n, void* stream);
 B2_API int b2_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
                             int64_t ld_out, float* out_small, void* stream);
 
+/*
+ * One-pass operand preparation for the K-major tensor-core GEMMs over x (R, C):
+ *   v = act'(y) * x when y != NULL (y = activation OUTPUT; fuses the activation backward)
+ *   out (R,C) = v, out_small = 3xTF32 small part, outT (C,R) = v^T, outT_small, colsum[c] = sum_r v[r,c]
+ * Every output may be NULL.  Replaces b2_act_bwd + b2_transpose_f32 + b2_split_tf32 + b2_colsum.
+ */
+B2_API int b2_prep_operand(const float* x, const float* y, int act, int64_t R, int64_t C, float* out,
+                           float* out_small, float* outT, float* outT_small, float* colsum, void* stream);
+/*
+ * The N = 1 output head of MLP_Block (Linear(K, 1), mlp_block.py:82): warp-per-row GEMV forward,
+ * y[m] = act(<x[m,:], w> + b); and one fused backward: gz = act'(y)*gy, gx[m,:] = gz[m]*w (gx may
+ * be NULL), gw (K) = sum_m gz[m]*x[m,:], gb (1) = sum_m gz[m]  ("=" semantics).
+ */
+B2_API int b2_head_fwd(const float* x, const float* w, const float* b, int64_t M, int K, int act, float* y,
+                       void* stream);
+B2_API int b2_head_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M, int K,
+                       int act, float* gx, float* gw, float* gb, void* stream);
 /* Elementwise helpers used by the dense backward.
  * b2_act_bwd: gx = gy * act'(y) where y is the activation OUTPUT (relu, sigmoid). */
 B2_API int b2_act_bwd(const float* y, const float* gy, float* gx, int64_t n, int act, void* stream);
