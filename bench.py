@@ -261,6 +261,20 @@ def kernel_rooflines(model, fm, dev_batch, peaks, args, with_gather=True):
                          "frac_of_measured_hbm": sbytes / ms / 1e6 / hbm}
     a.P.copy_(backup[0]); opt.M.copy_(backup[1]); opt.V.copy_(backup[2]); a.G.copy_(backup[3])
     opt.step_dev.sub_(1)
+    # the tensor-core GEMM of the first MLP layer (4096 x 300 x 624), the most frequent kernel of the step
+    mode = F2.get_matmul_precision()
+    if mode != "fp32":
+        M_, N_, K_ = B, HIDDEN[0], NF * DIM
+        xa = torch.randn(M_, K_, device="cuda"); wb = torch.randn(N_, K_, device="cuda")
+        yo = torch.empty(M_, N_, device="cuda")
+        xs = F2.split_tf32(xa) if mode == "tf32x3" else None
+        ws = F2.split_tf32(wb) if mode == "tf32x3" else None
+        ms = time_kernel(lambda: F2.gemm_nt(xa, wb, yo, a_small=xs, b_small=ws), 30, None)
+        flops = 2.0 * M_ * N_ * K_ * (3 if mode == "tf32x3" else 1)
+        tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0       # dense TF32 = half the measured bf16 rate
+        out["gemm_tf32"] = {"ms": ms, "shape": [M_, N_, K_], "passes": 3 if mode == "tf32x3" else 1,
+                            "TFLOPs": flops / ms / 1e9, "frac_of_tf32_peak": flops / ms / 1e9 / tf32_peak,
+                            "note": "launch + L2->SM operand traffic bound at this size (128 CTAs, 20 k-blocks each)"}
     return out
 
 
@@ -293,8 +307,9 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as fd:
             p = json.load(fd)
-        return {"hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops", 1590.0)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 def run_b200_arm(args):

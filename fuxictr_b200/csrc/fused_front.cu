@@ -19,9 +19,10 @@
 #include "embed_common.cuh"
 
 namespace {
-constexpr int MAX_PASSES = 8;  // F <= MAX_PASSES * (32 / LPR) per chunk of the pass loop
 
-template <typename IdxT>
+// MAX_PASSES: rows of one sample handled per chunk of the pass loop = MAX_PASSES * (32 / LPR);
+// a smaller value keeps the register arrays (and so the occupancy) matched to the field count.
+template <typename IdxT, int MAX_PASSES>
 __global__ void __launch_bounds__(256)
 front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant__ B2FieldPack lr,
                  int64_t batch, int dim, int lpr_log2, int has_lr, int want_fm,
@@ -206,8 +207,13 @@ int launch_front_fwd(const B2FieldPack& emb, const B2FieldPack& lr, int64_t batc
   int lpr_log2 = next_pow2_log2((dim + 3) / 4);
   const size_t smem = ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15) + pack_smem_bytes(emb.nfields) + 16;
   const int grid = grid_for(batch * 32, 256);
-  front_fwd_kernel<IdxT><<<grid, 256, smem, st>>>(emb, lr, batch, dim, lpr_log2, has_lr, want_fm, bias,
-                                                 logit_out, sum_out, status);
+  const int passes = (emb.nfields + (32 >> lpr_log2) - 1) / (32 >> lpr_log2);
+  if (passes <= 2)
+    front_fwd_kernel<IdxT, 2><<<grid, 256, smem, st>>>(emb, lr, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
+  else if (passes <= 5)
+    front_fwd_kernel<IdxT, 5><<<grid, 256, smem, st>>>(emb, lr, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
+  else
+    front_fwd_kernel<IdxT, 8><<<grid, 256, smem, st>>>(emb, lr, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
   B2_CUDA_LAUNCH_CHECK("b2_front_fwd");
   return B2_OK;
 }
