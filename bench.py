@@ -339,8 +339,15 @@ def run_b200_arm(args):
     model = zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
     sharded = world > 1 and not args.dp_only
     if sharded:
-        from fuxictr_b200.sharded import SymmPeerGroup
-        model.enable_sharding(SymmPeerGroup(), args.batch, NF + 1, torch.float64)
+        try:
+            from fuxictr_b200.sharded import SymmPeerGroup
+            model.enable_sharding(SymmPeerGroup(), args.batch, NF + 1, torch.float64)
+        except Exception as exc:   # no peer-mapped memory on this box: replicated tables + arena all-reduce
+            sys.stderr.write("[bench r%d] row-sharding unavailable (%r); using --dp-only\n" % (rank, exc))
+            sharded = False
+            args.dp_only = True
+            torch.manual_seed(2019)
+            model = zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
     opt = model.use_fused_optimizer()
     if world > 1 and not sharded:
         opt.grad_allreduce = True
