@@ -58,7 +58,10 @@ class ParamArena(object):
             self.tail_offset = off
         self.numel = off
         self.P = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.G = torch.zeros(off, dtype=torch.float32, device=dev)
+        # 4 spare floats behind the gradient arena: the sharded optimizer parks the local sum of
+        # squares there so that ONE all-reduce carries the dense gradients and the norm term
+        self._G_ext = torch.zeros(off + 4, dtype=torch.float32, device=dev)
+        self.G = self._G_ext[:off]
         self.params = uniq
         self.step_id = 0
         self.grads_are_zero = True
@@ -132,17 +135,19 @@ class FusedAdam(object):
         if self.sharded:
             import torch.distributed as dist
             world = dist.get_world_size()
+            slot = a._G_ext[a.numel:a.numel + 1]               # rides behind the dense slice
+            slot.zero_()
+            if self.max_norm is not None and a.tail_offset > 0:
+                _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr()), a.tail_offset,
+                          ctypes.c_void_p(slot.data_ptr()), st)   # this rank's shard part of ||g||^2
+            # ONE collective: dense gradients (to be averaged) + the shard norm term (to be summed)
+            dist.all_reduce(a._G_ext[a.tail_offset:a.numel + 1], op=dist.ReduceOp.SUM)
             dense = a.G[a.tail_offset:]
             if dense.numel() > 0:
-                dist.all_reduce(dense, op=dist.ReduceOp.SUM)     # dense grads: mean over the global batch
-                dense.mul_(1.0 / world)
+                dense.mul_(1.0 / world)                          # mean over the global batch
             if self.max_norm is not None:
                 # global norm^2 = sum over ranks of the shard parts + the (replicated) dense part once
-                self.sumsq.zero_()
-                if a.tail_offset > 0:
-                    _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr()), a.tail_offset,
-                              ctypes.c_void_p(self.sumsq.data_ptr()), st)
-                dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM)
+                self.sumsq.copy_(slot.view(()))
                 if dense.numel() > 0:
                     _lib.call("b2_sumsq", ctypes.c_void_p(dense.data_ptr()), dense.numel(),
                               ctypes.c_void_p(self.sumsq.data_ptr()), st)

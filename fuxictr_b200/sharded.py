@@ -170,7 +170,9 @@ class ShardedFront(object):
 
     def phase_reduce(self):
         """Local: logit (B,1) and field sums from the landed rows.  Returns (emb copy, logit, sums)."""
-        emb = self.emb.clone()           # the peer buffer is overwritten by the next step's pushes
+        # The landed rows are consumed in place: the next overwrite of this peer buffer is the NEXT
+        # step's push, which is ordered after this step's backward (and its closing barrier).
+        emb = self.emb
         logit = torch.empty((self.B, 1), dtype=torch.float32, device="cuda")
         sums = torch.empty((self.B, self.dim), dtype=torch.float32, device="cuda") if self.want_fm else None
         _lib.call("b2_front_reduce", F2._ptr(emb), F2._ptr(self.lrw) if self.lr_tables else None,
