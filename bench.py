@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--nbatches", type=int, default=8, help="distinct synthetic batches rotated through")
     ap.add_argument("--dp-only", action="store_true",
                     help="N>1: replicate the tables and all-reduce the whole gradient arena instead of row-sharding")
+    ap.add_argument("--lazy-adam", type=int, default=0,
+                    help="1: evaluate the dense Adam semantics of the tables row-wise and lazily (bit-identical)")
     ap.add_argument("--steps-only", action="store_true", help="skip the per-kernel / stress / CPU legs (profiling)")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the dense GEMMs: fp32 FFMA, 3xTF32 (fp32-class) or 1xTF32 on tcgen05")
@@ -348,7 +350,7 @@ def run_b200_arm(args):
             args.dp_only = True
             torch.manual_seed(2019)
             model = zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
-    opt = model.use_fused_optimizer()
+    opt = model.use_fused_optimizer(lazy_tables=bool(args.lazy_adam) and world == 1)
     if world > 1 and not sharded:
         opt.grad_allreduce = True
     model.train()
@@ -478,7 +480,9 @@ def run_b200_arm(args):
             "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core GEMMs, fp32 everything else)",
                       "tf32": "tf32 GEMMs, f32 elsewhere"}[args.precision],
-            "data": "synthetic", "config": dict(workload_config(args, world), matmul=args.precision),
+            "data": "synthetic", "config": dict(workload_config(args, world), matmul=args.precision,
+                                             adam=("dense semantics, lazy row-wise evaluation" if args.lazy_adam and world == 1
+                                                   else "dense pass over the arena")),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": host_batches[0].numel() * 8 * world, "d2h_bytes_per_step": 4 * world},

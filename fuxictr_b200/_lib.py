@@ -22,6 +22,24 @@ c_void_p, c_int, c_int32, c_int64, c_float = (ctypes.c_void_p, ctypes.c_int, cty
                                               ctypes.c_int64, ctypes.c_float)
 
 
+class b2_lazy_ctx(ctypes.Structure):
+    """struct b2_lazy_ctx of include/fuxictr_b200.h."""
+    _fields_ = [
+        ("last_step", ctypes.c_void_p), ("sched", ctypes.c_void_p), ("step_dev", ctypes.c_void_p),
+        ("mark", ctypes.c_void_p), ("worklist", ctypes.c_void_p), ("counter", ctypes.c_void_p),
+        ("delta_m", ctypes.c_int64), ("delta_v", ctypes.c_int64),
+        ("w1", ctypes.c_float), ("beta2", ctypes.c_float), ("w2", ctypes.c_float), ("eps", ctypes.c_float),
+        ("worklist_capacity", ctypes.c_int32), ("pad_", ctypes.c_int32),
+        ("grow_emb", ctypes.c_int64 * 128), ("grow_lr", ctypes.c_int64 * 128),
+    ]
+
+
+class b2_lazy_table(ctypes.Structure):
+    """struct b2_lazy_table of include/fuxictr_b200.h (32 bytes)."""
+    _fields_ = [("param", ctypes.c_void_p), ("rows", ctypes.c_int64), ("grow_base", ctypes.c_int64),
+                ("dim", ctypes.c_int32), ("pad_", ctypes.c_int32)]
+
+
 class b2_field(ctypes.Structure):
     """struct b2_field of include/fuxictr_b200.h (64 bytes)."""
     _fields_ = [
@@ -44,9 +62,17 @@ SIGNATURES = {
     "b2_lr_fwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2_lr_bwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_front_fwd": (c_int, [_FIELD_P, _FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                             c_void_p, c_void_p]),
-    "b2_front_bwd": (c_int, [_FIELD_P, _FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
+    "b2_front_bwd": (c_int, [_FIELD_P, _FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2_lazy_sumsq": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "b2_lazy_adam_step": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p]),
+    "b2_lazy_materialize": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_float, c_float, c_float, c_void_p]),
+    "b2_adam_sched": (c_int, [c_void_p, c_float, c_float, c_float, c_void_p, c_int64, c_void_p]),
+    "b2_adam_step_sched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
+                                   c_float, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "b2_shard_push": (c_int, [_FIELD_P, _FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_int64,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2_shard_pull": (c_int, [_FIELD_P, _FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_int64,

@@ -89,6 +89,69 @@ class ParamArena(object):
         self.G.zero_()
 
 
+class LazyTables(object):
+    """Bookkeeping of the lazily evaluated tables (see b2_lazy_ctx in include/fuxictr_b200.h):
+    per-row `last_step`, the per-step worklist, the schedule table shared with the dense pass."""
+
+    SCHED_LEN = 1 << 20   # optimizer steps the schedule table can hold
+
+    def __init__(self, arena, tables):
+        self.arena = arena
+        self.tables = list(tables)
+        dev = arena.P.device
+        base = 0
+        descs = (_lib.b2_lazy_table * len(self.tables))()
+        for d, p in zip(descs, self.tables):
+            if p.dim() != 2 or getattr(p, "_b2_slot", None) is None:
+                raise ValueError("lazy tables must be 2-D parameters living in the arena")
+            p._b2_lazy, p._b2_grow_base = self, base
+            d.param, d.rows, d.grow_base, d.dim = p.data_ptr(), p.shape[0], base, p.shape[1]
+            base += p.shape[0]
+        self.total_rows = base
+        raw = bytes(descs)
+        self.tables_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self.last_step = torch.zeros(base, dtype=torch.int32, device=dev)
+        self.mark = torch.zeros(base, dtype=torch.int32, device=dev)
+        self.capacity = base
+        self.worklist = torch.zeros(base, dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sched = torch.zeros((self.SCHED_LEN, 2), dtype=torch.float32, device=dev)
+        self.opt = None
+        self._ctx_cache = {}
+
+    def ctx_for(self, plan, lr_plan, emb_tables, lr_tables):
+        key = (id(plan), id(lr_plan))
+        ctx = self._ctx_cache.get(key)
+        if ctx is None:
+            opt, a = self.opt, self.arena
+            ctx = _lib.b2_lazy_ctx()
+            ctx.last_step, ctx.sched = self.last_step.data_ptr(), self.sched.data_ptr()
+            ctx.step_dev, ctx.mark = opt.step_dev.data_ptr(), self.mark.data_ptr()
+            ctx.worklist, ctx.counter = self.worklist.data_ptr(), self.counter.data_ptr()
+            ctx.delta_m = (opt.M.data_ptr() - a.P.data_ptr()) // 4
+            ctx.delta_v = (opt.V.data_ptr() - a.P.data_ptr()) // 4
+            ctx.w1, ctx.beta2 = 1.0 - opt.betas[0], opt.betas[1]
+            ctx.w2, ctx.eps = 1.0 - opt.betas[1], opt.eps
+            ctx.worklist_capacity = self.capacity
+            for i, f in enumerate(plan.fields):
+                ctx.grow_emb[i] = emb_tables[f.table_slot]._b2_grow_base
+            if lr_plan is not None:
+                for i, f in enumerate(lr_plan.fields):
+                    ctx.grow_lr[i] = lr_tables[f.table_slot]._b2_grow_base
+            self._ctx_cache[key] = ctx
+        return ctx
+
+    def materialize(self):
+        """Bring every row up to date (before reading the tables outside the kernels)."""
+        opt, a = self.opt, self.arena
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.call("b2_lazy_materialize", ctypes.c_void_p(self.tables_dev.data_ptr()), len(self.tables),
+                  self.total_rows, (opt.M.data_ptr() - a.P.data_ptr()) // 4,
+                  (opt.V.data_ptr() - a.P.data_ptr()) // 4, ctypes.c_void_p(self.last_step.data_ptr()),
+                  ctypes.c_void_p(self.sched.data_ptr()), ctypes.c_void_p(opt.step_dev.data_ptr()),
+                  opt.betas[0], opt.betas[1], opt.eps, st)
+
+
 class FusedAdam(object):
     """clip_grad_norm_(max_norm) + Adam over a ParamArena, two kernels per step.
 
@@ -107,11 +170,22 @@ class FusedAdam(object):
         self.step_dev = torch.zeros((), dtype=torch.int64, device=dev)
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.zero_grad_in_step = zero_grad_in_step
+        self.lazy = None             # LazyTables: tables in G[:tail_offset] are updated row-wise, exactly
+        self.sched = torch.zeros((LazyTables.SCHED_LEN, 2), dtype=torch.float32, device=dev)
         self.grad_allreduce = False  # data-parallel replicas: average G across ranks before the step
         self.sharded = False         # row-sharded tables in G[:tail_offset], replicated dense params after
 
+    def enable_lazy(self, tables):
+        """Evaluate the dense Adam semantics of `tables` (the arena's leading parameters) lazily."""
+        self.lazy = LazyTables(self.arena, tables)
+        self.lazy.opt = self
+        self.lazy.sched = self.sched          # one schedule table for the dense and the lazy kernels
+        return self.lazy
+
     def zero_grad(self, set_to_none=True):
         self.arena.begin_step(grads_zeroed=self.zero_grad_in_step and self._stepped)
+        if self.lazy is not None:
+            self.lazy.counter.zero_()
 
     _stepped = False
 
@@ -154,12 +228,39 @@ class FusedAdam(object):
                 sumsq_ptr = ctypes.c_void_p(self.sumsq.data_ptr())
         elif self.max_norm is not None:
             self.sumsq.zero_()
-            _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr()), a.numel,
-                      ctypes.c_void_p(self.sumsq.data_ptr()), st)
+            if self.lazy is not None:
+                lz = self.lazy
+                dg = (a.G.data_ptr() - a.P.data_ptr()) // 4
+                _lib.call("b2_lazy_sumsq", ctypes.c_void_p(lz.tables_dev.data_ptr()), len(lz.tables),
+                          ctypes.c_void_p(lz.worklist.data_ptr()), ctypes.c_void_p(lz.counter.data_ptr()),
+                          lz.capacity, dg, ctypes.c_void_p(self.sumsq.data_ptr()), st)
+                if a.numel > a.tail_offset:
+                    _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr() + 4 * a.tail_offset),
+                              a.numel - a.tail_offset, ctypes.c_void_p(self.sumsq.data_ptr()), st)
+            else:
+                _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr()), a.numel,
+                          ctypes.c_void_p(self.sumsq.data_ptr()), st)
             sumsq_ptr = ctypes.c_void_p(self.sumsq.data_ptr())
-        _lib.call("b2_adam_step", ctypes.c_void_p(a.P.data_ptr()), ctypes.c_void_p(a.G.data_ptr()),
-                  ctypes.c_void_p(self.M.data_ptr()), ctypes.c_void_p(self.V.data_ptr()), a.numel,
-                  sumsq_ptr, float(self.max_norm or 0.0), self.lr, self.betas[0], self.betas[1],
-                  self.eps, ctypes.c_void_p(self.step_dev.data_ptr()),
-                  1 if self.zero_grad_in_step else 0, st)
+        vp = ctypes.c_void_p
+        _lib.call("b2_adam_sched", vp(self.step_dev.data_ptr()), self.lr, self.betas[0], self.betas[1],
+                  vp(self.sched.data_ptr()), self.sched.shape[0], st)
+        lo = 0
+        if self.lazy is not None:
+            # tables: only the rows this step touched (missed zero-gradient steps are replayed)
+            lz = self.lazy
+            lo = a.tail_offset
+            dg = (a.G.data_ptr() - a.P.data_ptr()) // 4
+            dm = (self.M.data_ptr() - a.P.data_ptr()) // 4
+            dv = (self.V.data_ptr() - a.P.data_ptr()) // 4
+            _lib.call("b2_lazy_adam_step", vp(lz.tables_dev.data_ptr()), len(lz.tables), vp(lz.worklist.data_ptr()),
+                      vp(lz.counter.data_ptr()), lz.capacity, dg, dm, dv, vp(lz.last_step.data_ptr()),
+                      vp(self.sched.data_ptr()), vp(self.step_dev.data_ptr()), sumsq_ptr,
+                      float(self.max_norm or 0.0), self.betas[0], self.betas[1], self.eps, st)
+        n = a.numel - lo
+        if n > 0:
+            _lib.call("b2_adam_step_sched", vp(a.P.data_ptr() + 4 * lo), vp(a.G.data_ptr() + 4 * lo),
+                      vp(self.M.data_ptr() + 4 * lo), vp(self.V.data_ptr() + 4 * lo), n, sumsq_ptr,
+                      float(self.max_norm or 0.0), self.betas[0], self.betas[1], self.eps,
+                      vp(self.step_dev.data_ptr()), vp(self.sched.data_ptr()),
+                      1 if self.zero_grad_in_step else 0, st)
         self._stepped = True

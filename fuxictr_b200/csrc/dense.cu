@@ -11,6 +11,7 @@
 // same arithmetic class as the reference's ATen addmm.  The tensor-core (tcgen05)
 // GEMM for the bf16 throughput path lives in gemm_tc.cu.
 #include "b2_common.cuh"
+#include "adam_common.cuh"
 
 // ---------------------------------------------------------------------------------
 // SIMT SGEMM, 64x64x16 tile, 256 threads, 4x4 micro-tile, register-prefetched double
@@ -377,44 +378,50 @@ extern "C" B2_API int b2_sumsq(const float* g, int64_t n, float* out, void* stre
   return B2_OK;
 }
 
-struct AdamScalars {
-  float clip, w1, b2, w2, step_size, inv_bc2_sqrt, eps;
-};
-
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v,
-                                         const AdamScalars& s) {
-  g *= s.clip;                      // clip_grad_norm_: g.mul_(clip_coef_clamped)
-  m = m + (g - m) * s.w1;           // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * s.b2 + (s.w2 * g) * g;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
-  const float denom = sqrtf(v) * s.inv_bc2_sqrt + s.eps;
-  p = p - s.step_size * (m / denom);  // param.addcdiv_(exp_avg, denom, value=-step_size)
+// sched[step] is written first so that the dense pass and every later lazy catch-up of the same
+// step read the SAME two scalars.
+__global__ void adam_sched_kernel(const int64_t* __restrict__ step_dev, float lr, float beta1, float beta2,
+                                  B2AdamSched* __restrict__ sched, int64_t sched_len) {
+  const int64_t t = *step_dev;
+  if (t < 1 || t >= sched_len) return;
+  const double bc1 = 1.0 - pow((double) beta1, (double) t);
+  const double bc2 = 1.0 - pow((double) beta2, (double) t);
+  sched[t] = make_float2((float) ((double) lr / bc1), (float) (1.0 / sqrt(bc2)));
 }
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, const float* __restrict__ sumsq, float max_norm,
             float lr, float beta1, float beta2, float eps, const int64_t* __restrict__ step_dev,
-            int zero_grad) {
-  __shared__ AdamScalars sc;
+            int zero_grad, const B2AdamSched* __restrict__ sched) {
+  __shared__ B2AdamConst sc;
+  __shared__ float s_clip, s_step, s_ibc2;
   if (threadIdx.x == 0) {
-    const double step = (double) *step_dev;
-    const double bc1 = 1.0 - pow((double) beta1, step);
-    const double bc2 = 1.0 - pow((double) beta2, step);
+    const int64_t t = *step_dev;
     float clip = 1.f;
     if (sumsq != nullptr) {
       const float total_norm = sqrtf(*sumsq);
       clip = fminf(max_norm / (total_norm + 1e-6f), 1.f);
     }
-    sc.clip = clip;
+    s_clip = clip;
     sc.w1 = (float) (1.0 - (double) beta1);
     sc.b2 = beta2;
     sc.w2 = (float) (1.0 - (double) beta2);
-    sc.step_size = (float) ((double) lr / bc1);
-    sc.inv_bc2_sqrt = (float) (1.0 / sqrt(bc2));
     sc.eps = eps;
+    if (sched != nullptr) {
+      const B2AdamSched e = sched[t];
+      s_step = e.x;
+      s_ibc2 = e.y;
+    } else {
+      const double bc1 = 1.0 - pow((double) beta1, (double) t);
+      const double bc2 = 1.0 - pow((double) beta2, (double) t);
+      s_step = (float) ((double) lr / bc1);
+      s_ibc2 = (float) (1.0 / sqrt(bc2));
+    }
   }
   __syncthreads();
-  const AdamScalars s = sc;
+  const B2AdamConst c = sc;
+  const float clip = s_clip, step_size = s_step, ibc2 = s_ibc2;
   const int64_t n4 = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
   float4* g4 = reinterpret_cast<float4*>(g);
@@ -423,17 +430,17 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t) gridDim.x * blockDim.x) {
     float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
-    adam_one(pp.x, gg.x, mm.x, vv.x, s);
-    adam_one(pp.y, gg.y, mm.y, vv.y, s);
-    adam_one(pp.z, gg.z, mm.z, vv.z, s);
-    adam_one(pp.w, gg.w, mm.w, vv.w, s);
+    b2_adam_apply(pp.x, __fmul_rn(gg.x, clip), mm.x, vv.x, c, step_size, ibc2);   // g.mul_(clip_coef) first
+    b2_adam_apply(pp.y, __fmul_rn(gg.y, clip), mm.y, vv.y, c, step_size, ibc2);
+    b2_adam_apply(pp.z, __fmul_rn(gg.z, clip), mm.z, vv.z, c, step_size, ibc2);
+    b2_adam_apply(pp.w, __fmul_rn(gg.w, clip), mm.w, vv.w, c, step_size, ibc2);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
     if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
     float pp = p[i], mm = m[i], vv = v[i];
-    adam_one(pp, g[i], mm, vv, s);
+    b2_adam_apply(pp, __fmul_rn(g[i], clip), mm, vv, c, step_size, ibc2);
     p[i] = pp; m[i] = mm; v[i] = vv;
     if (zero_grad) g[i] = 0.f;
   }
@@ -452,7 +459,34 @@ extern "C" B2_API int b2_adam_step(float* p, float* g, float* m, float* v, int64
   if (blocks < 1) blocks = 1;
   adam_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(p, g, m, v, n, sumsq, max_norm, lr,
                                                               beta1, beta2, eps, step_dev,
-                                                              zero_grad);
+                                                              zero_grad, nullptr);
   B2_CUDA_LAUNCH_CHECK("b2_adam_step");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_adam_sched(const int64_t* step_dev, float lr, float beta1, float beta2, float* sched,
+                                    int64_t sched_len, void* stream) {
+  B2_REQUIRE(step_dev && sched && sched_len >= 2, "NULL pointer / empty schedule table");
+  adam_sched_kernel<<<1, 1, 0, (cudaStream_t) stream>>>(step_dev, lr, beta1, beta2,
+                                                        reinterpret_cast<B2AdamSched*>(sched), sched_len);
+  B2_CUDA_LAUNCH_CHECK("b2_adam_sched");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_adam_step_sched(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq,
+                                         float max_norm, float beta1, float beta2, float eps,
+                                         const int64_t* step_dev, const float* sched, int zero_grad,
+                                         void* stream) {
+  B2_REQUIRE(p && g && m && v && step_dev && sched, "NULL pointer");
+  B2_REQUIRE((((uintptr_t) p | (uintptr_t) g | (uintptr_t) m | (uintptr_t) v) % 16) == 0,
+             "arenas must be 16-byte aligned");
+  if (n <= 0) return B2_OK;
+  int64_t blocks = b2_ceil_div(n >> 2, 256 * 2);
+  if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(p, g, m, v, n, sumsq, max_norm, 0.f, beta1, beta2,
+                                                              eps, step_dev, zero_grad,
+                                                              reinterpret_cast<const B2AdamSched*>(sched));
+  B2_CUDA_LAUNCH_CHECK("b2_adam_step_sched");
   return B2_OK;
 }

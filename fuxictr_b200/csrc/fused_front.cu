@@ -17,6 +17,7 @@
 // pass, ceil(F / (32/LPR)) passes with all index loads, then all row loads, in flight together;
 // field sums are xor-shuffle reductions over the (fields x emb_dim) register tile.
 #include "embed_common.cuh"
+#include "adam_common.cuh"
 
 namespace {
 
@@ -25,6 +26,7 @@ namespace {
 template <typename IdxT, int MAX_PASSES>
 __global__ void __launch_bounds__(256)
 front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant__ B2FieldPack lr,
+                 const __grid_constant__ b2_lazy_ctx lz, int lazy,
                  int64_t batch, int dim, int lpr_log2, int has_lr, int want_fm,
                  const float* __restrict__ bias, float* __restrict__ logit_out,
                  float* __restrict__ sum_out, int32_t* __restrict__ status) {
@@ -44,6 +46,11 @@ front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
   const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
   const float bv = (bias != nullptr) ? __ldg(bias) : 0.f;
+  // lazy tables: steps completed so far; a row with last_step < done replays the missed
+  // zero-gradient Adam updates in registers (never written back here)
+  const int done = lazy ? (int) *lz.step_dev : 0;
+  const B2AdamConst ac = {lz.w1, lz.beta2, lz.w2, lz.eps};
+  const B2AdamSched* sched = reinterpret_cast<const B2AdamSched*>(lz.sched);
 
   for (int64_t b = warp; b < batch; b += nwarps) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -75,6 +82,40 @@ front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
             v[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sf.f[f].table) +
                                                          row[u] * dim + e));
           if (has_lr && sub == 0) w[u] = __ldg(reinterpret_cast<const float*>(lf.f[f].table) + row[u]);
+        }
+      }
+      if (lazy) {
+#pragma unroll
+        for (int u = 0; u < MAX_PASSES; ++u) {
+          const int f = f0 + u * rows_per_pass + rg;
+          if (f < F && ok[u]) {
+            if (lane_on) {
+              const int last = __ldg(lz.last_step + lz.grow_emb[f] + row[u]);
+              if (last < done) {
+                const float* pp = reinterpret_cast<const float*>(sf.f[f].table) + row[u] * dim + e;
+                float4 m4 = *reinterpret_cast<const float4*>(pp + lz.delta_m);
+                float4 v4 = *reinterpret_cast<const float4*>(pp + lz.delta_v);
+                for (int k = last + 1; k <= done; ++k) {
+                  const B2AdamSched sc = sched[k];
+                  b2_adam_apply(v[u].x, 0.f, m4.x, v4.x, ac, sc.x, sc.y);
+                  b2_adam_apply(v[u].y, 0.f, m4.y, v4.y, ac, sc.x, sc.y);
+                  b2_adam_apply(v[u].z, 0.f, m4.z, v4.z, ac, sc.x, sc.y);
+                  b2_adam_apply(v[u].w, 0.f, m4.w, v4.w, ac, sc.x, sc.y);
+                }
+              }
+            }
+            if (has_lr && sub == 0) {
+              const int last = __ldg(lz.last_step + lz.grow_lr[f] + row[u]);
+              if (last < done) {
+                const float* pp = reinterpret_cast<const float*>(lf.f[f].table) + row[u];
+                float m1 = pp[lz.delta_m], v1 = pp[lz.delta_v];
+                for (int k = last + 1; k <= done; ++k) {
+                  const B2AdamSched sc = sched[k];
+                  b2_adam_apply(w[u], 0.f, m1, v1, ac, sc.x, sc.y);
+                }
+              }
+            }
+          }
         }
       }
 #pragma unroll
@@ -117,6 +158,7 @@ front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 front_bwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant__ B2FieldPack lr,
+                 const __grid_constant__ b2_lazy_ctx lz, int lazy,
                  int64_t batch, int dim, int lpr_log2, int has_lr, int want_fm,
                  const float* __restrict__ emb_saved, const float* __restrict__ gx_base,
                  const float* __restrict__ sums, const float* __restrict__ glogit,
@@ -140,6 +182,7 @@ front_bwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
   const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> lpr_log2;
   const int64_t warp_first = group - my_group;
   float gb_acc = 0.f;
+  const int tmark = lazy ? (int) *lz.step_dev + 1 : 0;   // the optimizer step this backward feeds
 
   for (int64_t wbase = warp_first; wbase < nitems; wbase += ngroups) {
     const int64_t item = wbase + my_group;
@@ -157,8 +200,23 @@ front_bwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
         if (fd.table != nullptr) drow = reinterpret_cast<float*>(const_cast<void*>(fd.table)) + row * dim;
         if (has_lr && sub == 0) {
           const b2_field& ld = lf.f[f];
-          if (ld.table != nullptr && row != (int64_t) ld.padding_idx)
+          if (ld.table != nullptr && row != (int64_t) ld.padding_idx) {
             b2_red_add(reinterpret_cast<float*>(const_cast<void*>(ld.table)) + row, gl);
+            if (lazy) {   // enqueue the LR row once per step
+              const int grow = (int) (lz.grow_lr[f] + row);
+              if (atomicExch(lz.mark + grow, tmark) != tmark) {
+                const int pos = atomicAdd(lz.counter, 1);
+                if (pos < lz.worklist_capacity) lz.worklist[pos] = grow;
+              }
+            }
+          }
+        }
+        if (lazy && drow != nullptr && sub == 0) {   // enqueue the embedding row once per step
+          const int grow = (int) (lz.grow_emb[f] + row);
+          if (atomicExch(lz.mark + grow, tmark) != tmark) {
+            const int pos = atomicAdd(lz.counter, 1);
+            if (pos < lz.worklist_capacity) lz.worklist[pos] = grow;
+          }
         }
       }
       if (drow != nullptr && e < dim) {
@@ -201,7 +259,8 @@ front_bwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
 }
 
 template <typename IdxT>
-int launch_front_fwd(const B2FieldPack& emb, const B2FieldPack& lr, int64_t batch, int dim, int has_lr,
+int launch_front_fwd(const B2FieldPack& emb, const B2FieldPack& lr, const b2_lazy_ctx& lz, int lazy,
+                     int64_t batch, int dim, int has_lr,
                      int want_fm, const float* bias, float* logit_out, float* sum_out, int32_t* status,
                      cudaStream_t st) {
   int lpr_log2 = next_pow2_log2((dim + 3) / 4);
@@ -209,23 +268,24 @@ int launch_front_fwd(const B2FieldPack& emb, const B2FieldPack& lr, int64_t batc
   const int grid = grid_for(batch * 32, 256);
   const int passes = (emb.nfields + (32 >> lpr_log2) - 1) / (32 >> lpr_log2);
   if (passes <= 2)
-    front_fwd_kernel<IdxT, 2><<<grid, 256, smem, st>>>(emb, lr, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
+    front_fwd_kernel<IdxT, 2><<<grid, 256, smem, st>>>(emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
   else if (passes <= 5)
-    front_fwd_kernel<IdxT, 5><<<grid, 256, smem, st>>>(emb, lr, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
+    front_fwd_kernel<IdxT, 5><<<grid, 256, smem, st>>>(emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
   else
-    front_fwd_kernel<IdxT, 8><<<grid, 256, smem, st>>>(emb, lr, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
+    front_fwd_kernel<IdxT, 8><<<grid, 256, smem, st>>>(emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
   B2_CUDA_LAUNCH_CHECK("b2_front_fwd");
   return B2_OK;
 }
 
 template <typename IdxT>
-int launch_front_bwd(const B2FieldPack& emb, const B2FieldPack& lr, int64_t batch, int dim, int has_lr,
+int launch_front_bwd(const B2FieldPack& emb, const B2FieldPack& lr, const b2_lazy_ctx& lz, int lazy,
+                     int64_t batch, int dim, int has_lr,
                      int want_fm, const float* emb_saved, const float* gx, const float* sums,
                      const float* glogit, float* gbias, cudaStream_t st) {
   int lpr_log2 = next_pow2_log2((dim + 3) / 4);
   const size_t smem = ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15) + pack_smem_bytes(emb.nfields) + 16;
   const int grid = grid_for((batch * (int64_t) emb.nfields) << lpr_log2, 256);
-  front_bwd_kernel<IdxT><<<grid, 256, smem, st>>>(emb, lr, batch, dim, lpr_log2, has_lr, want_fm, emb_saved,
+  front_bwd_kernel<IdxT><<<grid, 256, smem, st>>>(emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, emb_saved,
                                                  gx, sums, glogit, gbias);
   B2_CUDA_LAUNCH_CHECK("b2_front_bwd");
   return B2_OK;
@@ -268,7 +328,8 @@ void fill_pack(B2FieldPack& pack, const b2_field* fields, int nfields) {
 
 extern "C" B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
                                    int64_t batch, int idx_dtype, int want_fm, const float* bias,
-                                   float* logit_out, float* sum_out, int32_t* status, void* stream) {
+                                   float* logit_out, float* sum_out, int32_t* status,
+                                   const b2_lazy_ctx* lazy, void* stream) {
   int rc = check_front(emb_fields, lr_fields, nfields, false);
   if (rc != B2_OK) return rc;
   B2_REQUIRE(batch >= 0, "negative batch");
@@ -280,10 +341,13 @@ extern "C" B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* l
   if (has_lr) fill_pack(lpack, lr_fields, nfields); else lpack.nfields = 0;
   cudaStream_t st = (cudaStream_t) stream;
   const int dim = emb_fields[0].dim;
+  static thread_local b2_lazy_ctx lz_none;
+  const b2_lazy_ctx& lz = lazy ? *lazy : lz_none;
+  const int lzf = lazy ? 1 : 0;
   switch (idx_dtype) {
-    case B2_F64: return launch_front_fwd<double>(epack, lpack, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
-    case B2_I64: return launch_front_fwd<int64_t>(epack, lpack, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
-    case B2_I32: return launch_front_fwd<int32_t>(epack, lpack, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
+    case B2_F64: return launch_front_fwd<double>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
+    case B2_I64: return launch_front_fwd<int64_t>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
+    case B2_I32: return launch_front_fwd<int32_t>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
     default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
   }
 }
@@ -291,7 +355,7 @@ extern "C" B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* l
 extern "C" B2_API int b2_front_bwd(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
                                    int64_t batch, int idx_dtype, int want_fm, const float* emb_saved,
                                    const float* gx, const float* sums, const float* glogit, float* gbias,
-                                   void* stream) {
+                                   const b2_lazy_ctx* lazy, void* stream) {
   int rc = check_front(emb_fields, lr_fields, nfields, true);
   if (rc != B2_OK) return rc;
   B2_REQUIRE(batch >= 0, "negative batch");
@@ -305,10 +369,13 @@ extern "C" B2_API int b2_front_bwd(const b2_field* emb_fields, const b2_field* l
   if (has_lr) fill_pack(lpack, lr_fields, nfields); else lpack.nfields = 0;
   cudaStream_t st = (cudaStream_t) stream;
   const int dim = emb_fields[0].dim;
+  static thread_local b2_lazy_ctx lz_none;
+  const b2_lazy_ctx& lz = lazy ? *lazy : lz_none;
+  const int lzf = lazy ? 1 : 0;
   switch (idx_dtype) {
-    case B2_F64: return launch_front_bwd<double>(epack, lpack, batch, dim, has_lr, want_fm, emb_saved, gx, sums, glogit, gbias, st);
-    case B2_I64: return launch_front_bwd<int64_t>(epack, lpack, batch, dim, has_lr, want_fm, emb_saved, gx, sums, glogit, gbias, st);
-    case B2_I32: return launch_front_bwd<int32_t>(epack, lpack, batch, dim, has_lr, want_fm, emb_saved, gx, sums, glogit, gbias, st);
+    case B2_F64: return launch_front_bwd<double>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, emb_saved, gx, sums, glogit, gbias, st);
+    case B2_I64: return launch_front_bwd<int64_t>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, emb_saved, gx, sums, glogit, gbias, st);
+    case B2_I32: return launch_front_bwd<int32_t>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, emb_saved, gx, sums, glogit, gbias, st);
     default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
   }
 }

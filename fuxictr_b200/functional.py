@@ -789,8 +789,12 @@ class _Front(torch.autograd.Function):
                 d.table, d.vocab = t.data_ptr(), t.shape[0]
                 d.idx, d.idx_stride = idx.data_ptr(), (idx.stride(0) if batch > 0 else 0)
                 d.out, d.out_stride = 0, 0
+        lazy = getattr(emb_tables[0], "_b2_lazy", None)       # set by arena.LazyTables on its parameters
+        lz = lazy.ctx_for(plan, lr_plan, emb_tables, lr_tables) if lazy is not None else None
         _lib.call("b2_front_fwd", descs, lr_descs, len(plan.fields), batch, ctx_code(idx_list),
-                  1 if want_fm else 0, _ptr(bias), _ptr(logit), _ptr(sums), _ptr(status), _stream())
+                  1 if want_fm else 0, _ptr(bias), _ptr(logit), _ptr(sums), _ptr(status),
+                  ctypes.byref(lz) if lz is not None else None, _stream())
+        ctx.lazy_ctx = lz
         ctx.plan, ctx.lr_plan, ctx.idx_list, ctx.want_fm = plan, lr_plan, idx_list, want_fm
         ctx.emb_tables, ctx.lr_tables, ctx.bias = emb_tables, lr_tables, bias
         ctx.save_for_backward(arena, sums)
@@ -827,9 +831,10 @@ class _Front(torch.autograd.Function):
                     d.vocab = ctx.lr_tables[f.table_slot].shape[0]
                     d.idx, d.idx_stride = idx.data_ptr(), idx.stride(0)
                     d.dim, d.seq_len, d.pool, d.padding_idx = 1, 1, 0, f.padding_idx
+            lz = ctx.lazy_ctx
             _lib.call("b2_front_bwd", descs, lr_descs, len(plan.fields), batch, ctx_code(idx_list),
                       1 if ctx.want_fm else 0, _ptr(arena), _ptr(garena), _ptr(sums), _ptr(glogit),
-                      _ptr(gbias), _stream())
+                      _ptr(gbias), ctypes.byref(lz) if lz is not None else None, _stream())
         return (None, None, None, None, None, gbias, None) + tuple(egrads) + tuple(lgrads)
 
 

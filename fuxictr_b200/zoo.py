@@ -185,16 +185,47 @@ class RankModel(nn.Module):
         mat = v.as_strided((v.shape[0], width), (v.stride(0), 1), v.storage_offset() - col)
         return mat.to(self.device)
 
-    def use_fused_optimizer(self):
+    def _front_tables(self):
+        """Embedding + LR tables read ONLY through the fused front kernels (lazy-Adam candidates)."""
+        fed = self.embedding_layer.embedding_layer
+        lr_layer = self.fm.lr_layer if hasattr(self, "fm") else getattr(self, "lr_layer", None)
+        tabs, seen = [], set()
+        for mod in ([fed] + ([lr_layer.embedding_layer.embedding_layer] if lr_layer is not None else [])):
+            for f in mod._feature_map.features.keys():
+                if f in mod.embedding_layers and type(mod.embedding_layers[f]) == nn.Embedding:
+                    w = mod.embedding_layers[f].weight
+                    if id(w) not in seen:
+                        seen.add(id(w))
+                        tabs.append(w)
+        return tabs
+
+    def use_fused_optimizer(self, lazy_tables=False):
         """Re-home parameters into one HBM arena and replace clip_grad_norm_ + torch Adam by
-        the two-kernel FusedAdam (same arithmetic; see arena.py).  Call after model_to_device()."""
+        the two-kernel FusedAdam (same arithmetic; see arena.py).  Call after model_to_device().
+        lazy_tables=True (models whose tables are read only by the fused front: DeepFM, xDeepFM):
+        the dense Adam semantics of the tables are evaluated row-wise and lazily — bit-identical
+        results, O(batch) instead of O(vocabulary) optimizer traffic; call materialize_tables()
+        before reading table weights outside the kernels (state_dict, evaluation on other paths)."""
         if self._optimizer_name != "Adam":
             raise NotImplementedError("the fused optimizer implements Adam only")
+        if lazy_tables:
+            if getattr(self, "_sharded_params", None):
+                raise NotImplementedError("lazy tables and row-sharding are not combined yet")
+            first = self._front_tables()
+            self._arena = ParamArena(self, first=first)
+            self._fused_optimizer = FusedAdam(self._arena, lr=self._lr, max_norm=self._max_gradient_norm)
+            self._lazy = self._fused_optimizer.enable_lazy(first)
+            self.optimizer = None
+            return self._fused_optimizer
         self._arena = ParamArena(self, first=getattr(self, "_sharded_params", ()))
         self._fused_optimizer = FusedAdam(self._arena, lr=self._lr, max_norm=self._max_gradient_norm)
         self._fused_optimizer.sharded = bool(getattr(self, "_sharded_params", None))
         self.optimizer = None
         return self._fused_optimizer
+
+    def materialize_tables(self):
+        if getattr(self, "_lazy", None) is not None:
+            self._lazy.materialize()
 
     def fused_train_step(self, batch_data):
         """train_step with the arena optimizer and the fused logit+BCE kernel when the model
@@ -254,6 +285,8 @@ class DeepFM(RankModel):
         if fused is not None:     # gather + FM + LR in one launch
             feature_emb, fm_lr = fused
             return (fm_lr, self.mlp(feature_emb.flatten(start_dim=1)))
+        if getattr(self, "_lazy", None) is not None:
+            raise RuntimeError("lazy tables are only readable through the fused front (unsupported config)")
         feature_emb = self.embedding_layer(X)
         return (self.fm.fm_layer(feature_emb), self.fm.lr_layer(X),
                 self.mlp(feature_emb.flatten(start_dim=1)))
@@ -455,6 +488,8 @@ class xDeepFM(RankModel):
             feature_emb, lr_logit = fused
             terms = [lr_logit, self.cin(feature_emb)]
         else:
+            if getattr(self, "_lazy", None) is not None:
+                raise RuntimeError("lazy tables are only readable through the fused front (unsupported config)")
             feature_emb = self.embedding_layer(X)
             terms = [self.lr_layer(X), self.cin(feature_emb)]
         if self.dnn is not None:

@@ -136,6 +136,33 @@ B2_API int b2_lr_fwd(const b2_field* fields, int nfields, int64_t batch, int idx
 B2_API int b2_lr_bwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype,
               const float* gout, float* gbias, void* stream);
 
+
+/*
+ * Lazy evaluation of the DENSE Adam semantics for embedding tables (an exact "next row" of SURVEY
+ * 8f-2).  The reference updates every row of every table every step (rows with zero gradient still
+ * move: m *= b1, v *= b2, p -= lr_t*m/(sqrt(v)/sqrt(bc2_t)+eps)).  In lazy mode a row is brought up
+ * to date only when a batch touches it: the fused front reads p and, when last_step[row] < steps
+ * done, replays the zero-gradient updates of the missed steps in registers (b2_front_fwd); the
+ * backward enqueues every touched row once (b2_front_bwd); b2_lazy_adam_step then replays the missed
+ * steps for the enqueued rows and applies the real update.  Every replayed update uses the same
+ * scalars (sched[t], written by b2_adam_sched) and the same explicitly rounded arithmetic as the
+ * dense pass, so the result is BIT-IDENTICAL to dense Adam (tests/test_gpu_parity.py).
+ * Rows are numbered globally: table i owns rows [grow_base[i], grow_base[i] + vocab_i).
+ */
+typedef struct b2_lazy_ctx {
+  const int32_t* last_step; /* [total rows] optimizer step each row is current for */
+  const float* sched;       /* float2[sched_len]: {lr/(1-b1^t), 1/sqrt(1-b2^t)} per step t */
+  const int64_t* step_dev;  /* device scalar: optimizer steps completed so far */
+  int32_t* mark;            /* [total rows] scratch: step at which the row was last enqueued */
+  int32_t* worklist;        /* [capacity] global row ids touched this step */
+  int32_t* counter;         /* device scalar: worklist length */
+  int64_t delta_m, delta_v; /* element offsets from a parameter to its Adam moments (arena layout) */
+  float w1, beta2, w2, eps; /* 1-beta1, beta2, 1-beta2, eps */
+  int32_t worklist_capacity, pad_;
+  int64_t grow_emb[B2_MAX_FIELDS]; /* global row base of the embedding table of each field */
+  int64_t grow_lr[B2_MAX_FIELDS];  /* ... and of its LR table */
+} b2_lazy_ctx;
+
 /*
  * The sparse front of an FM-style model in one launch each way (DeepFM, xDeepFM's LR term):
  *   emb   = FeatureEmbedding.forward  (feature_embedding.py:73-88)      -> written through emb_fields[i].out
@@ -147,7 +174,8 @@ B2_API int b2_lr_bwd(const b2_field* fields, int nfields, int64_t batch, int idx
  */
 B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* lr_fields, int nfields, int64_t batch,
                         int idx_dtype, int want_fm, const float* bias, float* logit_out, float* sum_out,
-                        int32_t* status, void* stream);
+                        int32_t* status, const b2_lazy_ctx* lazy /* NULL = tables are up to date */,
+                        void* stream);
 /*
  * Backward of b2_front_fwd.  In emb_fields, `table` is the (vocab, dim) gradient buffer (NULL =
  * no gradient wanted) and `out` addresses the incoming gradient arena gx (same layout as the
@@ -158,7 +186,32 @@ B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* lr_fields, i
  */
 B2_API int b2_front_bwd(const b2_field* emb_fields, const b2_field* lr_fields, int nfields, int64_t batch,
                         int idx_dtype, int want_fm, const float* emb_saved, const float* gx,
-                        const float* sums, const float* glogit, float* gbias, void* stream);
+                        const float* sums, const float* glogit, float* gbias,
+                        const b2_lazy_ctx* lazy /* non-NULL: enqueue every touched row once */, void* stream);
+/*
+ * Lazy optimizer step over the rows enqueued by b2_front_bwd (tables[i]: parameter pointer, rows, dim,
+ * global row base, sorted by base; gradients/moments at the arena deltas):
+ *   b2_lazy_sumsq      sumsq[0] += sum of g^2 over the enqueued rows
+ *   b2_lazy_adam_step  for each enqueued row: replay the missed zero-gradient steps, apply step t with
+ *                      clip_coef*g, store p/m/v, last_step = t, zero the gradient row
+ *   b2_lazy_materialize bring EVERY row up to date (before checkpoints / reads outside the kernels)
+ */
+typedef struct b2_lazy_table {
+  float* param;      /* (rows, dim) parameter slice inside the arena */
+  int64_t rows;
+  int64_t grow_base; /* first global row id */
+  int32_t dim, pad_;
+} b2_lazy_table;
+B2_API int b2_lazy_sumsq(const b2_lazy_table* tables_dev, int ntables, const int32_t* worklist,
+                         const int32_t* counter, int capacity, int64_t delta_g, float* sumsq, void* stream);
+B2_API int b2_lazy_adam_step(const b2_lazy_table* tables_dev, int ntables, const int32_t* worklist,
+                             const int32_t* counter, int capacity, int64_t delta_g, int64_t delta_m,
+                             int64_t delta_v, int32_t* last_step, const float* sched,
+                             const int64_t* step_dev, const float* sumsq, float max_norm, float beta1,
+                             float beta2, float eps, void* stream);
+B2_API int b2_lazy_materialize(const b2_lazy_table* tables_dev, int ntables, int64_t total_rows,
+                               int64_t delta_m, int64_t delta_v, int32_t* last_step, const float* sched,
+                               const int64_t* step_dev, float beta1, float beta2, float eps, void* stream);
 
 /*
  * Row-sharded tables across the GPUs of one NVSwitch box: row r of every table
@@ -352,11 +405,18 @@ B2_API int b2_logit_bce_fwd(const float* t0, const float* t1, const float* t2, c
  *                 bc1 = 1-b1^step, bc2 = 1-b2^step, step read from step_dev[0]
  *                 (device int64, already incremented by the caller).
  *   If zero_grad != 0 the gradient arena is zeroed in the same pass.
+ *   b2_adam_sched writes sched[step] = {lr/(1-b1^step), 1/sqrt(1-b2^step)}; b2_adam_step_sched is
+ *   b2_adam_step reading those two scalars from the table (shared with the lazy row-wise kernels).
  */
 B2_API int b2_sumsq(const float* g, int64_t n, float* out, void* stream);
 B2_API int b2_adam_step(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq,
                  float max_norm, float lr, float beta1, float beta2, float eps,
                  const int64_t* step_dev, int zero_grad, void* stream);
+B2_API int b2_adam_sched(const int64_t* step_dev, float lr, float beta1, float beta2, float* sched,
+                         int64_t sched_len, void* stream);
+B2_API int b2_adam_step_sched(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq,
+                              float max_norm, float beta1, float beta2, float eps, const int64_t* step_dev,
+                              const float* sched, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }
