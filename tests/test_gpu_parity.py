@@ -666,8 +666,10 @@ def test_lazy_adam_is_bit_identical_to_dense_adam(name):
     specs = [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 200 + 17 * i})
              for i in range(9)]
     fm = FeatureMap.from_specs(specs, embedding_dim=8)
-    kwargs = dict(embedding_dim=8, hidden_units=[32, 16]) if name == "DeepFM" else \\
-        dict(embedding_dim=8, dnn_hidden_units=[32, 16], cin_hidden_units=[6, 5])
+    if name == "DeepFM":
+        kwargs = dict(embedding_dim=8, hidden_units=[32, 16])
+    else:
+        kwargs = dict(embedding_dim=8, dnn_hidden_units=[32, 16], cin_hidden_units=[6, 5])
 
     def build(lazy):
         torch.manual_seed(123)
