@@ -85,36 +85,47 @@ front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
         }
       }
       if (lazy) {
+        int last_e[MAX_PASSES], last_l[MAX_PASSES];
 #pragma unroll
-        for (int u = 0; u < MAX_PASSES; ++u) {
+        for (int u = 0; u < MAX_PASSES; ++u) {   // all last_step loads in flight
           const int f = f0 + u * rows_per_pass + rg;
+          last_e[u] = done;
+          last_l[u] = done;
           if (f < F && ok[u]) {
-            if (lane_on) {
-              const int last = __ldg(lz.last_step + lz.grow_emb[f] + row[u]);
-              if (last < done) {
-                const float* pp = reinterpret_cast<const float*>(sf.f[f].table) + row[u] * dim + e;
-                float4 m4 = *reinterpret_cast<const float4*>(pp + lz.delta_m);
-                float4 v4 = *reinterpret_cast<const float4*>(pp + lz.delta_v);
-                for (int k = last + 1; k <= done; ++k) {
-                  const B2AdamSched sc = sched[k];
-                  b2_adam_apply(v[u].x, 0.f, m4.x, v4.x, ac, sc.x, sc.y);
-                  b2_adam_apply(v[u].y, 0.f, m4.y, v4.y, ac, sc.x, sc.y);
-                  b2_adam_apply(v[u].z, 0.f, m4.z, v4.z, ac, sc.x, sc.y);
-                  b2_adam_apply(v[u].w, 0.f, m4.w, v4.w, ac, sc.x, sc.y);
-                }
-              }
-            }
-            if (has_lr && sub == 0) {
-              const int last = __ldg(lz.last_step + lz.grow_lr[f] + row[u]);
-              if (last < done) {
-                const float* pp = reinterpret_cast<const float*>(lf.f[f].table) + row[u];
-                float m1 = pp[lz.delta_m], v1 = pp[lz.delta_v];
-                for (int k = last + 1; k <= done; ++k) {
-                  const B2AdamSched sc = sched[k];
-                  b2_adam_apply(w[u], 0.f, m1, v1, ac, sc.x, sc.y);
-                }
-              }
-            }
+            if (lane_on) last_e[u] = __ldg(lz.last_step + lz.grow_emb[f] + row[u]);
+            if (has_lr && sub == 0) last_l[u] = __ldg(lz.last_step + lz.grow_lr[f] + row[u]);
+          }
+        }
+        float4 m4[MAX_PASSES], v4[MAX_PASSES];
+        float m1[MAX_PASSES], v1[MAX_PASSES];
+#pragma unroll
+        for (int u = 0; u < MAX_PASSES; ++u) {   // all moment loads of stale rows in flight
+          const int f = f0 + u * rows_per_pass + rg;
+          m4[u] = v4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          m1[u] = v1[u] = 0.f;
+          if (last_e[u] < done) {
+            const float* pp = reinterpret_cast<const float*>(sf.f[f].table) + row[u] * dim + e;
+            m4[u] = *reinterpret_cast<const float4*>(pp + lz.delta_m);
+            v4[u] = *reinterpret_cast<const float4*>(pp + lz.delta_v);
+          }
+          if (last_l[u] < done) {
+            const float* pp = reinterpret_cast<const float*>(lf.f[f].table) + row[u];
+            m1[u] = pp[lz.delta_m];
+            v1[u] = pp[lz.delta_v];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < MAX_PASSES; ++u) {   // replay the missed zero-gradient updates
+          for (int k = last_e[u] + 1; k <= done; ++k) {
+            const B2AdamSched sc = sched[k];
+            b2_adam_apply(v[u].x, 0.f, m4[u].x, v4[u].x, ac, sc.x, sc.y);
+            b2_adam_apply(v[u].y, 0.f, m4[u].y, v4[u].y, ac, sc.x, sc.y);
+            b2_adam_apply(v[u].z, 0.f, m4[u].z, v4[u].z, ac, sc.x, sc.y);
+            b2_adam_apply(v[u].w, 0.f, m4[u].w, v4[u].w, ac, sc.x, sc.y);
+          }
+          for (int k = last_l[u] + 1; k <= done; ++k) {
+            const B2AdamSched sc = sched[k];
+            b2_adam_apply(w[u], 0.f, m1[u], v1[u], ac, sc.x, sc.y);
           }
         }
       }
@@ -188,6 +199,7 @@ front_bwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
     const int64_t item = wbase + my_group;
     float* drow = nullptr;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int enq_e = -1, enq_l = -1;   // global rows this lane has to append to the worklist
     if (item < nitems) {
       const int64_t b = item / F;
       const int f = (int) (item - b * F);
@@ -202,21 +214,15 @@ front_bwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
           const b2_field& ld = lf.f[f];
           if (ld.table != nullptr && row != (int64_t) ld.padding_idx) {
             b2_red_add(reinterpret_cast<float*>(const_cast<void*>(ld.table)) + row, gl);
-            if (lazy) {   // enqueue the LR row once per step
+            if (lazy) {   // first toucher of the LR row this step enqueues it
               const int grow = (int) (lz.grow_lr[f] + row);
-              if (atomicExch(lz.mark + grow, tmark) != tmark) {
-                const int pos = atomicAdd(lz.counter, 1);
-                if (pos < lz.worklist_capacity) lz.worklist[pos] = grow;
-              }
+              if (atomicExch(lz.mark + grow, tmark) != tmark) enq_l = grow;
             }
           }
         }
-        if (lazy && drow != nullptr && sub == 0) {   // enqueue the embedding row once per step
+        if (lazy && drow != nullptr && sub == 0) {   // first toucher of the embedding row enqueues it
           const int grow = (int) (lz.grow_emb[f] + row);
-          if (atomicExch(lz.mark + grow, tmark) != tmark) {
-            const int pos = atomicAdd(lz.counter, 1);
-            if (pos < lz.worklist_capacity) lz.worklist[pos] = grow;
-          }
+          if (atomicExch(lz.mark + grow, tmark) != tmark) enq_e = grow;
         }
       }
       if (drow != nullptr && e < dim) {
@@ -228,6 +234,26 @@ front_bwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
           const float4 sv = __ldg(reinterpret_cast<const float4*>(sums + b * dim + e));
           v.x = fmaf(gl, sv.x - ev.x, v.x); v.y = fmaf(gl, sv.y - ev.y, v.y);
           v.z = fmaf(gl, sv.z - ev.z, v.z); v.w = fmaf(gl, sv.w - ev.w, v.w);
+        }
+      }
+    }
+    if (lazy) {
+      // warp-aggregated append: one atomicAdd on the shared counter per warp, not per row
+      const unsigned me = __ballot_sync(0xffffffffu, enq_e >= 0);
+      const unsigned ml = __ballot_sync(0xffffffffu, enq_l >= 0);
+      const int ne = __popc(me), nl = __popc(ml);
+      if (ne + nl > 0) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(lz.counter, ne + nl);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (enq_e >= 0) {
+          const int pos = base + __popc(me & lt);
+          if (pos < lz.worklist_capacity) lz.worklist[pos] = enq_e;
+        }
+        if (enq_l >= 0) {
+          const int pos = base + ne + __popc(ml & lt);
+          if (pos < lz.worklist_capacity) lz.worklist[pos] = enq_l;
         }
       }
     }

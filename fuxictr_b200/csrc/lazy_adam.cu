@@ -51,6 +51,10 @@ lazy_adam_kernel(const b2_lazy_table* __restrict__ tables, int ntables,
                  int64_t delta_g, int64_t delta_m, int64_t delta_v, int32_t* __restrict__ last_step,
                  const B2AdamSched* __restrict__ sched, const int64_t* __restrict__ step_dev,
                  const float* __restrict__ sumsq, float max_norm, B2AdamConst c) {
+  extern __shared__ b2_lazy_table stab[];
+  for (int i = threadIdx.x; i < ntables; i += blockDim.x) stab[i] = tables[i];
+  __syncthreads();
+  tables = stab;
   const int n = min(*counter, capacity);
   const int t = (int) *step_dev;                  // the step being applied (already incremented)
   float clip = 1.f;
@@ -63,15 +67,38 @@ lazy_adam_kernel(const b2_lazy_table* __restrict__ tables, int ntables,
     const b2_lazy_table tb = tables[find_table(tables, ntables, grow)];
     float* p = tb.param + (grow - tb.grow_base) * tb.dim;
     const int last = last_step[grow];
-    for (int e = sub; e < tb.dim; e += 4) {
-      float pv = p[e], mv = p[e + delta_m], vv = p[e + delta_v];
-      for (int k = last + 1; k < t; ++k) {        // missed zero-gradient steps
-        const B2AdamSched sc = sched[k];
-        b2_adam_apply(pv, 0.f, mv, vv, c, sc.x, sc.y);
+    if ((tb.dim & 3) == 0 && (delta_g & 3) == 0 && (delta_m & 3) == 0 && (delta_v & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      for (int e = sub * 4; e < tb.dim; e += 16) {   // 16-byte accesses: a D=16 row is one float4 per lane
+        float4 pv = *reinterpret_cast<float4*>(p + e), mv = *reinterpret_cast<float4*>(p + e + delta_m);
+        float4 vv = *reinterpret_cast<float4*>(p + e + delta_v), gv = *reinterpret_cast<float4*>(p + e + delta_g);
+        for (int k = last + 1; k < t; ++k) {
+          const B2AdamSched sc = sched[k];
+          b2_adam_apply(pv.x, 0.f, mv.x, vv.x, c, sc.x, sc.y);
+          b2_adam_apply(pv.y, 0.f, mv.y, vv.y, c, sc.x, sc.y);
+          b2_adam_apply(pv.z, 0.f, mv.z, vv.z, c, sc.x, sc.y);
+          b2_adam_apply(pv.w, 0.f, mv.w, vv.w, c, sc.x, sc.y);
+        }
+        b2_adam_apply(pv.x, __fmul_rn(gv.x, clip), mv.x, vv.x, c, now.x, now.y);
+        b2_adam_apply(pv.y, __fmul_rn(gv.y, clip), mv.y, vv.y, c, now.x, now.y);
+        b2_adam_apply(pv.z, __fmul_rn(gv.z, clip), mv.z, vv.z, c, now.x, now.y);
+        b2_adam_apply(pv.w, __fmul_rn(gv.w, clip), mv.w, vv.w, c, now.x, now.y);
+        *reinterpret_cast<float4*>(p + e) = pv;
+        *reinterpret_cast<float4*>(p + e + delta_m) = mv;
+        *reinterpret_cast<float4*>(p + e + delta_v) = vv;
+        *reinterpret_cast<float4*>(p + e + delta_g) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      b2_adam_apply(pv, __fmul_rn(p[e + delta_g], clip), mv, vv, c, now.x, now.y);
-      p[e] = pv; p[e + delta_m] = mv; p[e + delta_v] = vv;
-      p[e + delta_g] = 0.f;                       // the gradient arena stays all-zero between steps
+    } else {
+      for (int e = sub; e < tb.dim; e += 4) {
+        float pv = p[e], mv = p[e + delta_m], vv = p[e + delta_v];
+        for (int k = last + 1; k < t; ++k) {        // missed zero-gradient steps
+          const B2AdamSched sc = sched[k];
+          b2_adam_apply(pv, 0.f, mv, vv, c, sc.x, sc.y);
+        }
+        b2_adam_apply(pv, __fmul_rn(p[e + delta_g], clip), mv, vv, c, now.x, now.y);
+        p[e] = pv; p[e + delta_m] = mv; p[e + delta_v] = vv;
+        p[e + delta_g] = 0.f;                       // the gradient arena stays all-zero between steps
+      }
     }
     __syncwarp(0xFu << (threadIdx.x & 28));   // the 4 lanes of this row have read `last`
     if (sub == 0) last_step[grow] = t;
@@ -137,7 +164,7 @@ extern "C" B2_API int b2_lazy_adam_step(const b2_lazy_table* tables_dev, int nta
                                         float beta1, float beta2, float eps, void* stream) {
   B2_REQUIRE(tables_dev && worklist && counter && last_step && sched && step_dev && ntables >= 1 && capacity >= 1,
              "bad argument");
-  lazy_adam_kernel<<<grid_rows(capacity), 256, 0, (cudaStream_t) stream>>>(
+  lazy_adam_kernel<<<grid_rows(capacity), 256, sizeof(b2_lazy_table) * ntables, (cudaStream_t) stream>>>(
       tables_dev, ntables, worklist, counter, capacity, delta_g, delta_m, delta_v, last_step,
       reinterpret_cast<const B2AdamSched*>(sched), step_dev, sumsq, max_norm, make_const(beta1, beta2, eps));
   B2_CUDA_LAUNCH_CHECK("b2_lazy_adam_step");
