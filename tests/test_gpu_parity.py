@@ -655,16 +655,7 @@ def test_cin_fused_vs_oracle(F_, D, units, B):
 
 
 # ------------------------------------------------------------------ lazy (row-wise) evaluation of dense Adam
-@pytest.mark.parametrize("max_norm", [10.0, 0.05])
-@pytest.mark.parametrize("name", ["DeepFM", "xDeepFM"])
-def test_lazy_adam_is_bit_identical_to_dense_adam(name, max_norm):
-    """The reference's Adam moves EVERY table row at every step.  Lazy mode touches only the rows
-    a batch touches and replays the missed zero-gradient updates on demand; after any number of
-    steps (rows skipped for 0..N steps) parameters and both Adam moments are BIT-identical to the
-    dense evaluation as long as the clip coefficient is 1 (max_norm=10, the reference's setting on
-    this workload).  With clipping active (max_norm=0.05) the coefficient itself is a floating-point
-    sum over all gradients whose (atomic) summation order differs between — and within — the two
-    modes, so the bar there is 1e-6 relative."""
+def _lazy_pair(name="DeepFM"):
     from fuxictr_b200 import zoo
     from fuxictr_b200.schema import FeatureMap
     specs = [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 200 + 17 * i})
@@ -675,7 +666,7 @@ def test_lazy_adam_is_bit_identical_to_dense_adam(name, max_norm):
     else:
         kwargs = dict(embedding_dim=8, dnn_hidden_units=[32, 16], cin_hidden_units=[6, 5])
 
-    def build(lazy):
+    def build(lazy, max_norm):
         torch.manual_seed(123)
         m = getattr(zoo, name)(fm, gpu=0, **kwargs)
         with torch.no_grad():
@@ -685,30 +676,91 @@ def test_lazy_adam_is_bit_identical_to_dense_adam(name, max_norm):
         m._max_gradient_norm = max_norm
         m.use_fused_optimizer(lazy_tables=lazy)
         return m
-    dense, lazy = build(False), build(True)
+    return fm, specs, build
+
+
+def _batch(specs, gen, B=48):
+    ids = torch.cat([torch.randint(0, s["vocab_size"], (B, 1), generator=gen) for _, s in specs], 1)
+    return torch.cat([ids.double(), (torch.rand(B, 1, generator=gen) < 0.4).double()], 1).cuda()
+
+
+def test_lazy_adam_optimizer_is_bit_identical_given_identical_gradients():
+    """The reference's Adam moves EVERY table row at every step (zero-gradient rows included).  Lazy
+    mode touches only the rows a batch touches and REPLAYS the missed zero-gradient updates on demand.
+    Given bit-identical gradients (copied from the dense model: backward atomics make two backward
+    passes differ in the last bit) the parameters and both Adam moments after 8 steps with rows idle
+    for 0..7 steps must be BIT-identical, and so must the embeddings the fused front reads from the
+    not-yet-materialised tables."""
+    from fuxictr_b200 import layers
+    fm, specs, build = _lazy_pair("DeepFM")
+    dense, lazy = build(False, 10.0), build(True, 10.0)
+    lz = lazy._lazy
+    gen = torch.Generator().manual_seed(9)
+    dn, ln = dict(dense.named_parameters()), dict(lazy.named_parameters())
+    for step in range(8):
+        mat = _batch(specs, gen)
+        batch = fm.batch_dict(mat)
+        dense._fused_optimizer.zero_grad()
+        lazy._fused_optimizer.zero_grad()
+        from fuxictr_b200 import functional as F2
+        loss, _ = F2.logit_bce(dense.get_labels(batch), *dense.forward_logits(batch))
+        loss.backward()
+        # hand the dense model's gradients to the lazy arena, parameter by parameter
+        for k, p in dn.items():
+            q = ln[k]
+            lazy._arena.grad_view(q._b2_slot).copy_(dense._arena.grad_view(p._b2_slot))
+        # worklist = every (table, row) of this batch except padding rows, exactly once
+        rows = []
+        for p in lz.tables:
+            name = [k for k, q in ln.items() if q is p][0]
+            feat = name.split("embedding_layers.")[1].split(".")[0]
+            col = fm.get_column_index(feat)
+            r = mat[:, col].long().unique()
+            rows.append(r[r != 0] + p._b2_grow_base)
+        wl = torch.cat(rows).int()
+        lz.worklist[:wl.numel()].copy_(wl)
+        lz.counter.fill_(wl.numel())
+        dense._fused_optimizer.step()
+        lazy._fused_optimizer.step()
+    torch.cuda.synchronize()
+    # the fused front reads stale rows through the replay: must equal the dense tables bit for bit
+    probe = _batch(specs, torch.Generator().manual_seed(77), B=256)
+    X = OrderedDict((k, v) for k, v in fm.batch_dict(probe).items() if k != "label")
+    with torch.no_grad():
+        e_dense, l_dense = layers.fused_front(dense.embedding_layer, dense.fm.lr_layer, X, True)
+        e_lazy, l_lazy = layers.fused_front(lazy.embedding_layer, lazy.fm.lr_layer, X, True)
+    assert torch.equal(e_dense, e_lazy) and torch.equal(l_dense, l_lazy)
+    stale = int((lz.last_step < int(lazy._fused_optimizer.step_dev)).sum())
+    assert stale > 0                                        # rows really were left behind
+    lazy.materialize_tables()
+    torch.cuda.synchronize()
+    for k, p in dn.items():
+        q = ln[k]
+        assert torch.equal(p.data, q.data), k
+        for a0, a1 in ((dense._fused_optimizer.M, lazy._fused_optimizer.M),
+                       (dense._fused_optimizer.V, lazy._fused_optimizer.V)):
+            s0, s1 = p._b2_slot, q._b2_slot
+            assert torch.equal(a0[s0.offset:s0.offset + s0.numel], a1[s1.offset:s1.offset + s1.numel]), k
+    assert float(lazy._arena.G.abs().sum()) == 0.0          # gradient arena left all-zero
+
+
+@pytest.mark.parametrize("max_norm", [10.0, 0.05])
+@pytest.mark.parametrize("name", ["DeepFM", "xDeepFM"])
+def test_lazy_adam_training_matches_dense_adam(name, max_norm):
+    """End to end (own backward in each model, clipping inactive and active): lazy and dense
+    training agree to 1e-6 — the residual is the atomic summation order of the backward kernels and
+    of the gradient norm, which also differs between two runs of the SAME mode."""
+    fm, specs, build = _lazy_pair(name)
+    dense, lazy = build(False, max_norm), build(True, max_norm)
     gen = torch.Generator().manual_seed(9)
     for step in range(7):
-        B = 48
-        ids = torch.cat([torch.randint(0, s["vocab_size"], (B, 1), generator=gen) for _, s in specs], 1)
-        mat = torch.cat([ids.double(), (torch.rand(B, 1, generator=gen) < 0.4).double()], 1).cuda()
+        mat = _batch(specs, gen)
         l0 = dense.fused_train_step(fm.batch_dict(mat))
         l1 = lazy.fused_train_step(fm.batch_dict(mat))
-        if max_norm >= 1.0:
-            assert float(l0) == float(l1), step           # the forward reads caught-up rows
-        else:
-            assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0)), step
+        assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0)), step
     lazy.materialize_tables()
     torch.cuda.synchronize()
     sd0, sd1 = dense.state_dict(), lazy.state_dict()
-
-    def same(a, b):
-        return torch.equal(a, b) if max_norm >= 1.0 else close(a, b, 1e-6, atol=1e-9)
     for k in sd0:
-        assert same(sd0[k], sd1[k]), k
-    # moments: compare per parameter (the two arenas order their slices differently)
-    for (k, p0), (_, p1) in zip(dense.named_parameters(), lazy.named_parameters()):
-        s0, s1 = p0._b2_slot, p1._b2_slot
-        for a0, a1 in ((dense._fused_optimizer.M, lazy._fused_optimizer.M),
-                       (dense._fused_optimizer.V, lazy._fused_optimizer.V)):
-            assert same(a0[s0.offset:s0.offset + s0.numel], a1[s1.offset:s1.offset + s1.numel]), k
-    assert float(lazy._arena.G.abs().sum()) == 0.0         # gradient arena left all-zero
+        assert close(sd0[k], sd1[k], 1e-6, atol=1e-9), k
+    assert float(lazy._arena.G.abs().sum()) == 0.0
