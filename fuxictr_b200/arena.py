@@ -10,6 +10,7 @@ two streaming kernels over the arena instead of ~6 launches per parameter.
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -130,8 +131,11 @@ class LazyTables(object):
             ctx.worklist, ctx.counter = self.worklist.data_ptr(), self.counter.data_ptr()
             ctx.delta_m = (opt.M.data_ptr() - a.P.data_ptr()) // 4
             ctx.delta_v = (opt.V.data_ptr() - a.P.data_ptr()) // 4
-            ctx.w1, ctx.beta2 = 1.0 - opt.betas[0], opt.betas[1]
-            ctx.w2, ctx.eps = 1.0 - opt.betas[1], opt.eps
+            # the same float32 roundings as make_const() in csrc/lazy_adam.cu / adam_kernel in dense.cu:
+            # beta is rounded to fp32 FIRST, then 1 - beta is taken in double and rounded again
+            b1, b2 = float(np.float32(opt.betas[0])), float(np.float32(opt.betas[1]))
+            ctx.w1, ctx.beta2 = float(np.float32(1.0 - b1)), b2
+            ctx.w2, ctx.eps = float(np.float32(1.0 - b2)), opt.eps
             ctx.worklist_capacity = self.capacity
             for i, f in enumerate(plan.fields):
                 ctx.grow_emb[i] = emb_tables[f.table_slot]._b2_grow_base
