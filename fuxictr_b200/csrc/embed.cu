@@ -350,7 +350,7 @@ static int launch_gather(const B2FieldPack& pack, int64_t batch, int vec, int ma
   const int64_t nitems = batch * (int64_t) pack.nslots;
   if (!any_pooled && one_pass) {
     // Large launches unroll deeper: 8 independent 16-byte row loads per lane in flight
-    // (tests/debug_gather.py on 10 GB of tables, B=524288: 3.31 TB/s at 4, 3.77 TB/s at 8).
+    // (tools/debug_gather.py on 10 GB of tables, B=524288: 3.31 TB/s at 4, 3.77 TB/s at 8).
     static const int env_unroll = getenv("B2_GATHER_UNROLL") ? atoi(getenv("B2_GATHER_UNROLL")) : 0;
     static const int env_stream = getenv("B2_GATHER_STREAM") ? atoi(getenv("B2_GATHER_STREAM")) : -1;
     const bool big = nitems >= (int64_t) 1 << 20;

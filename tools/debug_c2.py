@@ -7,6 +7,7 @@ import __graft_entry__; __graft_entry__.build()
 from fuxictr_b200 import zoo, arena
 from oracle import fuxictr_oracle as O
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
 from test_gpu_parity import criteo_shape
 
 fm, specs, mat = criteo_shape()

@@ -1,7 +1,7 @@
 """torchrun script (N GPUs): a row-sharded DeepFM trained for 3 steps must equal the SAME model
 trained unsharded on the concatenated global batch (each rank recomputes that reference locally):
 logits, losses, the rank's table shards and the replicated dense weights, within 1e-5.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_sharded_check.py
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dist_sharded_check.py
 """
 import os, sys
 from collections import OrderedDict
