@@ -764,3 +764,89 @@ def test_lazy_adam_training_matches_dense_adam(name, max_norm):
     for k in sd0:
         assert close(sd0[k], sd1[k], 1e-6, atol=1e-9), k
     assert float(lazy._arena.G.abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------ the other BASELINE configs at full shape
+def _taobao_specs():
+    specs = [("item_id", {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 400000}),
+             ("cate_id", {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 10000})]
+    specs += [("f%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 20000}) for i in range(23)]
+    specs += [("click_history", {"type": "sequence", "source": "", "padding_idx": 0, "vocab_size": 400000, "max_len": 50,
+                                 "share_embedding": "item_id", "feature_encoder": None}),
+              ("cate_history", {"type": "sequence", "source": "", "padding_idx": 0, "vocab_size": 10000, "max_len": 50,
+                                "share_embedding": "cate_id", "feature_encoder": None})]
+    return specs
+
+
+@pytest.mark.parametrize("config", ["C3_DCNv2", "C4_DIN", "C5_DLRM_shape", "C2_xDeepFM"])
+def test_baseline_shapes_forward_and_step(config):
+    """BASELINE.json configs[2..4] (and xDeepFM at the C2 shape) at their full batch / field / sequence
+    sizes: predictions and loss against the oracle (1e-5), then one fused training step must run and
+    lower-bound sanity (finite loss, gradient arena consumed).  C5's 200 M-row vocabulary is reduced to
+    26 x 100 k rows so that the CPU oracle can hold it; the shapes that drive the kernels
+    (26 fields, D=16, 325 pair products, top MLP 64-64-64, batch 8192) are the real ones."""
+    from fuxictr_b200 import zoo, functional as F2
+    from fuxictr_b200.schema import FeatureMap
+    from oracle import fuxictr_oracle as O
+    gen = torch.Generator().manual_seed(5)
+    if config == "C4_DIN":
+        specs, B = _taobao_specs(), 2048
+    elif config == "C5_DLRM_shape":
+        specs, B = [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 100000})
+                    for i in range(26)], 8192
+    else:
+        specs = [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 25641})
+                 for i in range(39)]
+        B = 8192 if config == "C3_DCNv2" else 4096
+    fm = FeatureMap.from_specs(specs, embedding_dim=16)
+    cols = []
+    for name, sp in specs:
+        if sp["type"] == "sequence":
+            ids = torch.randint(1, sp["vocab_size"], (B, 50), generator=gen)
+            lens = torch.randint(1, 51, (B, 1), generator=gen)
+            cols.append((ids * (torch.arange(50).view(1, -1) < lens)).double())
+        else:
+            cols.append(torch.randint(1, sp["vocab_size"], (B, 1), generator=gen).double())
+    mat = torch.cat(cols + [(torch.rand(B, 1, generator=gen) < 0.25).double()], dim=1)
+    torch.manual_seed(2019)
+    spec_map = OrderedDict(specs)
+    if config == "C3_DCNv2":
+        model = zoo.DCNv2(fm, gpu=-1, embedding_dim=16, model_structure="parallel", num_cross_layers=3,
+                          parallel_dnn_hidden_units=[500, 500, 500])
+        pred = lambda s, X: torch.sigmoid(O.dcnv2_logit(spec_map, s, X, 3, 3))
+    elif config == "C4_DIN":
+        model = zoo.DIN(fm, gpu=-1, embedding_dim=16, dnn_hidden_units=[500, 500, 500], attention_hidden_units=[64],
+                        attention_hidden_activations="Dice")
+        pred = lambda s, X: O.din_pred(spec_map, s, X, 16, [("item_id", "cate_id")],
+                                       [("click_history", "cate_history")], 1, 3, training=True)
+    elif config == "C5_DLRM_shape":
+        model = zoo.DLRM(fm, gpu=-1, embedding_dim=16, top_mlp_units=[64, 64, 64], interaction_op="dot")
+        pred = lambda s, X: O.dlrm_pred(spec_map, s, X, 3)
+    else:
+        model = zoo.xDeepFM(fm, gpu=-1, embedding_dim=16, dnn_hidden_units=[400, 400, 400], cin_hidden_units=[16, 16, 16])
+        pred = lambda s, X: torch.sigmoid(O.xdeepfm_logit(spec_map, s, X, [16, 16, 16], 3))
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.Embedding):
+                m.weight[1:].normal_(0, 0.05)
+    state0 = OrderedDict((k, v.detach().clone()) for k, v in model.state_dict().items())
+    tr = O.OracleTrainer(state0, pred, spec_map, ["label"])
+    with torch.no_grad():
+        y_ref, y_true = tr.forward(fm.batch_dict(mat))
+        loss_ref = O.bce_mean(y_ref, y_true)
+    model.device = torch.device("cuda:0")
+    model.model_to_device()
+    model.compile("adam", "binary_crossentropy", 1e-3)
+    model.train()
+    batch = fm.batch_dict(mat.cuda())
+    with torch.no_grad():
+        y = model.forward(batch)["y_pred"]
+    assert close(y, y_ref, RTOL), rel_err(y, y_ref)
+    model.use_fused_optimizer()
+    if config == "C4_DIN":      # fresh Dice running statistics for the training step (the forward above updated them)
+        model.load_state_dict({k: v.cuda() for k, v in state0.items()})
+    loss = model.fused_train_step(batch)
+    torch.cuda.synchronize()
+    assert close(loss, loss_ref, RTOL), (float(loss), float(loss_ref))
+    assert float(model._arena.G.abs().sum()) == 0.0
+    assert all(torch.isfinite(p).all() for p in model.parameters())
