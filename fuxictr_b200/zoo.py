@@ -396,7 +396,11 @@ class DLRM(RankModel):
 
     def forward(self, inputs):
         X = self.get_inputs(inputs)
-        feat_emb = self.embedding_layer(X)
+        if getattr(self, "_sharded_front", None) is not None:   # row-sharded tables
+            from .sharded import sharded_front
+            feat_emb, _ = sharded_front(self._sharded_front, self._batch_matrix(inputs))
+        else:
+            feat_emb = self.embedding_layer(X)
         if self.dense_feats:
             dense_x = torch.cat([X[k] for k in self.dense_feats], dim=-1)
             dense_emb = self.bottom_mlp(dense_x)

@@ -99,3 +99,53 @@ def test_shard_roundtrip_gpu():
         shards = [SH.shard_rows(w, r, world) for r in range(world)]
         assert [s.shape[0] for s in shards] == [SH.local_rows(101, r, world) for r in range(world)]
         assert torch.equal(SH.unshard_rows(shards, 101), w)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_virtual_ranks_embedding_only(world):
+    """DLRM-style front: embeddings only (no LR tables, no FM term) over row shards."""
+    import __graft_entry__
+    __graft_entry__.build()
+    from fuxictr_b200 import layers, sharded as SH
+    from fuxictr_b200.schema import FeatureMap
+    nf, dim, B_l = 26, 16, 40
+    specs = [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 90 + 11 * i})
+             for i in range(nf)]
+    fm = FeatureMap.from_specs(specs, embedding_dim=dim)
+    torch.manual_seed(world)
+    emb_layer = layers.FeatureEmbedding(fm, dim, embedding_initializer="partial(nn.init.normal_, std=0.1)").cuda()
+    B = B_l * world
+    gen = torch.Generator().manual_seed(4)
+    ids = torch.cat([torch.randint(0, s["vocab_size"], (B, 1), generator=gen) for _, s in specs], dim=1)
+    mat = torch.cat([ids.double(), torch.zeros(B, 1, dtype=torch.float64)], dim=1).cuda()
+    gx = torch.randn(B, nf, dim, generator=gen).cuda()
+    X = OrderedDict((k, v) for k, v in fm.batch_dict(mat).items() if k != "label")
+    emb_ref = emb_layer(X)
+    (emb_ref * gx).sum().mul(1.0 / world).backward()
+    fed = emb_layer.embedding_layer
+    names = list(fm.features.keys())
+    registry, fronts, shard_tabs = {}, [], []
+    for r in range(world):
+        etabs = [SH.shard_rows(fed.embedding_layers[f].weight.detach(), r, world) for f in names]
+        shard_tabs.append(etabs)
+        fronts.append(SH.ShardedFront(SH.VirtualPeerGroup(r, world, registry), names, etabs, None,
+                                      [fed.embedding_layers[f].num_embeddings for f in names],
+                                      [fm.get_column_index(f) for f in names], [0] * nf, dim, B_l, mat.shape[1],
+                                      torch.float64, bias=None, want_fm=False))
+    for r, fr in enumerate(fronts):
+        fr.phase_ids(mat[r * B_l:(r + 1) * B_l])
+    for fr in fronts:
+        fr.phase_push()
+    outs = [fr.phase_reduce() for fr in fronts]
+    assert torch.equal(torch.cat([o[0] for o in outs]).view(B, nf, dim), emb_ref.detach())
+    zeros = torch.zeros(B_l, device="cuda")
+    for r, fr in enumerate(fronts):
+        fr.phase_gprep(gx[r * B_l:(r + 1) * B_l].reshape(B_l, -1).contiguous(), outs[r][0], None, zeros)
+    egrads = [[torch.zeros_like(t) for t in shard_tabs[r]] for r in range(world)]
+    for r, fr in enumerate(fronts):
+        fr.phase_pull(egrads[r], None)
+    torch.cuda.synchronize()
+    for i, f in enumerate(names):
+        full = SH.unshard_rows([egrads[r][i] for r in range(world)], fed.embedding_layers[f].num_embeddings)
+        ref = fed.embedding_layers[f].weight.grad
+        assert close(full, ref, RTOL, atol=RTOL * float(ref.abs().max())), f
