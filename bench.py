@@ -356,14 +356,10 @@ def run_b200_arm(args):
     model.train()
     host_batches = [m.pin_memory() for m in make_batches(args.nbatches, args.batch, seed=1000 + rank)]
     dev_batches = [m.cuda(non_blocking=True) for m in host_batches]
-    static_in = torch.empty_like(dev_batches[0])
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-    batch_views = fm.batch_dict(static_in)
-
-    def step_eager():
-        return model.fused_train_step(batch_views)
-
-    # launches per step (our kernels only): counted by wrapping the C-ABI call once
+    # launches per step (our kernels only): counted by wrapping the C-ABI call around one eager step
+    from fuxictr_b200.pipeline import TrainPipeline
+    pipe = TrainPipeline(model, args.batch, NF + 1, torch.float64, graph=False)
+    pipe.prime(dev_batches[0])
     counter = {"n": 0}
     orig_call = _lib.call
 
@@ -373,43 +369,22 @@ def run_b200_arm(args):
 
     if os.environ.get("B2_BENCH_VERBOSE"):
         sys.stderr.write("[bench r%d] model built\n" % rank); sys.stderr.flush()
-    static_in.copy_(dev_batches[0])
     _lib.call = counting_call
-    step_eager()
+    pipe.step_device(dev_batches[0])
     torch.cuda.synchronize()
     launches = counter["n"]
     _lib.call = orig_call
-
-    graph = None
-    loss_static = None
     if args.graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step_eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss_static = step_eager()
+        pipe._capture(3)        # the public constructor does this; done late here to count launches first
 
     if os.environ.get("B2_BENCH_VERBOSE"):
         sys.stderr.write("[bench r%d] graph captured\n" % rank); sys.stderr.flush()
 
     def run_step(i, e2e):
-        if e2e:
-            static_in.copy_(host_batches[i % len(host_batches)], non_blocking=True)   # H2D from pinned
-        else:
-            static_in.copy_(dev_batches[i % len(dev_batches)], non_blocking=True)    # already in HBM
-        if graph is not None:
-            graph.replay()
-            loss = loss_static
-        else:
-            loss = step_eager()
-        if e2e:
-            loss_host.copy_(loss.detach(), non_blocking=True)                        # D2H of the result
-        return loss
+        if e2e:     # the user-facing call: pinned host matrix -> async H2D (overlapping the previous
+            pipe.step(host_batches[i % len(host_batches)])     # step) -> graph replay -> loss D2H
+        else:       # inputs already resident in HBM
+            pipe.step_device(dev_batches[i % len(dev_batches)])
 
     def timed(e2e, steps, warmup):
         for i in range(warmup):
@@ -438,7 +413,7 @@ def run_b200_arm(args):
     ms_total = timed(False, args.steps, warmup)
     ms_e2e = timed(True, args.steps, warmup)
     clocks = sampler.stop() if rank == 0 else None
-    final_loss = float(loss_host.item())
+    final_loss = pipe.loss()
 
     def note(msg):
         if os.environ.get("B2_BENCH_VERBOSE"):
@@ -485,7 +460,8 @@ def run_b200_arm(args):
                                                    else "dense pass over the arena")),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": host_batches[0].numel() * 8 * world, "d2h_bytes_per_step": 4 * world},
+                    "h2d_bytes_per_step": pipe.h2d_bytes_per_step * world, "d2h_bytes_per_step": pipe.d2h_bytes_per_step * world,
+                    "api": "fuxictr_b200.pipeline.TrainPipeline.step (double-buffered H2D on a copy stream)"},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
             "cuda_graph": bool(args.graph), "final_loss": final_loss,
             "roofline": roofline, "kernels": kernels}

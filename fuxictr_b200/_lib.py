@@ -120,6 +120,10 @@ SIGNATURES = {
     "b2_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "b2_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
                              c_float, c_float, c_float, c_void_p, c_int, c_void_p]),
+    "b2_logloss_sum": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b2_auc_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(c_int64)]),
+    "b2_auc": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b2_sort_u32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
 }
 
 _lib = None

@@ -418,6 +418,27 @@ B2_API int b2_adam_step_sched(float* p, float* g, float* m, float* v, int64_t n,
                               float max_norm, float beta1, float beta2, float eps, const int64_t* step_dev,
                               const float* sched, int zero_grad, void* stream);
 
+/*
+ * Device-resident evaluation.  BaseModel.evaluate
+ * (fuxictr/pytorch/models/rank_model.py:350-381) moves y_pred / y_true to the host after every
+ * batch and calls sklearn's log_loss / roc_auc_score on float64 copies (fuxictr/metrics.py:45-48);
+ * these entry points compute the same two numbers from fp32 device arrays of the whole split.
+ *   b2_logloss_sum: sum[0] += sum_i -[y_i log(clip(p_i)) + (1-y_i) log(clip(1-p_i))], fp64,
+ *                   clip to [eps, 1-eps] with eps = DBL_EPSILON (sklearn clips the widened float64
+ *                   array); the caller zeroes sum and divides by n.
+ *   b2_auc: result (device, 5 x u64, zeroed inside) = {n_neg, n_pos, n_nan, n_badlabel, 2U} with
+ *           U = #(neg < pos) + 0.5 #(neg == pos) over all (pos, neg) pairs, exact in integers;
+ *           AUC = 2U / (2 n_pos n_neg).  Labels must be exactly 0 or 1 (others are counted in
+ *           n_badlabel and skipped; sklearn raises); NaN scores are counted in n_nan (sklearn
+ *           raises).  workspace: b2_auc_workspace_bytes(n) bytes, 256-byte aligned.
+ *   b2_sort_u32: ascending stable LSD radix sort (the building block of b2_auc), same workspace.
+ */
+B2_API int b2_logloss_sum(const float* y_pred, const float* y_true, int64_t n, double* sum, void* stream);
+B2_API int b2_auc_workspace_bytes(int64_t n, int64_t* bytes);
+B2_API int b2_auc(const float* y_pred, const float* y_true, int64_t n, void* workspace, int64_t workspace_bytes,
+                  uint64_t* result, void* stream);
+B2_API int b2_sort_u32(uint32_t* keys, int64_t n, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

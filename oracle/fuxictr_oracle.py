@@ -348,3 +348,52 @@ class OracleTrainer(object):
         torch.nn.utils.clip_grad_norm_(self.params, self.max_norm)
         self.optimizer.step()
         return loss
+
+
+# ----------------------------------------------------------------------------------------
+# Evaluation metrics (fuxictr/metrics.py:45-48 as called by rank_model.py:350-381), numpy.
+# The reference delegates to scikit-learn 1.x: log_loss (clip the float64 [1-p, p] rows to
+# [eps, 1-eps], mean of -xlogy) and roc_auc_score (trapezoid over the ROC curve == tie-aware
+# Mann-Whitney U / (P N)).  Restated here without sklearn and pinned to the real reference's output
+# in tests/golden/metrics_eval.npz.
+# ----------------------------------------------------------------------------------------
+def logloss(y_true, y_pred):
+    p = np.asarray(y_pred, dtype=np.float64).reshape(-1)
+    y = np.asarray(y_true, dtype=np.float64).reshape(-1)
+    eps = np.finfo(np.float64).eps
+    p1 = np.clip(p, eps, 1 - eps)
+    p0 = np.clip(1 - p, eps, 1 - eps)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        terms = np.where(y != 0, y * np.log(p1), 0.0) + np.where(y != 1, (1 - y) * np.log(p0), 0.0)
+    return float(-terms.mean())
+
+
+def auc_twice_u(y_true, y_pred):
+    """2U as an exact integer: sum over positives of #(neg < s) + #(neg <= s); also (P, N)."""
+    p = np.asarray(y_pred).reshape(-1)
+    y = np.asarray(y_true).reshape(-1)
+    neg = np.sort(p[y == 0])
+    pos = p[y == 1]
+    lower = np.searchsorted(neg, pos, side="left").astype(np.int64)
+    upper = np.searchsorted(neg, pos, side="right").astype(np.int64)
+    return int(lower.sum() + upper.sum()), int(pos.size), int(neg.size)
+
+
+def auc(y_true, y_pred):
+    twice_u, n_pos, n_neg = auc_twice_u(y_true, y_pred)
+    if n_pos == 0 or n_neg == 0:
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+    return twice_u / (2.0 * n_pos * n_neg)
+
+
+def evaluate_metrics(y_true, y_pred, metrics):
+    """metrics.py:26-52 for the pointwise metrics."""
+    out = OrderedDict()
+    for m in metrics:
+        if m in ("logloss", "binary_crossentropy"):
+            out[m] = logloss(y_true, y_pred)
+        elif m == "AUC":
+            out[m] = auc(y_true, y_pred)
+        else:
+            raise ValueError("metric={} not supported.".format(m))
+    return out

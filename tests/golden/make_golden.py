@@ -378,7 +378,35 @@ def case_init_parity():
                                   "kwargs": dict(embedding_dim=4, hidden_units=[8, 8])}, w=sd(model))
 
 
+def case_metrics():
+    """fuxictr.metrics.evaluate_metrics (metrics.py:26-48) as BaseModel.evaluate calls it: float64
+    copies of fp32 predictions.  Three splits: smooth scores, heavy ties, saturated (0/1) scores."""
+    import warnings
+    from fuxictr.metrics import evaluate_metrics
+    rng = np.random.default_rng(41)
+    cases = {}
+    n = 6000
+    y = (rng.random(n) < 0.25).astype(np.float32)
+    smooth = (1.0 / (1.0 + np.exp(-(rng.normal(size=n) + 1.5 * y - 1.0)))).astype(np.float32)
+    ties = np.round(smooth, 2).astype(np.float32)
+    sat = smooth.copy()
+    sat[:50], sat[50:100] = 0.0, 1.0
+    out, inp = {}, {}
+    for name, p in [("smooth", smooth), ("ties", ties), ("saturated", sat)]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = evaluate_metrics(np.array(y, np.float64), np.array(p, np.float64), ["logloss", "AUC"])
+        inp["y_pred_" + name] = p
+        out["logloss_" + name] = np.array(r["logloss"], np.float64)
+        out["auc_" + name] = np.array(r["AUC"], np.float64)
+    inp["y_true"] = y
+    save("metrics_eval", {"what": "fuxictr.metrics.evaluate_metrics(['logloss','AUC'])", "n": n}, **{"in": inp, "out": out})
+
+
 if __name__ == "__main__":
+    if "--only-metrics" in sys.argv:
+        case_metrics()
+        sys.exit(0)
     case_feature_embedding_tiny_npz()
     case_feature_embedding_dict_tiny_seq()
     case_logistic_regression_tiny_seq()
@@ -388,3 +416,4 @@ if __name__ == "__main__":
     case_mlp_dice_din()
     case_models()
     case_init_parity()
+    case_metrics()

@@ -222,3 +222,29 @@ def test_model_forward_grads_and_train_steps(name):
     for k, ref in g["w3"].items():
         if k in tr.state and tr.state[k].is_floating_point():
             assert rel_err(tr.state[k], ref) <= 5e-6, k
+
+
+def test_metrics_oracle_matches_reference(golden):
+    """oracle logloss / AUC (numpy restatement of sklearn's arithmetic) vs the real
+    fuxictr.metrics.evaluate_metrics on smooth, tied and saturated predictions."""
+    g = golden("metrics_eval")
+    y = g["in"]["y_true"].numpy()
+    for name in ("smooth", "ties", "saturated"):
+        p = g["in"]["y_pred_" + name].numpy()
+        r = O.evaluate_metrics(y, p, ["logloss", "AUC"])
+        assert abs(r["logloss"] - float(g["out"]["logloss_" + name])) <= 1e-13 * abs(float(g["out"]["logloss_" + name]))
+        assert abs(r["AUC"] - float(g["out"]["auc_" + name])) <= 1e-13
+
+
+def test_metrics_oracle_matches_sklearn_on_random_ties():
+    sk = pytest.importorskip("sklearn.metrics")
+    import warnings
+    rng = np.random.default_rng(5)
+    for n, decimals in [(1000, 1), (20000, 3), (5000, 8)]:
+        y = (rng.random(n) < 0.3).astype(np.float32)
+        p = np.round(rng.random(n), decimals).astype(np.float32)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ll = sk.log_loss(y.astype(np.float64), p.astype(np.float64))
+        assert abs(O.logloss(y, p) - ll) <= 1e-13 * ll
+        assert abs(O.auc(y, p) - sk.roc_auc_score(y.astype(np.float64), p.astype(np.float64))) <= 1e-13
