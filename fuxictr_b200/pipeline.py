@@ -57,7 +57,8 @@ class TrainPipeline(object):
     def _capture(self, warmup):
         """Warm-up steps run on a side stream (they are REAL optimizer steps on whatever static_in
         holds: load a valid batch with `prime()` first if the trajectory matters)."""
-        side = torch.cuda.Stream()
+        self.loss_dev = None            # a live loss of an earlier eager step pins its autograd graph (and the
+        side = torch.cuda.Stream()      # AccumulateGrad nodes' stream) and would invalidate the capture
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -66,7 +67,7 @@ class TrainPipeline(object):
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss_dev = self._eager()
+            self.loss_dev = self._eager().detach()
 
     def prime(self, matrix):
         """Put a valid batch into the static input (before capture warm-up / first replay)."""
@@ -77,7 +78,7 @@ class TrainPipeline(object):
         if self.graph is not None:
             self.graph.replay()
             return self.loss_dev
-        self.loss_dev = self._eager()
+        self.loss_dev = self._eager().detach()
         return self.loss_dev
 
     def step_device(self, dev_matrix):

@@ -181,9 +181,11 @@ def test_train_pipeline_matches_eager_steps(graph):
     prime = mats[0]
     pipe = TrainPipeline(model, B, len(specs) + 1, torch.float64, graph=False)
     pipe.prime(prime.cuda())
+    pipe.step_device(prime.cuda())                       # an eager step BEFORE the capture (bench.py counts launches so)
     if graph:
         pipe._capture(warm)                              # 3 real warm-up steps on the primed batch
     ref.train()
+    ref.fused_train_step(fm.batch_dict(prime.cuda()))
     if graph:
         for _ in range(warm):
             ref.fused_train_step(fm.batch_dict(prime.cuda()))
