@@ -57,6 +57,7 @@ SIGNATURES = {
     "b2_version": (ctypes.c_char_p, []),
     "b2_last_error": (ctypes.c_char_p, []),
     "b2_device_cc": (c_int, [c_int]),
+    "b2_set_l2_fetch_granularity": (c_int, [c_int]),
     "b2_embed_gather_fwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_embed_scatter_bwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "b2_lr_fwd": (c_int, [_FIELD_P, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -148,6 +149,11 @@ def load():
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = lib
+    gran = os.environ.get("B2_L2_FETCH", "")
+    if gran:      # diagnostic override of cudaLimitMaxL2FetchGranularity (see b2_set_l2_fetch_granularity)
+        rc = lib.b2_set_l2_fetch_granularity(int(gran))
+        if rc != 0 and lib.b2_device_cc(0) > 0:
+            raise B2Error("b2_set_l2_fetch_granularity(%s): %s" % (gran, lib.b2_last_error().decode()))
     return lib
 
 

@@ -24,3 +24,13 @@ extern "C" B2_API int b2_device_cc(int device) {
   }
   return prop.major * 10 + prop.minor;
 }
+
+extern "C" B2_API int b2_set_l2_fetch_granularity(int bytes) {
+  B2_REQUIRE(bytes == 32 || bytes == 64 || bytes == 128, "granularity %d not in {32, 64, 128}", bytes);
+  cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return b2_fail(B2_E_CUDA, "b2_set_l2_fetch_granularity: %s", cudaGetErrorString(e));
+  }
+  return B2_OK;
+}

@@ -20,26 +20,36 @@
 // Forward, fast path: no pooled field, every row fits one pass of its LPR lanes.
 // ---------------------------------------------------------------------------------
 template <int VEC>
-__device__ __forceinline__ typename VecT<VEC>::type b2_ld_row(const typename VecT<VEC>::type* p, bool stream) {
+__device__ __forceinline__ typename VecT<VEC>::type b2_ld_row(const typename VecT<VEC>::type* p, int mode) {
   return __ldg(p);
 }
+// mode 0: plain read-only load; 1: L1::no_allocate (one-touch); 2: read-only load with the L2::64B
+// prefetch-size hint — a D=16 row is exactly one 64-byte sector pair.  Measured: no gain in this kernel
+// (3773 vs 3755 GB/s, profiles/r1_gather_ceiling.md), kept selectable through B2_GATHER_STREAM=2.
 template <>
-__device__ __forceinline__ float4 b2_ld_row<4>(const float4* p, bool stream) {
-  return stream ? b2_ldg_stream(p) : __ldg(p);
+__device__ __forceinline__ float4 b2_ld_row<4>(const float4* p, int mode) {
+  if (mode == 2) {
+    float4 r;
+    asm volatile("ld.global.nc.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+  }
+  return mode == 1 ? b2_ldg_stream(p) : __ldg(p);
 }
 template <int VEC>
-__device__ __forceinline__ void b2_st_row(typename VecT<VEC>::type* p, const typename VecT<VEC>::type& v, bool stream) {
+__device__ __forceinline__ void b2_st_row(typename VecT<VEC>::type* p, const typename VecT<VEC>::type& v, int mode) {
   *p = v;
 }
 template <>
-__device__ __forceinline__ void b2_st_row<4>(float4* p, const float4& v, bool stream) {
-  if (stream) b2_stg_stream(p, v); else *p = v;
+__device__ __forceinline__ void b2_st_row<4>(float4* p, const float4& v, int mode) {
+  if (mode == 1) b2_stg_stream(p, v); else *p = v;
 }
 
 template <typename IdxT, int VEC, int UNROLL>
 __global__ void __launch_bounds__(256)
 gather_fast_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int lpr_log2,
-                   int32_t* __restrict__ status, bool stream) {
+                   int32_t* __restrict__ status, int stream) {
   using V = typename VecT<VEC>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemFields sf = b2_stage_fields(pack, smem_raw);
@@ -355,7 +365,7 @@ static int launch_gather(const B2FieldPack& pack, int64_t batch, int vec, int ma
     static const int env_stream = getenv("B2_GATHER_STREAM") ? atoi(getenv("B2_GATHER_STREAM")) : -1;
     const bool big = nitems >= (int64_t) 1 << 20;
     const int unroll = env_unroll ? env_unroll : (big ? 8 : 4);
-    const bool stream = env_stream > 0;  // measured (10 GB tables, B=524288): 3.77 TB/s plain vs 3.65 TB/s streaming
+    const int stream = env_stream > 0 ? env_stream : 0;  // load flavour (b2_ld_row); measured (10 GB tables, B=524288): 3.77 TB/s plain vs 3.65 TB/s streaming
     if (unroll == 8) {
       const int grid = grid_for(b2_ceil_div(nitems, 8) << lpr_log2, block);
       if (vec == 4) gather_fast_kernel<IdxT, 4, 8><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);

@@ -65,6 +65,11 @@ B2_API const char* b2_last_error(void);
 /* Returns the compute capability major*10+minor of `device`, or a negative
  * error.  The library only contains sm_100a code. */
 B2_API int b2_device_cc(int device);
+/* Sets cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes) on the current device: how much L2 pulls
+ * from HBM around a missing 32-byte sector.  Embedding rows are 64 bytes (D=16 fp32) at random
+ * addresses; with 128-byte fetches every row read costs 128 bytes of DRAM traffic
+ * (profiles/r1_gather_ceiling.md).  A context-wide hint; no effect on results. */
+B2_API int b2_set_l2_fetch_granularity(int bytes);
 
 /*
  * One feature of the fused multi-field gather.  Mirrors one iteration of the

@@ -1,16 +1,26 @@
-"""Diagnostic: fused gather bandwidth on tables >> L2 for a few launch variants."""
-import os, sys, subprocess, json
-if len(sys.argv) > 1 and sys.argv[1] == "child":
-    import torch
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import bench
-    print(json.dumps(bench.gather_stress(bench.load_peaks())["points"]))
-else:
-    for unroll, stream in [(4, 0), (4, 1), (8, 0), (8, 1)]:
-        env = dict(os.environ, B2_GATHER_UNROLL=str(unroll), B2_GATHER_STREAM=str(stream))
-        out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        try:
-            pts = json.loads(out.stdout.strip().splitlines()[-1])
-            print("unroll", unroll, "stream", stream, [(p["batch"], round(p["GBps"]), round(p["frac_of_measured_hbm"], 3)) for p in pts], flush=True)
-        except Exception:
-            print("unroll", unroll, "stream", stream, "FAILED", out.stderr[-400:], flush=True)
+"""Diagnostic: fused gather bandwidth on tables >> L2 (10 GB) for cudaLimitMaxL2FetchGranularity
+settings (one process; the limit is changed between measurements)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import bench  # noqa: E402
+import __graft_entry__  # noqa: E402
+
+__graft_entry__.build()
+from fuxictr_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+torch.zeros(1, device="cuda")
+for gran in [None, 32, 64, 128, 32]:
+    if gran is not None:
+        rc = lib.b2_set_l2_fetch_granularity(gran)
+        if rc != 0:
+            print(json.dumps({"l2_fetch": gran, "error": lib.b2_last_error().decode()}), flush=True)
+            continue
+    pts = bench.gather_stress(bench.load_peaks())["points"]
+    print(json.dumps({"l2_fetch": gran or "default",
+                      "points": [(p["batch"], round(p["ms"], 4), round(p["GBps"]), round(p["frac_of_measured_hbm"], 3))
+                                 for p in pts]}), flush=True)
