@@ -91,17 +91,20 @@ class TrainPipeline(object):
         """Batch in host memory, laid out as the collator yields it.  Fully asynchronous: returns
         after enqueueing the H2D (copy stream), the replay and the loss D2H; read the loss with
         `loss()`.  A pinned `host_matrix` is copied from directly and must stay untouched until
-        this step's H2D finished (`wait_inputs()`); a pageable one is staged through the pipeline's
-        own pinned ring first."""
+        this step's H2D finished — guaranteed once `depth` further step() calls were entered, or after
+        `wait_inputs()`; a pageable one is staged through the pipeline's own pinned ring first."""
         if tuple(host_matrix.shape) != self.shape or host_matrix.dtype != self.dtype:
             raise ValueError("batch matrix %s %s does not match the pipeline's %s %s"
                              % (tuple(host_matrix.shape), host_matrix.dtype, self.shape, self.dtype))
         d = self._k % len(self._stage)
         self._k += 1
+        # Host throttle: at most `depth` H2D copies are ever outstanding, so a caller that feeds pinned
+        # ring buffers (dataloader.py) knows the copy of batch k-depth has left its source when step(k)
+        # is entered.  The event is normally long complete; this costs a microsecond.
+        self._h2d_done[d].synchronize()
         if not host_matrix.is_pinned():
             if self._pinned[d] is None:
                 self._pinned[d] = torch.empty(self.shape, dtype=self.dtype).pin_memory()
-            self._h2d_done[d].synchronize()      # the previous H2D out of this pinned slot is done
             self._pinned[d].copy_(host_matrix)
             host_matrix = self._pinned[d]
         compute = torch.cuda.current_stream()

@@ -204,3 +204,46 @@ def test_train_pipeline_matches_eager_steps(graph):
     assert pipe.h2d_bytes_per_step == B * (len(specs) + 1) * 8 and pipe.d2h_bytes_per_step == 4
     with pytest.raises(ValueError):
         pipe.step(torch.zeros(B, len(specs), dtype=torch.float64))
+
+
+def test_loader_feeds_pipeline_from_pinned_ring(tmp_path):
+    """dataloader.NpzDataLoader(shuffle=True).matrices() -> TrainPipeline.step: the pinned ring slots
+    are consumed asynchronously (copy stream) while the prefetch thread refills later slots; the
+    trajectory equals eager steps over the same (cloned) batches, and model.evaluate() runs over the
+    loader's dict protocol."""
+    from fuxictr_b200 import dataloader as DL
+    from fuxictr_b200.pipeline import TrainPipeline
+    fm, specs, ref = _small_deepfm()
+    _, _, model = _small_deepfm()
+    rng = np.random.default_rng(0)
+    n, B = 4096 + 37, 128
+    cols = {name: rng.integers(0, s["vocab_size"], n).astype(np.int64) for name, s in specs}
+    cols["label"] = (rng.random(n) < 0.4).astype(np.float64)
+    path = str(tmp_path / "train.npz")
+    np.savez(path, **cols)
+    loader = DL.NpzDataLoader(fm, path, batch_size=B, shuffle=True)
+    assert loader.matrix.is_pinned() and len(loader) == 33
+    torch.manual_seed(5)
+    kept = [m.clone() for m in loader.matrices()]          # the epoch's batches, in order
+    ref.use_fused_optimizer()
+    model.use_fused_optimizer()
+    ref.train()
+    want = [float(ref.fused_train_step(fm.batch_dict(m.cuda()))) for m in kept[:-1]]
+    pipe = TrainPipeline(model, B, len(specs) + 1, torch.float64, graph=False)
+    torch.manual_seed(5)
+    got = []
+    for m in loader.matrices():
+        if m.shape[0] != B:                                # the short last batch is not the captured shape
+            break
+        assert m.is_pinned()
+        pipe.step(m)                                       # no host sync here: the ring must stay ahead safely
+        got.append(pipe.loss_host.clone())                 # (value read after the epoch)
+    last = pipe.loss()
+    assert len(got) == len(want) == 32
+    assert abs(last - want[-1]) <= 1e-5 * abs(want[-1])
+    dn, pn = dict(ref.named_parameters()), dict(model.named_parameters())
+    for k in dn:
+        err = float((dn[k] - pn[k]).abs().max())
+        assert err <= 1e-5 * max(float(dn[k].abs().max()), 1e-3), (k, err)
+    logs = model.evaluate(loader, metrics=["logloss", "AUC"])
+    assert 0.0 < logs["AUC"] < 1.0 and logs["logloss"] > 0.0
