@@ -375,7 +375,12 @@ def run_b200_arm(args):
     launches = counter["n"]
     _lib.call = orig_call
     if args.graph:
-        pipe._capture(3)        # the public constructor does this; done late here to count launches first
+        try:
+            pipe._capture(3)    # the public constructor does this; done late here to count launches first
+        except Exception as exc:   # report an eager number rather than none (the JSON line says cuda_graph: false)
+            sys.stderr.write("[bench r%d] CUDA-graph capture failed (%r); timing the eager step\n" % (rank, exc))
+            pipe.graph, pipe.loss_dev = None, None
+            torch.cuda.synchronize()
 
     if os.environ.get("B2_BENCH_VERBOSE"):
         sys.stderr.write("[bench r%d] graph captured\n" % rank); sys.stderr.flush()
@@ -463,7 +468,7 @@ def run_b200_arm(args):
                     "h2d_bytes_per_step": pipe.h2d_bytes_per_step * world, "d2h_bytes_per_step": pipe.d2h_bytes_per_step * world,
                     "api": "fuxictr_b200.pipeline.TrainPipeline.step (double-buffered H2D on a copy stream)"},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
-            "cuda_graph": bool(args.graph), "final_loss": final_loss,
+            "cuda_graph": pipe.graph is not None, "final_loss": final_loss,
             "roofline": roofline, "kernels": kernels}
     if world == 1:
         try:

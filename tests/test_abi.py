@@ -72,3 +72,27 @@ def test_missing_library_is_a_hard_error(lib, monkeypatch):
     monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libfuxictr_b200.so")
     with pytest.raises(ImportError):
         lib.load()
+
+
+def test_metric_entry_points_validate_before_cuda(lib):
+    """b2_auc / b2_sort_u32 / b2_logloss_sum reject bad sizes, NULLs, small or misaligned workspaces
+    without touching a device; b2_auc_workspace_bytes is pure arithmetic."""
+    L = lib.load()
+    null = ctypes.c_void_p(0)
+    nbytes = ctypes.c_int64(0)
+    assert L.b2_auc_workspace_bytes(1000, ctypes.byref(nbytes)) == 0
+    small = nbytes.value
+    assert small >= 2 * 4 * 1000 + 256 * 4 and small % 256 == 0
+    assert L.b2_auc_workspace_bytes(6_000_000, ctypes.byref(nbytes)) == 0 and nbytes.value > 48_000_000
+    assert L.b2_auc_workspace_bytes(0, ctypes.byref(nbytes)) == -1
+    assert L.b2_auc_workspace_bytes(1 << 31, ctypes.byref(nbytes)) == -1 and b"2^31" in L.b2_last_error()
+    ptr = ctypes.c_void_p(4096)
+    assert L.b2_auc(null, ptr, 10, ptr, 1 << 20, ptr, null) == -1 and b"NULL" in L.b2_last_error()
+    assert L.b2_auc(ptr, ptr, 1000, ptr, small - 1, ptr, null) == -1 and b"workspace" in L.b2_last_error()
+    assert L.b2_auc(ptr, ptr, 1000, ctypes.c_void_p(4096 + 8), small, ptr, null) == -1 and b"aligned" in L.b2_last_error()
+    assert L.b2_auc(ptr, ptr, 1000, ptr, small, ctypes.c_void_p(4100), null) == -1
+    assert L.b2_sort_u32(null, 0, null, 0, null) == 0                     # empty input: nothing to do
+    assert L.b2_sort_u32(null, 5, ptr, small, null) == -1
+    assert L.b2_logloss_sum(null, null, 0, null, null) == 0
+    assert L.b2_logloss_sum(null, ptr, 4, ptr, null) == -1
+    assert L.b2_set_l2_fetch_granularity(48) == -1 and b"granularity" in L.b2_last_error()
