@@ -376,7 +376,7 @@ def run_b200_arm(args):
     _lib.call = orig_call
     if args.graph:
         try:
-            pipe._capture(3)    # the public constructor does this; done late here to count launches first
+            pipe.capture(3)     # the constructor does this for graph=True; done late here to count launches first
         except Exception as exc:   # report an eager number rather than none (the JSON line says cuda_graph: false)
             sys.stderr.write("[bench r%d] CUDA-graph capture failed (%r); timing the eager step\n" % (rank, exc))
             pipe.graph, pipe.loss_dev = None, None

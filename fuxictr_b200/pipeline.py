@@ -35,7 +35,7 @@ class TrainPipeline(object):
         self.shape = (int(batch_rows), int(matrix_width))
         self.dtype = dtype
         self.static_in = torch.zeros(self.shape, dtype=dtype, device=dev)
-        self._views = model.feature_map.batch_dict(self.static_in)
+        self._views = model.feature_map.batch_views(self.static_in)     # every entry aliases static_in
         self._stage = [torch.empty_like(self.static_in) for _ in range(depth)]
         self._pinned = [None] * depth           # lazily allocated: only for callers with pageable matrices
         self._h2d_done = [torch.cuda.Event() for _ in range(depth)]
@@ -53,6 +53,10 @@ class TrainPipeline(object):
     # -- capture ---------------------------------------------------------------------------------
     def _eager(self):
         return self.model.fused_train_step(self._views)
+
+    def capture(self, warmup=3):
+        """Capture the step into a CUDA graph now (what graph=True does in the constructor)."""
+        self._capture(warmup)
 
     def _capture(self, warmup):
         """Warm-up steps run on a side stream (they are REAL optimizer steps on whatever static_in

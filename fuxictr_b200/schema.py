@@ -97,6 +97,21 @@ class FeatureMap(object):
             self.set_column_index()
         return self.column_index[feature]
 
+    def batch_views(self, batch_matrix):
+        """Like batch_dict, but sequence features are column-RANGE views too (their columns are
+        consecutive), so every entry aliases `batch_matrix`: what a static, graph-captured input
+        buffer needs (pipeline.TrainPipeline).  The fused gather takes the row stride as is."""
+        out = {}
+        for c in list(self.features.keys()) + list(self.labels):
+            idx = self.get_column_index(c)
+            if isinstance(idx, list):
+                if idx != list(range(idx[0], idx[0] + len(idx))):
+                    raise ValueError("feature %s: columns %s are not consecutive" % (c, idx))
+                out[c] = batch_matrix[:, idx[0]:idx[0] + len(idx)]
+            else:
+                out[c] = batch_matrix[:, idx]
+        return out
+
     def batch_dict(self, batch_matrix):
         """name -> column view(s) of one (B, input_length + n_labels) matrix, as the collator
         hands them to the model (scalar features are strided views, sequences are copies)."""

@@ -110,3 +110,22 @@ def test_unsupported_configs_fail_loudly():
         zoo.DCNv2(fm_from(g, 8), gpu=-1, use_low_rank_mixture=True, parallel_dnn_hidden_units=[8])
     with pytest.raises(ValueError):
         layers.InnerProductInteraction(4, output="nope")
+
+
+def test_batch_views_alias_the_matrix_for_sequences_too():
+    """schema.FeatureMap.batch_views: every entry (scalar columns AND sequence column ranges) is a
+    view of the batch matrix, so a graph-captured static input stays live; values equal batch_dict."""
+    import torch
+    from fuxictr_b200.schema import FeatureMap
+    specs = [("u", {"type": "categorical", "source": "", "vocab_size": 9}),
+             ("hist", {"type": "sequence", "source": "", "vocab_size": 9, "max_len": 4}),
+             ("i", {"type": "categorical", "source": "", "vocab_size": 9})]
+    fm = FeatureMap.from_specs(specs, embedding_dim=4)
+    mat = torch.arange(5 * 7, dtype=torch.float64).reshape(5, 7)
+    views, copies = fm.batch_views(mat), fm.batch_dict(mat)
+    assert list(views.keys()) == list(copies.keys()) == ["u", "hist", "i", "label"]
+    for k in views:
+        assert torch.equal(views[k], copies[k])
+    mat.mul_(-1)
+    assert torch.equal(views["hist"], mat[:, 1:5]) and views["hist"].stride() == (7, 1)
+    assert not torch.equal(copies["hist"], mat[:, 1:5])        # the collator-style entry is a copy
