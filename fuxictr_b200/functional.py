@@ -5,7 +5,6 @@ tape; all arithmetic happens in libfuxictr_b200.so.  Every function requires CUD
 tensors and raises otherwise — there is no eager/CPU fallback on this path.
 """
 import ctypes
-from collections import OrderedDict
 
 import torch
 

@@ -13,7 +13,6 @@ Pinning: tests/golden/*.npz hold inputs, weights, outputs and gradients produced
 REAL reference modules (imported from /root/reference by tests/golden/make_golden.py in the
 build container); tests/test_oracle_golden.py checks every function here against them.
 """
-import math
 from collections import OrderedDict
 
 import numpy as np

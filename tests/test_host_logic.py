@@ -1,8 +1,6 @@
 """Host-side mirror of the reference interface, CPU only: schema, construction order /
 state_dict keys (pinned by reference goldens), launch plans, and the refusal to compute
 on CPU tensors (there is no fallback path)."""
-import os
-from collections import OrderedDict
 
 import pytest
 import torch

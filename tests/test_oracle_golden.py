@@ -1,7 +1,6 @@
 """Pins oracle/fuxictr_oracle.py against fixtures produced by the REAL reference
 (tests/golden/make_golden.py).  CPU only.  Tolerance: the integer gather is bit-exact;
 float results must agree to 1e-6 relative (same ATen ops, same order)."""
-import os
 import sys
 from collections import OrderedDict
 
