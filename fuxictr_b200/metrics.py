@@ -108,3 +108,29 @@ class DeviceMetrics(object):
 
     def compute(self, metrics):
         return evaluate_metrics(self._true[:self.n], self._pred[:self.n], metrics)
+
+
+def device_metrics_supported(metrics, group_id=None):
+    """True when every requested metric is one of the pointwise device metrics."""
+    return group_id is None and all(m in _DEVICE_METRICS for m in metrics)
+
+
+def evaluate_generator(model, data_generator, metrics):
+    """The loop of BaseModel.evaluate (rank_model.py:360-381) with device-resident accumulation:
+    `model` needs .forward(batch) -> {"y_pred"}, .get_labels(batch), .device, .eval()."""
+    model.eval()
+    with torch.no_grad():
+        acc = DeviceMetrics(model.device)
+        for batch_data in data_generator:
+            acc.append(model.forward(batch_data)["y_pred"], model.get_labels(batch_data))
+        return acc.compute(metrics)
+
+
+def predict_generator(model, data_generator):
+    """BaseModel.predict (rank_model.py:383-398): flattened float64 numpy array, one D2H."""
+    model.eval()
+    with torch.no_grad():
+        acc = DeviceMetrics(model.device)
+        for batch_data in data_generator:
+            acc.append(model.forward(batch_data)["y_pred"])
+        return acc.predictions().cpu().numpy().astype("float64")

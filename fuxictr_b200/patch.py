@@ -10,8 +10,12 @@ calls the reference's original forward (the reference's own code, not a fallback
 
 Patched: FeatureEmbedding, FeatureEmbeddingDict, LogisticRegression, InnerProductInteraction,
 CrossNet, CrossNetV2, CompressedInteractionNet, DIN_Attention, Dice, MLP_Block
-(fuxictr/pytorch/layers/**).
+(fuxictr/pytorch/layers/**); and BaseModel.evaluate / BaseModel.predict
+(fuxictr/pytorch/models/rank_model.py:350-398): for a model on a CUDA device
+whose metrics are logloss / AUC (no group metrics) the predictions stay in HBM and
+csrc/metrics.cu computes the numbers; any other case runs the reference's own method.
 """
+import logging
 import functools
 
 import torch
@@ -66,6 +70,33 @@ def _mlp_supported(self):
     return True
 
 
+def _wrap_base_model(base_cls):
+    from . import metrics as DM
+    orig_evaluate, orig_predict = base_cls.evaluate, base_cls.predict
+    _ORIGINALS[(base_cls, "evaluate")], _ORIGINALS[(base_cls, "predict")] = orig_evaluate, orig_predict
+
+    def _device_model(self):
+        return _STATE["enabled"] and getattr(self, "device", None) is not None and self.device.type == "cuda"
+
+    @functools.wraps(orig_evaluate)
+    def evaluate(self, data_generator, metrics=None):
+        names = metrics if metrics is not None else self.validation_metrics
+        if _device_model(self) and DM.device_metrics_supported(names, getattr(self.feature_map, "group_id", None)):
+            _STATE["calls"]["evaluate"] = _STATE["calls"].get("evaluate", 0) + 1
+            val_logs = DM.evaluate_generator(self, data_generator, names)
+            logging.info("[Metrics] " + " - ".join("{}: {:.6f}".format(k, v) for k, v in val_logs.items()))
+            return val_logs
+        return orig_evaluate(self, data_generator, metrics)
+
+    @functools.wraps(orig_predict)
+    def predict(self, data_generator):
+        if _device_model(self):
+            _STATE["calls"]["predict"] = _STATE["calls"].get("predict", 0) + 1
+            return DM.predict_generator(self, data_generator)
+        return orig_predict(self, data_generator)
+    base_cls.evaluate, base_cls.predict = evaluate, predict
+
+
 def enable():
     """Patch the reference classes in place (idempotent).  Raises ImportError when the reference
     package is not importable — this module is only meaningful next to it."""
@@ -73,6 +104,8 @@ def enable():
     if _ORIGINALS:
         _STATE["enabled"] = True
         return
+    from fuxictr.pytorch.models.rank_model import BaseModel
+    _wrap_base_model(BaseModel)
     # helper methods the mirrored forwards call on `self`
     _graft_methods(R.FeatureEmbeddingDict, M.FeatureEmbeddingDict,
                    ["_active_features", "_is_fusable", "_plan", "_fused_arena", "forward_tensor"])

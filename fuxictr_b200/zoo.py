@@ -140,27 +140,16 @@ class RankModel(nn.Module):
     def evaluate(self, data_generator, metrics=None):
         """Same contract as BaseModel.evaluate; predictions and labels stay in HBM (no per-batch
         `.cpu().numpy()`), logloss / AUC come from csrc/metrics.cu, one small D2H at the end."""
-        from .metrics import DeviceMetrics
+        from .metrics import evaluate_generator
         self.materialize_tables()
-        self.eval()
-        with torch.no_grad():
-            acc = DeviceMetrics(self.device)
-            for batch_data in data_generator:
-                return_dict = self.forward(batch_data)
-                acc.append(return_dict["y_pred"], self.get_labels(batch_data))
-            names = metrics if metrics is not None else getattr(self, "validation_metrics", ["logloss", "AUC"])
-            return acc.compute(names)
+        names = metrics if metrics is not None else getattr(self, "validation_metrics", ["logloss", "AUC"])
+        return evaluate_generator(self, data_generator, names)
 
     def predict(self, data_generator):
         """BaseModel.predict: flattened float64 numpy array; one D2H for the whole generator."""
-        from .metrics import DeviceMetrics
+        from .metrics import predict_generator
         self.materialize_tables()
-        self.eval()
-        with torch.no_grad():
-            acc = DeviceMetrics(self.device)
-            for batch_data in data_generator:
-                acc.append(self.forward(batch_data)["y_pred"])
-            return acc.predictions().cpu().numpy().astype("float64")
+        return predict_generator(self, data_generator)
 
     # -- B200 extension: flat arenas + 2-kernel clip/Adam -------------------------------------
     def enable_sharding(self, group, batch_local, matrix_width, idx_dtype=torch.float64, want_fm=True):

@@ -82,3 +82,39 @@ def test_cuda_tensors_are_routed_to_the_kernels(ref, monkeypatch):
         assert patch.call_counts().get("FeatureEmbedding", 0) >= 1
     finally:
         patch.disable()
+
+
+def test_evaluate_is_patched_but_cpu_models_use_the_reference_path(ref, monkeypatch):
+    """BaseModel.evaluate / predict: a CPU model keeps the reference's sklearn path (identical
+    numbers to fuxictr.metrics); a model that claims a CUDA device is routed to the device metrics
+    (which refuse CPU tensors loudly here, where there is no GPU)."""
+    import numpy as np
+    from fuxictr_b200 import patch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle import fuxictr_oracle as O
+    g = Golden("model_DeepFM")
+    patch.enable()
+    try:
+        fm, model = build_ref_deepfm(ref, g)
+        model._verbose = 0
+        B = g.meta["batch"]
+        mats = [g["in"]["matrix"][:B], g["in"]["matrix"][:B // 2]]
+        cols = list(fm.features.keys()) + fm.labels
+        gen = [{c: m[:, fm.get_column_index(c)] for c in cols} for m in mats]
+        logs = model.evaluate(gen, metrics=["logloss", "AUC"])
+        preds = model.predict(gen)
+        assert patch.call_counts().get("evaluate", 0) == 0 and patch.call_counts().get("predict", 0) == 0
+        y = np.concatenate([m[:, -1].numpy() for m in mats])
+        want = O.evaluate_metrics(y, preds, ["logloss", "AUC"])
+        assert abs(logs["logloss"] - want["logloss"]) <= 1e-12 and abs(logs["AUC"] - want["AUC"]) <= 1e-12
+        monkeypatch.setattr(model, "device", torch.device("cuda:0"))
+        with pytest.raises((RuntimeError, AssertionError)):
+            model.evaluate(gen, metrics=["logloss", "AUC"])
+        assert patch.call_counts().get("evaluate", 0) == 1
+        # group metrics stay on the reference path even for a CUDA model
+        fm.group_id = "C0"
+        with pytest.raises(Exception):
+            model.evaluate(gen, metrics=["gAUC"])
+        assert patch.call_counts().get("evaluate", 0) == 1
+    finally:
+        patch.disable()
