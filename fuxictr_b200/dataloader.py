@@ -150,31 +150,53 @@ class _MatrixLoaderBase(object):
 # In-memory splits (NpzDataLoader / ParquetDataLoader)
 # ----------------------------------------------------------------------------------------------
 class MatrixDataLoader(_MatrixLoaderBase):
-    """One file, whole split resident in (pinned) host memory."""
+    """One file, whole split resident in (pinned) host memory.
 
-    def __init__(self, feature_map, darray, batch_size=32, shuffle=False, pin="auto"):
+    shard=(rank, world) is the data-parallel view for one-process-per-GPU runs (the
+    reference is single-device): a GLOBAL batch is `batch_size * world` rows, taken in exactly the
+    order the unsharded loader with that batch size would take them, and this rank gets rows
+    [rank*batch_size, (rank+1)*batch_size) of it.  Every rank must seed the torch RNG identically so
+    all draw the same permutation.  An incomplete last global batch is dropped (drop_last=True, the
+    default when sharded: the captured step has a fixed shape) or split as evenly as its rows allow."""
+
+    def __init__(self, feature_map, darray, batch_size=32, shuffle=False, pin="auto", shard=None,
+                 drop_last=None):
         super(MatrixDataLoader, self).__init__(feature_map, batch_size, pin)
         self.matrix = _to_host_tensor(darray, pin)
         self.shuffle = shuffle
+        self.rank, self.world = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+        if not 0 <= self.rank < self.world:
+            raise ValueError("shard=(rank, world) needs 0 <= rank < world, got %s" % (shard,))
+        self.drop_last = (self.world > 1) if drop_last is None else bool(drop_last)
         self.num_samples = self.matrix.shape[0]
         self.num_blocks = 1
-        self.num_batches = int(np.ceil(self.num_samples * 1.0 / self.batch_size))
+        gb = self.batch_size * self.world
+        self.num_batches = self.num_samples // gb if self.drop_last else int(np.ceil(self.num_samples * 1.0 / gb))
         self._slots = None
         self._ring_backed = bool(shuffle)
 
+    def _spans(self):
+        """(lo, hi) row ranges, in visiting order, of this rank's share of each global batch."""
+        n, B, gb = self.num_samples, self.batch_size, self.batch_size * self.world
+        for g0 in range(0, n, gb):
+            rows = min(gb, n - g0)
+            if rows < gb and self.drop_last:
+                return
+            lo = min(self.rank * B, rows)
+            yield g0 + lo, g0 + min(lo + B, rows)
+
     def matrices(self):
-        n, B = self.num_samples, self.batch_size
         if not self.shuffle:
-            for lo in range(0, n, B):
-                yield self.matrix[lo:lo + B]            # zero-copy slice of the pinned split
+            for lo, hi in self._spans():
+                yield self.matrix[lo:hi]                # zero-copy slice of the pinned split
             return
-        perm = torch_loader_permutation(n)              # on the caller's thread: global RNG order as torch's
+        perm = torch_loader_permutation(self.num_samples)   # on the caller's thread: global RNG order as torch's
         if self._slots is None:
             self._slots = self._ring_slots(self.matrix.shape[1], self.matrix.numpy().dtype)
 
         def produce():
-            for k, lo in enumerate(range(0, n, B)):
-                idx = perm[lo:lo + B]
+            for k, (lo, hi) in enumerate(self._spans()):
+                idx = perm[lo:hi]
                 slot = self._slots[k % self.ring][:idx.numel()]
                 torch.index_select(self.matrix, 0, idx, out=slot)
                 yield slot
@@ -186,21 +208,23 @@ class NpzDataLoader(MatrixDataLoader):
     """fuxictr.pytorch.dataloaders.NpzDataLoader (npz_dataloader.py:69-97).  num_workers is accepted
     and ignored: there is no per-row work left to parallelise."""
 
-    def __init__(self, feature_map, data_path, batch_size=32, shuffle=False, num_workers=1, pin="auto", **kwargs):
+    def __init__(self, feature_map, data_path, batch_size=32, shuffle=False, num_workers=1, pin="auto", shard=None,
+                 drop_last=None, **kwargs):
         if not data_path.endswith(".npz"):
             data_path += ".npz"
-        super(NpzDataLoader, self).__init__(feature_map, load_npz_matrix(feature_map, data_path),
-                                            batch_size=batch_size, shuffle=shuffle, pin=pin)
+        super(NpzDataLoader, self).__init__(feature_map, load_npz_matrix(feature_map, data_path), batch_size=batch_size,
+                                           shuffle=shuffle, pin=pin, shard=shard, drop_last=drop_last)
 
 
 class ParquetDataLoader(MatrixDataLoader):
     """fuxictr.pytorch.dataloaders.ParquetDataLoader (parquet_dataloader.py:77-106)."""
 
-    def __init__(self, feature_map, data_path, batch_size=32, shuffle=False, num_workers=1, pin="auto", **kwargs):
+    def __init__(self, feature_map, data_path, batch_size=32, shuffle=False, num_workers=1, pin="auto", shard=None,
+                 drop_last=None, **kwargs):
         if not data_path.endswith(".parquet"):
             data_path += ".parquet"
-        super(ParquetDataLoader, self).__init__(feature_map, load_parquet_matrix(feature_map, data_path),
-                                                batch_size=batch_size, shuffle=shuffle, pin=pin)
+        super(ParquetDataLoader, self).__init__(feature_map, load_parquet_matrix(feature_map, data_path), batch_size=batch_size,
+                                           shuffle=shuffle, pin=pin, shard=shard, drop_last=drop_last)
 
 
 # ----------------------------------------------------------------------------------------------

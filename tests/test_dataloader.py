@@ -192,3 +192,36 @@ def test_prefetcher_surfaces_producer_errors():
     assert next(it) == 1
     with pytest.raises(ValueError, match="boom"):
         next(it)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_loader_is_a_partition_of_the_global_batches(world, shuffle):
+    """shard=(rank, world): rank r holds rows [r*B, (r+1)*B) of every global batch of B*world rows —
+    concatenating the ranks rebuilds the unsharded loader's batches (same seed on every rank)."""
+    from fuxictr_b200 import dataloader as DL
+    fm = _feature_map("tiny_npz")
+    path = os.path.join(FIXTURES, "tiny_npz", "train")
+    B = 16
+    torch.manual_seed(9)
+    whole = [m.clone() for m in DL.NpzDataLoader(fm, path, batch_size=B * world, shuffle=shuffle, pin=False).matrices()]
+    parts = []
+    for r in range(world):
+        torch.manual_seed(9)
+        loader = DL.NpzDataLoader(fm, path, batch_size=B, shuffle=shuffle, pin=False, shard=(r, world))
+        parts.append([m.clone() for m in loader.matrices()])
+        assert len(parts[-1]) == len(loader) == 203 // (B * world)          # incomplete last global batch dropped
+        assert all(m.shape[0] == B for m in parts[-1])
+    for g in range(len(parts[0])):
+        assert torch.equal(torch.cat([parts[r][g] for r in range(world)]), whole[g])
+    # drop_last=False: the tail is split in rank order, short or empty shares allowed
+    tails = []
+    for r in range(world):
+        torch.manual_seed(9)
+        loader = DL.NpzDataLoader(fm, path, batch_size=B, shuffle=shuffle, pin=False, shard=(r, world), drop_last=False)
+        ms = [m.clone() for m in loader.matrices()]
+        assert len(ms) == len(loader) == len(whole)
+        tails.append(ms[-1])
+    assert torch.equal(torch.cat(tails), whole[-1])
+    with pytest.raises(ValueError):
+        DL.NpzDataLoader(fm, path, batch_size=B, pin=False, shard=(world, world))
