@@ -34,7 +34,7 @@ def make_dataset(name, fmt, features, label, sizes, seed):
     blob = {"dataset_id": name, "num_fields": len(features), "total_features": sum(s.get("vocab_size", 0) for _, s in features),
             "input_length": input_length, "labels": [label], "features": [{k: s} for k, s in features]}
     with open(os.path.join(out_dir, "feature_map.json"), "w") as fd:
-        json.dump(blob, fd, indent=1)
+        json.dump(blob, fd, separators=(",", ":"))
     for split, n in sizes.items():
         cols = {}
         for k, s in features:
@@ -59,13 +59,13 @@ def make_dataset(name, fmt, features, label, sizes, seed):
 
 def write_fixtures():
     sizes = {"train": 203, "valid": 61, "test": 47}
-    make_dataset("tiny_npz", "npz", [("C%d" % i, spec_cat(20 + 7 * i)) for i in range(6)] +
+    make_dataset("syn_cat", "npz", [("C%d" % i, spec_cat(20 + 7 * i)) for i in range(6)] +
                  [("price", {"source": "", "type": "numeric"})], "label", sizes, 1)
-    make_dataset("tiny_seq", "npz", [("userid", spec_cat(30)), ("item", spec_cat(90)),
+    make_dataset("syn_seq", "npz", [("userid", spec_cat(30)), ("item", spec_cat(90)),
                                      ("history", {"source": "", "type": "sequence", "share_embedding": "item",
                                                   "padding_idx": 0, "vocab_size": 90, "max_len": 5})],
                  "clk", sizes, 2)
-    make_dataset("tiny_parquet", "parquet", [("userid", spec_cat(30)), ("item", spec_cat(90)),
+    make_dataset("syn_pq", "parquet", [("userid", spec_cat(30)), ("item", spec_cat(90)),
                                              ("history", {"source": "", "type": "sequence", "share_embedding": "item",
                                                           "padding_idx": 0, "vocab_size": 90, "max_len": 4}),
                                              ("cate", spec_cat(12))], "label", sizes, 3)

@@ -47,9 +47,9 @@ def _ours(dataset, fmt, split, batch_size, shuffle, seed=7):
     return loader, list(loader)
 
 
-CASES = [("tiny_npz", "npz", "train", 32, False), ("tiny_npz", "npz", "train", 32, True),
-         ("tiny_npz", "npz", "valid", 7, False), ("tiny_seq", "npz", "train", 16, True),
-         ("tiny_parquet", "parquet", "train", 32, False), ("tiny_parquet", "parquet", "test", 10, True)]
+CASES = [("syn_cat", "npz", "train", 32, False), ("syn_cat", "npz", "train", 32, True),
+         ("syn_cat", "npz", "valid", 7, False), ("syn_seq", "npz", "train", 16, True),
+         ("syn_pq", "parquet", "train", 32, False), ("syn_pq", "parquet", "test", 10, True)]
 
 
 @pytest.mark.parametrize("dataset,fmt,split,batch_size,shuffle", CASES)
@@ -106,7 +106,7 @@ def test_batches_match_the_live_reference(ref_loaders, dataset, fmt, split, batc
 
 def test_matrices_are_the_collators_matrix():
     """`.matrices()` yields the (B, W) matrix whose column views the batch dict holds."""
-    loader, batches = _ours("tiny_npz", "npz", "train", 32, False)
+    loader, batches = _ours("syn_cat", "npz", "train", 32, False)
     fm = loader.feature_map
     for mat, b in zip(loader.matrices(), batches):
         assert mat.shape[1] == fm.input_length + len(fm.labels)
@@ -116,7 +116,7 @@ def test_matrices_are_the_collators_matrix():
 
 
 def _write_blocks(tmp_path, fmt, sizes, seed=0):
-    fm = _feature_map("tiny_npz" if fmt == "npz" else "tiny_parquet")
+    fm = _feature_map("syn_cat" if fmt == "npz" else "syn_pq")
     src = os.path.join(FIXTURES, fm.dataset_id, "train." + fmt)
     from fuxictr_b200 import dataloader as DL
     full = (DL.load_npz_matrix if fmt == "npz" else DL.load_parquet_matrix)(fm, src)
@@ -167,8 +167,8 @@ def test_block_loader_shuffle_is_a_permutation_and_seeded(tmp_path):
 
 def test_rank_dataloader_stages():
     from fuxictr_b200 import dataloader as DL
-    fm = _feature_map("tiny_npz")
-    base = os.path.join(FIXTURES, "tiny_npz")
+    fm = _feature_map("syn_cat")
+    base = os.path.join(FIXTURES, "syn_cat")
     kw = dict(train_data=os.path.join(base, "train"), valid_data=os.path.join(base, "valid"),
               test_data=os.path.join(base, "test"), batch_size=64, data_format="npz", pin=False)
     train, valid, test = DL.RankDataLoader(fm, stage="both", **kw).make_iterator()
@@ -200,8 +200,8 @@ def test_sharded_loader_is_a_partition_of_the_global_batches(world, shuffle):
     """shard=(rank, world): rank r holds rows [r*B, (r+1)*B) of every global batch of B*world rows —
     concatenating the ranks rebuilds the unsharded loader's batches (same seed on every rank)."""
     from fuxictr_b200 import dataloader as DL
-    fm = _feature_map("tiny_npz")
-    path = os.path.join(FIXTURES, "tiny_npz", "train")
+    fm = _feature_map("syn_cat")
+    path = os.path.join(FIXTURES, "syn_cat", "train")
     B = 16
     torch.manual_seed(9)
     whole = [m.clone() for m in DL.NpzDataLoader(fm, path, batch_size=B * world, shuffle=shuffle, pin=False).matrices()]
