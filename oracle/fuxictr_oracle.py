@@ -396,3 +396,80 @@ def evaluate_metrics(y_true, y_pred, metrics):
         else:
             raise ValueError("metric={} not supported.".format(m))
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# Neighbouring interaction layers (second half) — restated ahead of their
+# kernels so the parity gates exist first.  Pinned by tests/golden/next_*.npz.
+# ----------------------------------------------------------------------------------------
+def bilinear_interaction(state, prefix, feature_emb, bilinear_type):
+    """BilinearInteraction / BilinearInteractionV2.forward (bilinear_interaction.py:63-78,128-141):
+    out[:, p, :] = (e_i @ W_*) * e_j over the upper-triangular pairs p = (i < j); W_* is the one
+    shared matrix (field_all), W[i] (field_each) or W[p] (field_interaction)."""
+    W = state[prefix + "bilinear_W"]
+    F_ = feature_emb.shape[1]
+    iu = torch.triu_indices(F_, F_, offset=1)
+    left, right = feature_emb[:, iu[0]], feature_emb[:, iu[1]]
+    if bilinear_type == "field_all":
+        hidden = torch.matmul(left, W)
+    elif bilinear_type == "field_each":
+        hidden = torch.einsum("bpd,pde->bpe", left, W[iu[0]])
+    elif bilinear_type == "field_interaction":
+        hidden = torch.einsum("bpd,pde->bpe", left, W)
+    else:
+        raise NotImplementedError
+    return hidden * right
+
+
+def squeeze_excitation(state, prefix, feature_emb, excitation_activation="ReLU"):
+    """SqueezeExcitation.forward (squeeze_excitation.py:61-64): per-field mean over the embedding
+    axis -> Linear(F, F/r) -> ReLU -> Linear(F/r, F) -> ReLU|Sigmoid -> rescale the fields."""
+    z = feature_emb.mean(dim=-1)
+    a = F.relu(F.linear(z, state[prefix + "excitation.0.weight"]))
+    a = F.linear(a, state[prefix + "excitation.2.weight"])
+    a = F.relu(a) if excitation_activation.lower() == "relu" else torch.sigmoid(a)
+    return feature_emb * a.unsqueeze(-1)
+
+
+def multi_head_target_attention(state, prefix, target_item, history_sequence, mask, num_heads,
+                                use_scale=True, use_qkvo=True):
+    """MultiHeadTargetAttention.forward + ScaledDotProductAttention (target_attention.py:141-172,
+    dot_product_attention.py:48-58): one query (the target) per sample, masked positions filled with
+    -1e9 before the softmax over the history, heads concatenated, optional W_o."""
+    if use_qkvo:
+        q = F.linear(target_item, state[prefix + "W_q.weight"])
+        k = F.linear(history_sequence, state[prefix + "W_k.weight"])
+        v = F.linear(history_sequence, state[prefix + "W_v.weight"])
+    else:
+        q, k, v = target_item, history_sequence, history_sequence
+    B, L = k.shape[0], k.shape[1]
+    hd = q.shape[-1] // num_heads
+    q = q.view(B, 1, num_heads, hd).transpose(1, 2)
+    k = k.view(B, L, num_heads, hd).transpose(1, 2)
+    v = v.view(B, L, num_heads, hd).transpose(1, 2)
+    scores = torch.matmul(q, k.transpose(-1, -2))                     # (B, H, 1, L)
+    if use_scale:
+        scores = scores / (hd ** 0.5)
+    if mask is not None:
+        scores = scores.masked_fill(mask.view(B, 1, 1, L).float() == 0, -1.e9)
+    out = torch.matmul(scores.softmax(dim=-1), v)                     # (B, H, 1, hd)
+    out = out.transpose(1, 2).contiguous().view(B, num_heads * hd)
+    return F.linear(out, state[prefix + "W_o.weight"]) if use_qkvo else out
+
+
+def crossnet_mix(state, prefix, x0, layer_num, num_experts):
+    """CrossNetMix.forward (cross_net.py:168-201): per layer a softmax-gated mixture of low-rank
+    experts  x0 * (U_e tanh(C_e tanh(V_e^T x_l)) + b),  residual added."""
+    xl = x0
+    for i in range(layer_num):
+        outs, gates = [], []
+        for e in range(num_experts):
+            gates.append(F.linear(xl, state[prefix + "gating.%d.weight" % e]))          # (B, 1)
+            U, V, C = (state[prefix + "%s_list.%d" % (n, i)][e] for n in ("U", "V", "C"))
+            vx = torch.tanh(xl @ V)                                                       # (B, r)
+            vx = torch.tanh(vx @ C.t())
+            outs.append(x0 * (vx @ U.t() + state[prefix + "bias.%d" % i].view(1, -1)))
+        outs = torch.stack(outs, 2)                                                       # (B, d, E)
+        score = torch.stack(gates, 1).softmax(1)                                          # (B, E, 1)
+        xl = torch.matmul(outs, score).squeeze(2) + xl
+    return xl

@@ -378,6 +378,66 @@ def case_init_parity():
                                   "kwargs": dict(embedding_dim=4, hidden_units=[8, 8])}, w=sd(model))
 
 
+def case_next_layers():
+    """Layers of the "next" row 8f-4 (kernels not built yet): pins the oracle restatement first."""
+    import fuxictr.pytorch.layers as LL
+    gen = torch.Generator().manual_seed(51)
+    B, F_, D = 6, 5, 8
+    emb0 = torch.randn(B, F_, D, generator=gen) * 0.5
+    for cls_name in ("BilinearInteraction", "BilinearInteractionV2"):
+        for btype in ("field_all", "field_each", "field_interaction"):
+            torch.manual_seed(51)
+            layer = getattr(LL, cls_name)(F_, D, bilinear_type=btype)
+            emb = emb0.clone().requires_grad_(True)
+            w0 = sd(layer)
+            out = layer(emb)
+            gout = torch.randn(out.shape, generator=gen)
+            (out * gout).sum().backward()
+            save("next_%s_%s" % (cls_name, btype), {"B": B, "F": F_, "D": D, "bilinear_type": btype},
+                 **{"in": {"emb": emb0, "gout": gout}, "w": w0, "out": {"y": out}, "g": grads(layer),
+                    "gin": {"emb": emb.grad}})
+    for act in ("ReLU", "Sigmoid"):
+        torch.manual_seed(52)
+        layer = LL.SqueezeExcitation(F_, reduction_ratio=2, excitation_activation=act)
+        emb = emb0.clone().requires_grad_(True)
+        w0 = sd(layer)
+        out = layer(emb)
+        gout = torch.randn(out.shape, generator=gen)
+        (out * gout).sum().backward()
+        save("next_SqueezeExcitation_%s" % act, {"act": act}, **{"in": {"emb": emb0, "gout": gout}, "w": w0,
+             "out": {"y": out}, "g": grads(layer), "gin": {"emb": emb.grad}})
+    L_, d = 7, 12
+    tgt0, hist0 = torch.randn(B, d, generator=gen), torch.randn(B, L_, d, generator=gen)
+    lens = torch.randint(1, L_ + 1, (B,), generator=gen)
+    mask = (torch.arange(L_)[None, :] < lens[:, None]).float()
+    for heads, qkvo, scale in ((1, True, True), (3, True, True), (2, False, False)):
+        torch.manual_seed(53)
+        layer = LL.MultiHeadTargetAttention(input_dim=d, attention_dim=d, num_heads=heads, use_scale=scale,
+                                            use_qkvo=qkvo)
+        tgt, hist = tgt0.clone().requires_grad_(True), hist0.clone().requires_grad_(True)
+        w0 = sd(layer)
+        out = layer(tgt, hist, mask)
+        gout = torch.randn(out.shape, generator=gen)
+        (out * gout).sum().backward()
+        save("next_MHTA_h%d_qkvo%d" % (heads, int(qkvo)), {"heads": heads, "use_qkvo": qkvo, "use_scale": scale},
+             **{"in": {"target": tgt0, "history": hist0, "mask": mask, "gout": gout}, "w": w0,
+                "out": {"y": out}, "g": grads(layer), "gin": {"target": tgt.grad, "history": hist.grad}})
+    dd = 20
+    x0 = torch.randn(B, dd, generator=gen)
+    torch.manual_seed(54)
+    layer = LL.CrossNetMix(dd, layer_num=2, low_rank=4, num_experts=3)
+    with torch.no_grad():
+        for b in layer.bias:
+            b.normal_(0, 0.1)
+    x = x0.clone().requires_grad_(True)
+    w0 = sd(layer)
+    out = layer(x)
+    gout = torch.randn(out.shape, generator=gen)
+    (out * gout).sum().backward()
+    save("next_CrossNetMix", {"layer_num": 2, "low_rank": 4, "num_experts": 3},
+         **{"in": {"x": x0, "gout": gout}, "w": w0, "out": {"y": out}, "g": grads(layer), "gin": {"x": x.grad}})
+
+
 def case_metrics():
     """fuxictr.metrics.evaluate_metrics (metrics.py:26-48) as BaseModel.evaluate calls it: float64
     copies of fp32 predictions.  Three splits: smooth scores, heavy ties, saturated (0/1) scores."""
@@ -407,6 +467,9 @@ if __name__ == "__main__":
     if "--only-metrics" in sys.argv:
         case_metrics()
         sys.exit(0)
+    if "--only-next" in sys.argv:
+        case_next_layers()
+        sys.exit(0)
     case_feature_embedding_tiny_npz()
     case_feature_embedding_dict_tiny_seq()
     case_logistic_regression_tiny_seq()
@@ -417,3 +480,4 @@ if __name__ == "__main__":
     case_models()
     case_init_parity()
     case_metrics()
+    case_next_layers()

@@ -247,3 +247,46 @@ def test_metrics_oracle_matches_sklearn_on_random_ties():
             ll = sk.log_loss(y.astype(np.float64), p.astype(np.float64))
         assert abs(O.logloss(y, p) - ll) <= 1e-13 * ll
         assert abs(O.auc(y, p) - sk.roc_auc_score(y.astype(np.float64), p.astype(np.float64))) <= 1e-13
+
+
+# ------------------------------------------------------------------ "next" layers (8f-4): oracle pinned before the kernels exist
+def _check_next(g, fn, inputs, tol=2e-6):
+    """forward output, input gradients and parameter gradients of an oracle function vs the golden."""
+    state = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in g["w"].items()}
+    ins = {k: (v.clone().requires_grad_(True) if k in g["gin"] else v) for k, v in inputs.items()}
+    out = fn(state, ins)
+    assert close(out, g["out"]["y"], tol), rel_err(out, g["out"]["y"])
+    (out * g["in"]["gout"]).sum().backward()
+    for k, ref in g["gin"].items():
+        assert close(ins[k].grad, ref, tol), (k, rel_err(ins[k].grad, ref))
+    scale = max([float(v.abs().max()) for v in g["g"].values()] + [1e-30])
+    for k, ref in g["g"].items():
+        assert close(state[k].grad, ref, tol, atol=tol * scale), (k, rel_err(state[k].grad, ref))
+
+
+@pytest.mark.parametrize("cls_name", ["BilinearInteraction", "BilinearInteractionV2"])
+@pytest.mark.parametrize("btype", ["field_all", "field_each", "field_interaction"])
+def test_next_bilinear_interaction(golden, cls_name, btype):
+    g = golden("next_%s_%s" % (cls_name, btype))
+    _check_next(g, lambda st, i: O.bilinear_interaction(st, "", i["emb"], btype), {"emb": g["in"]["emb"]})
+
+
+@pytest.mark.parametrize("act", ["ReLU", "Sigmoid"])
+def test_next_squeeze_excitation(golden, act):
+    g = golden("next_SqueezeExcitation_%s" % act)
+    _check_next(g, lambda st, i: O.squeeze_excitation(st, "", i["emb"], act), {"emb": g["in"]["emb"]})
+
+
+@pytest.mark.parametrize("name", ["h1_qkvo1", "h3_qkvo1", "h2_qkvo0"])
+def test_next_multi_head_target_attention(golden, name):
+    g = golden("next_MHTA_" + name)
+    m = g.meta
+    _check_next(g, lambda st, i: O.multi_head_target_attention(st, "", i["target"], i["history"], i["mask"],
+                                                               m["heads"], m["use_scale"], m["use_qkvo"]),
+                {"target": g["in"]["target"], "history": g["in"]["history"], "mask": g["in"]["mask"]})
+
+
+def test_next_crossnet_mix(golden):
+    g = golden("next_CrossNetMix")
+    m = g.meta
+    _check_next(g, lambda st, i: O.crossnet_mix(st, "", i["x"], m["layer_num"], m["num_experts"]), {"x": g["in"]["x"]})
