@@ -116,7 +116,7 @@ class LazyTables(object):
         self.capacity = base
         self.worklist = torch.zeros(base, dtype=torch.int32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.sched = torch.zeros((self.SCHED_LEN, 2), dtype=torch.float32, device=dev)
+        self.sched = None      # FusedAdam.enable_lazy shares its schedule table
         self.opt = None
         self._ctx_cache = {}
 
@@ -175,16 +175,29 @@ class FusedAdam(object):
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.zero_grad_in_step = zero_grad_in_step
         self.lazy = None             # LazyTables: tables in G[:tail_offset] are updated row-wise, exactly
-        self.sched = torch.zeros((LazyTables.SCHED_LEN, 2), dtype=torch.float32, device=dev)
+        self.sched = None            # per-step scalar table: only the lazy replay needs one (enable_lazy)
+        self.host_steps = 0          # optimizer steps issued (eager calls + graph replays), see count_step()
         self.grad_allreduce = False  # data-parallel replicas: average G across ranks before the step
         self.sharded = False         # row-sharded tables in G[:tail_offset], replicated dense params after
 
     def enable_lazy(self, tables):
         """Evaluate the dense Adam semantics of `tables` (the arena's leading parameters) lazily."""
+        self.sched = torch.zeros((LazyTables.SCHED_LEN, 2), dtype=torch.float32, device=self.arena.P.device)
         self.lazy = LazyTables(self.arena, tables)
         self.lazy.opt = self
         self.lazy.sched = self.sched          # one schedule table for the dense and the lazy kernels
         return self.lazy
+
+    def count_step(self, n=1):
+        """Host-side count of optimizer steps (TrainPipeline calls it once per graph replay, step()
+        once per eager call).  The lazy replay reads sched[t] for every step t it catches up on, and
+        the table holds SCHED_LEN entries: refuse to run past it instead of reading out of bounds
+        (the dense pass computes its two scalars in-kernel and has no such limit)."""
+        self.host_steps += n
+        if self.lazy is not None and self.host_steps >= LazyTables.SCHED_LEN - 1:
+            raise RuntimeError("lazy Adam: the per-step schedule table holds %d steps; materialize_tables() and "
+                               "rebuild the optimizer (or use the dense pass) before step %d"
+                               % (LazyTables.SCHED_LEN, self.host_steps))
 
     def zero_grad(self, set_to_none=True):
         self.arena.begin_step(grads_zeroed=self.zero_grad_in_step and self._stepped)
@@ -196,6 +209,8 @@ class FusedAdam(object):
     def step(self):
         a = self.arena
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if not torch.cuda.is_current_stream_capturing():
+            self.count_step()
         self.step_dev.add_(1)
         # Gradients produced by stock autograd ops (parameters our kernels do not own, e.g. Dice's
         # alpha or a Conv1d weight reached through a view) live in p.grad, not in the arena: bring
@@ -246,10 +261,10 @@ class FusedAdam(object):
                           ctypes.c_void_p(self.sumsq.data_ptr()), st)
             sumsq_ptr = ctypes.c_void_p(self.sumsq.data_ptr())
         vp = ctypes.c_void_p
-        _lib.call("b2_adam_sched", vp(self.step_dev.data_ptr()), self.lr, self.betas[0], self.betas[1],
-                  vp(self.sched.data_ptr()), self.sched.shape[0], st)
         lo = 0
         if self.lazy is not None:
+            _lib.call("b2_adam_sched", vp(self.step_dev.data_ptr()), self.lr, self.betas[0], self.betas[1],
+                      vp(self.sched.data_ptr()), self.sched.shape[0], st)
             # tables: only the rows this step touched (missed zero-gradient steps are replayed)
             lz = self.lazy
             lo = a.tail_offset
@@ -261,10 +276,15 @@ class FusedAdam(object):
                       vp(self.sched.data_ptr()), vp(self.step_dev.data_ptr()), sumsq_ptr,
                       float(self.max_norm or 0.0), self.betas[0], self.betas[1], self.eps, st)
         n = a.numel - lo
-        if n > 0:
+        if n > 0 and self.lazy is not None:     # same scalars as the lazy replay: read them from the table
             _lib.call("b2_adam_step_sched", vp(a.P.data_ptr() + 4 * lo), vp(a.G.data_ptr() + 4 * lo),
                       vp(self.M.data_ptr() + 4 * lo), vp(self.V.data_ptr() + 4 * lo), n, sumsq_ptr,
                       float(self.max_norm or 0.0), self.betas[0], self.betas[1], self.eps,
                       vp(self.step_dev.data_ptr()), vp(self.sched.data_ptr()),
+                      1 if self.zero_grad_in_step else 0, st)
+        elif n > 0:                             # dense pass: the two per-step scalars are computed in-kernel
+            _lib.call("b2_adam_step", vp(a.P.data_ptr()), vp(a.G.data_ptr()), vp(self.M.data_ptr()),
+                      vp(self.V.data_ptr()), n, sumsq_ptr, float(self.max_norm or 0.0), self.lr,
+                      self.betas[0], self.betas[1], self.eps, vp(self.step_dev.data_ptr()),
                       1 if self.zero_grad_in_step else 0, st)
         self._stepped = True

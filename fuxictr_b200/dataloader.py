@@ -162,7 +162,9 @@ class MatrixDataLoader(_MatrixLoaderBase):
     def __init__(self, feature_map, darray, batch_size=32, shuffle=False, pin="auto", shard=None,
                  drop_last=None):
         super(MatrixDataLoader, self).__init__(feature_map, batch_size, pin)
-        self.matrix = _to_host_tensor(darray, pin)
+        # shuffled batches leave through the pinned ring slots (index_select into them), so page-locking
+        # the whole split buys nothing there; unshuffled batches are zero-copy slices and want it pinned
+        self.matrix = _to_host_tensor(darray, False if (shuffle and pin == "auto") else pin)
         self.shuffle = shuffle
         self.rank, self.world = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
         if not 0 <= self.rank < self.world:
@@ -182,8 +184,12 @@ class MatrixDataLoader(_MatrixLoaderBase):
             rows = min(gb, n - g0)
             if rows < gb and self.drop_last:
                 return
-            lo = min(self.rank * B, rows)
-            yield g0 + lo, g0 + min(lo + B, rows)
+            if rows == gb:
+                yield g0 + self.rank * B, g0 + (self.rank + 1) * B
+            else:       # incomplete tail kept: split its rows evenly, earlier ranks take the remainder
+                base, extra = divmod(rows, self.world)
+                lo = self.rank * base + min(self.rank, extra)
+                yield g0 + lo, g0 + lo + base + (1 if self.rank < extra else 0)
 
     def matrices(self):
         if not self.shuffle:

@@ -80,6 +80,7 @@ class TrainPipeline(object):
     # -- one step --------------------------------------------------------------------------------
     def _run(self):
         if self.graph is not None:
+            self.model._fused_optimizer.count_step()      # a replay is one optimizer step (host-side bound check)
             self.graph.replay()
             return self.loss_dev
         self.loss_dev = self._eager().detach()

@@ -155,8 +155,13 @@ class RankModel(nn.Module):
     def enable_sharding(self, group, batch_local, matrix_width, idx_dtype=torch.float64, want_fm=True):
         """Row-shard every embedding / LR table over `group` (fuxictr_b200.sharded) and route the
         sparse front through the peer-memory push/pull kernels.  Call after model_to_device() and
-        before use_fused_optimizer().  Models: the FM-style fronts (DeepFM, xDeepFM)."""
+        before use_fused_optimizer().  Only models whose forward consumes `self._sharded_front`
+        (DeepFM, DLRM) may be sharded: any other forward would keep reading the 1/world row shards
+        with global ids."""
         from . import sharded as SH
+        if not getattr(type(self), "_routes_sharded_front", False):
+            raise NotImplementedError("%s does not route its lookups through the sharded front; row-sharding "
+                                      "is implemented for DeepFM and DLRM" % type(self).__name__)
         fed = self.embedding_layer.embedding_layer
         lr_layer = self.fm.lr_layer if hasattr(self, "fm") else getattr(self, "lr_layer", None)
         names = [f for f in self.feature_map.features.keys() if f in fed.embedding_layers]
@@ -242,6 +247,11 @@ class RankModel(nn.Module):
         if getattr(self, "_lazy", None) is not None:
             self._lazy.materialize()
 
+    def state_dict(self, *args, **kwargs):
+        """Checkpoints must see up-to-date rows and moments: bring lazily evaluated tables current first."""
+        self.materialize_tables()
+        return super(RankModel, self).state_dict(*args, **kwargs)
+
     def fused_train_step(self, batch_data):
         """train_step with the arena optimizer and the fused logit+BCE kernel when the model
         exposes its pre-sigmoid logit terms (`forward_logits`)."""
@@ -275,6 +285,8 @@ def _parse_regularizer(reg):
 
 
 class DeepFM(RankModel):
+    _routes_sharded_front = True
+
     def __init__(self, feature_map, model_id="DeepFM", gpu=-1, learning_rate=1e-3, embedding_dim=10,
                  hidden_units=[64, 64, 64], hidden_activations="ReLU", net_dropout=0, batch_norm=False,
                  embedding_regularizer=None, net_regularizer=None, **kwargs):
@@ -373,6 +385,8 @@ class DCNv2(RankModel):
 
 
 class DLRM(RankModel):
+    _routes_sharded_front = True
+
     def __init__(self, feature_map, model_id="DLRM", gpu=-1, learning_rate=1e-3, embedding_dim=10,
                  top_mlp_units=[64, 64, 64], bottom_mlp_units=[64, 64, 64], top_mlp_activations="ReLU",
                  bottom_mlp_activations="ReLU", top_mlp_dropout=0, bottom_mlp_dropout=0,

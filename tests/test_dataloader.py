@@ -13,8 +13,8 @@ import torch
 
 from conftest import GOLDEN, ROOT
 
-REF = os.environ.get("FUXICTR_REFERENCE", "/root/reference")
-HAVE_REF = os.path.isdir(os.path.join(REF, "fuxictr"))
+from baseline import refenv  # noqa: E402  (the unmodified reference under baseline/_ref)
+HAVE_REF = refenv.available()
 FIXTURES = os.path.join(ROOT, "tests", "golden", "data")
 
 
@@ -67,17 +67,10 @@ def test_batches_match_golden_digest(dataset, fmt, split, batch_size, shuffle):
 @pytest.fixture(scope="module")
 def ref_loaders():
     if not HAVE_REF:
-        pytest.skip("reference checkout not present on this machine")
-    for name in ["h5py", "polars", "keras_preprocessing", "keras_preprocessing.sequence"]:
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["keras_preprocessing.sequence"].pad_sequences = lambda *a, **k: None
-    sys.modules["keras_preprocessing"].sequence = sys.modules["keras_preprocessing.sequence"]
-    sys.path.insert(0, REF)
-    from fuxictr.features import FeatureMap
+        pytest.skip(refenv.why_unavailable())
+    R = refenv.import_reference()
     from fuxictr.pytorch.dataloaders import rank_dataloader as RD   # re-exports the four loader classes
-    for name in ["h5py", "polars"]:
-        sys.modules.pop(name, None)
-    return types.SimpleNamespace(FeatureMap=FeatureMap, RD=RD)
+    return types.SimpleNamespace(FeatureMap=R.FeatureMap, RD=RD)
 
 
 @pytest.mark.parametrize("dataset,fmt,split,batch_size,shuffle", CASES)

@@ -1,6 +1,6 @@
-"""fuxictr_b200.patch.enable() on the REAL reference (only where /root/reference exists, i.e. in the
-build container; the GPU box has no reference checkout): class identity, state_dict and CPU
-behaviour are untouched, and CUDA tensors would be routed to the kernels."""
+"""fuxictr_b200.patch.enable() on the REAL reference (baseline/_ref) without a GPU: class identity,
+state_dict and CPU behaviour are untouched, and CUDA tensors would be routed to the kernels.  The
+same boundary on a real device: tests/test_reference_boundary.py (-m gpu)."""
 import os
 import sys
 import types
@@ -10,25 +10,15 @@ import torch
 
 from conftest import Golden, rel_err
 
-REF = os.environ.get("FUXICTR_REFERENCE", "/root/reference")
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "fuxictr")),
-                                reason="reference checkout not present on this machine")
+from baseline import refenv  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not refenv.available(), reason=refenv.why_unavailable())
 
 
 @pytest.fixture(scope="module")
 def ref():
-    for name in ["h5py", "polars", "keras_preprocessing", "keras_preprocessing.sequence"]:
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["keras_preprocessing.sequence"].pad_sequences = lambda *a, **k: None
-    sys.modules["keras_preprocessing"].sequence = sys.modules["keras_preprocessing.sequence"]
-    sys.path.insert(0, REF)
-    import fuxictr.pytorch.layers as L
-    from fuxictr.features import FeatureMap
-    for name in ["h5py", "polars"]:
-        sys.modules.pop(name, None)
-    sys.path.insert(0, os.path.join(REF, "model_zoo", "DeepFM", "DeepFM_torch"))
-    from src.DeepFM import DeepFM
-    return types.SimpleNamespace(L=L, FeatureMap=FeatureMap, DeepFM=DeepFM)
+    R = refenv.import_reference()
+    return types.SimpleNamespace(L=R.layers, FeatureMap=R.FeatureMap, DeepFM=refenv.load_model_class("DeepFM"))
 
 
 def build_ref_deepfm(ref, g):
