@@ -1,13 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — samples/sec of one DeepFM Criteo-shape training step on B200 (BASELINE.json
-configs[1]): 39 categorical fields x 25,641 rows (~1.0 M rows), emb_dim 16, MLP 300-300-300,
-batch 4096 per GPU.  A "step" is one pass of the hot path over one synthetic batch:
-zero_grad -> fused gather + LR + FM + MLP forward -> BCE -> backward (dense-gradient
-scatter-add, GEMM dgrad/wgrad) -> clip_grad_norm_(10) -> Adam  (the reference's
-BaseModel.train_step, fuxictr/pytorch/models/rank_model.py:307-323).
+"""bench.py — samples/sec of one training step of the hot path on B200.
+
+Default workload = BASELINE.json configs[1]: DeepFM Criteo-shape, 39 categorical fields x 25,641
+rows (~1.0 M rows), emb_dim 16, MLP 300-300-300, batch 4096 per GPU (weak scaling).
+`--workload dlrm` = configs[4]: DLRM Criteo-1TB-shape, 26 sparse fields, ~200 M rows, emb_dim 16,
+dot interaction, top MLP 64-64-64, GLOBAL batch 65,536 split over the GPUs (strong scaling), tables
+row-sharded over the GPUs.
+
+A "step" is one pass of the hot path over one synthetic batch = the reference's
+BaseModel.train_step (fuxictr/pytorch/models/rank_model.py:307-323): zero_grad -> gather / FM / LR /
+interaction / MLP forward -> BCE -> backward (dense-gradient scatter-add, GEMM dgrad/wgrad) ->
+clip_grad_norm_(10) -> Adam over every parameter.
 
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
-    python bench.py --impl reference ...                   # the reference's CPU path (oracle port)
+    python bench.py --impl reference ...                   # the UNMODIFIED reference (baseline/_ref) on host CPU
+    python bench.py --impl reference-gpu ...               # the unmodified reference, eager, on cuda:0
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -24,7 +31,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NF, VOCAB, DIM, HIDDEN, BATCH = 39, 25641, 16, [300, 300, 300], 4096
-METRIC = "samples/sec DeepFM Criteo-shape train_step (fwd+bwd+clip+Adam)"
+# C5: 26 categorical fields, Criteo-1TB-like cardinalities summing to ~200 M
+DLRM_VOCABS = [19_000_000] * 10 + [625_000] * 16
+DLRM_TOP, DLRM_GLOBAL_BATCH = [64, 64, 64], 65536
+METRICS = {"deepfm": "samples/sec DeepFM Criteo-shape train_step (fwd+bwd+clip+Adam)",
+           "dlrm": "samples/sec DLRM Criteo-1TB-shape train_step (fwd+bwd+clip+Adam), row-sharded tables"}
 
 
 def parse():
@@ -32,12 +43,14 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
+    ap.add_argument("--workload", default="deepfm", choices=["deepfm", "dlrm"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (deepfm: 4096; dlrm: 65536 / gpus)")
+    ap.add_argument("--vocab-scale", type=float, default=1.0, help="dlrm: scale every cardinality (smoke runs)")
     ap.add_argument("--graph", type=int, default=1, help="capture the step in a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--nbatches", type=int, default=8, help="distinct synthetic batches rotated through")
+    ap.add_argument("--nbatches", type=int, default=64, help="distinct synthetic batches rotated through")
     ap.add_argument("--dp-only", action="store_true",
                     help="N>1: replicate the tables and all-reduce the whole gradient arena instead of row-sharding")
     ap.add_argument("--lazy-adam", type=int, default=0,
@@ -45,36 +58,72 @@ def parse():
     ap.add_argument("--steps-only", action="store_true", help="skip the per-kernel / stress / CPU legs (profiling)")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the dense GEMMs: fp32 FFMA, 3xTF32 (fp32-class) or 1xTF32 on tcgen05")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch <= 0:
+        a.batch = BATCH if a.workload == "deepfm" else max(DLRM_GLOBAL_BATCH // max(a.gpus, 1), 1)
+    return a
+
+
+# ------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------
+def vocabs(args):
+    if args.workload == "deepfm":
+        return [VOCAB] * NF
+    return [max(int(v * args.vocab_scale), 16) for v in DLRM_VOCABS]
+
+
+def make_specs(args=None):
+    vs = [VOCAB] * NF if args is None else vocabs(args)
+    return [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": v})
+            for i, v in enumerate(vs)]
 
 
 def workload_config(args, n_gpus):
-    return {"workload": "DeepFM Criteo-shape: %d fields x %d rows, emb_dim %d, MLP %s, fp32 Adam"
-                        % (NF, VOCAB, DIM, HIDDEN),
-            "global_batch": args.batch * n_gpus, "per_gpu_batch": args.batch,
-            "parallelism": ("single" if n_gpus == 1 else
-                            ("dp%d (replicated tables, all-reduce of the gradient arena)" % n_gpus if args.dp_only else
-                             "tables row-sharded over %d GPUs (P2P push/pull over NVLink) + dense dp all-reduce" % n_gpus)),
-            "cache": "working set (4 fp32 arenas x 68 MB: params, grads, Adam m/v) exceeds the 126 MB L2; "
-                     "%d distinct index batches are rotated" % args.nbatches}
+    vs = vocabs(args)
+    if args.workload == "deepfm":
+        name = ("DeepFM Criteo-shape: %d fields x %d rows, emb_dim %d, MLP %s, fp32 Adam" % (NF, VOCAB, DIM, HIDDEN))
+        par = ("single" if n_gpus == 1 else
+               ("dp%d (replicated tables, all-reduce of the gradient arena)" % n_gpus if args.dp_only else
+                "tables row-sharded over %d GPUs (P2P push/pull over NVLink) + dense dp all-reduce" % n_gpus))
+    else:
+        name = ("DLRM Criteo-1TB-shape: %d sparse fields, %.1f M rows total, emb_dim %d, dot interaction, top MLP %s, "
+                "dense fp32 Adam over every row" % (len(vs), sum(vs) / 1e6, DIM, DLRM_TOP))
+        par = ("single GPU holds all tables" if n_gpus == 1 else
+               "tables row-sharded over %d GPUs (P2P push/pull over NVLink) + dense dp all-reduce" % n_gpus)
+    arena_mb = sum(vs) * (DIM + (1 if args.workload == "deepfm" else 0)) * 4 / 1e6 / (1 if n_gpus == 1 or args.dp_only else n_gpus)
+    return {"workload": name, "global_batch": args.batch * n_gpus, "per_gpu_batch": args.batch, "parallelism": par,
+            "cache": "working set (4 fp32 arenas x %.0f MB per GPU: params, grads, Adam m/v) exceeds the 126 MB L2; "
+                     "%d distinct index batches are rotated" % (arena_mb, args.nbatches)}
 
 
-def make_specs():
-    return [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": VOCAB})
-            for i in range(NF)]
-
-
-def make_batches(n, batch, seed=0):
+def make_batches(n, batch, seed=0, vs=None):
     """uniform ids in [1, V), Bernoulli(0.25) labels, one (B, F+1) float64 matrix
     per batch — exactly what the reference's BatchCollator hands to the model."""
     import torch
+    vs = [VOCAB] * NF if vs is None else vs
     gen = torch.Generator().manual_seed(seed)
+    hi = torch.tensor(vs, dtype=torch.float64)
     out = []
     for _ in range(n):
-        ids = torch.randint(1, VOCAB, (batch, NF), generator=gen).double()
+        u = torch.rand(batch, len(vs), generator=gen, dtype=torch.float64)
+        ids = (1 + torch.floor(u * (hi - 1))).clamp_(max=hi - 1)          # uniform in [1, V_f)
         label = (torch.rand(batch, 1, generator=gen) < 0.25).double()
         out.append(torch.cat([ids, label], dim=1))
     return out
+
+
+def zipf_ids(batch, vs, alpha=1.05, seed=0, device="cpu"):
+    """Zipf(alpha) ranks clipped to [1, V_f) (Criteo-like skew), inverse-CDF sampled."""
+    import torch
+    gen = torch.Generator(device=device).manual_seed(seed)
+    cols = []
+    for v in vs:
+        u = torch.rand(batch, generator=gen, device=device, dtype=torch.float64)
+        # continuous approximation of the Zipf CDF on [1, V): F(x) = (x^(1-a) - 1) / (V^(1-a) - 1)
+        x = (1.0 + u * (float(v) ** (1.0 - alpha) - 1.0)) ** (1.0 / (1.0 - alpha))
+        cols.append(torch.floor(x).clamp_(1, v - 1))
+    return torch.stack(cols, dim=1)
 
 
 # ------------------------------------------------------------------------------------------
@@ -127,45 +176,86 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU leg: the reference's own path (ATen ops on host cores), via the oracle restatement
+# Reference arms: the UNMODIFIED reference from baseline/_ref (its own model class, its own
+# BaseModel.train_step), on the host CPU or eager on cuda:0.  Falls back to the oracle port when
+# baseline/_ref is absent.
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(batch, steps, warmup, seconds=None, threads=None):
-    """Times BaseModel.train_step as the reference executes it on CPU (oracle port: the same ATen
-    ops — F.embedding x39, stack, FM, LR, Linear/ReLU, BCE, autograd, clip_grad_norm_, Adam)."""
+def build_reference_model(args, gpu):
+    """(model, feature_map) of the reference's own class for the workload, from a synthetic FeatureMap."""
+    from baseline import refenv
+    R = refenv.import_reference()
     import torch
-    from oracle import fuxictr_oracle as O
-    from fuxictr_b200 import zoo
-    from fuxictr_b200.schema import FeatureMap
+    fm = refenv.synthetic_feature_map(make_specs(args), embedding_dim=DIM)
+    common = dict(model_root="/tmp/b2_bench_ref/", metrics=["logloss", "AUC"], verbose=0, optimizer="adam",
+                  loss="binary_crossentropy", task="binary_classification", gpu=gpu, learning_rate=1e-3,
+                  embedding_dim=DIM, embedding_regularizer=0, net_regularizer=0, net_dropout=0, batch_norm=False)
+    R.torch_utils.seed_everything(seed=2019)
+    if args.workload == "deepfm":
+        cls = refenv.load_model_class("DeepFM")
+        model = cls(fm, model_id="DeepFM_bench", hidden_units=HIDDEN, hidden_activations="relu", **common)
+    else:
+        cls = refenv.load_model_class("DLRM")
+        common.pop("net_dropout")
+        model = cls(fm, model_id="DLRM_bench", top_mlp_units=DLRM_TOP, bottom_mlp_units=[64, 64, 64],
+                    top_mlp_activations="ReLU", bottom_mlp_activations="ReLU", top_mlp_dropout=0,
+                    bottom_mlp_dropout=0, interaction_op="dot", **common)
+    model._max_gradient_norm = 10.0          # BaseModel.fit() sets it (rank_model.py:213); train_step reads it
+    model.train()
+    return model, fm, torch
+
+
+def reference_batches(fm, mats):
+    """What BatchCollator.__call__ yields (npz_dataloader.py:111-125): column views of one matrix."""
+    cols = list(fm.features.keys()) + list(fm.labels)
+    return [{c: m[:, fm.get_column_index(c)] for c in cols} for m in mats]
+
+
+def cpu_reference_run(args, steps, warmup, seconds=None, threads=None):
+    """Times the reference's own BaseModel.train_step on the host cores.  Thread count: a fixed sweep
+    with >= 5 timed steps per candidate, the fastest is used for the sample and reported."""
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    specs = make_specs()
-    fm = FeatureMap.from_specs(specs, embedding_dim=DIM)
-    torch.manual_seed(2019)
-    model = zoo.DeepFM(fm, gpu=-1, embedding_dim=DIM, hidden_units=HIDDEN)  # parameter container only
-    spec_map = OrderedDict(specs)
-    tr = O.OracleTrainer(model.state_dict(), lambda s, X: torch.sigmoid(O.deepfm_logit(spec_map, s, X, len(HIDDEN))),
-                         spec_map, ["label"])
-    batches = [fm.batch_dict(m) for m in make_batches(4, batch)]
+    batch = args.batch
+    try:
+        model, fm, torch = build_reference_model(args, -1)
+        step = model.train_step
+        batches = reference_batches(fm, make_batches(4, batch, vs=vocabs(args)))
+        kind = "reference"
+    except ImportError:       # no baseline/_ref on this machine: the oracle restatement (same ATen ops)
+        import torch
+        from oracle import fuxictr_oracle as O
+        from fuxictr_b200 import zoo
+        from fuxictr_b200.schema import FeatureMap
+        if args.workload != "deepfm":
+            raise
+        specs = make_specs(args)
+        fm = FeatureMap.from_specs(specs, embedding_dim=DIM)
+        torch.manual_seed(2019)
+        holder = zoo.DeepFM(fm, gpu=-1, embedding_dim=DIM, hidden_units=HIDDEN)  # parameter container only
+        spec_map = OrderedDict(specs)
+        tr = O.OracleTrainer(holder.state_dict(),
+                             lambda s, X: torch.sigmoid(O.deepfm_logit(spec_map, s, X, len(HIDDEN))), spec_map, ["label"])
+        step = tr.train_step
+        batches = [fm.batch_dict(m) for m in make_batches(4, batch)]
+        kind = "port"
+    sweep = {}
     if threads is None:
-        # "all the host threads it can use": ATen's intra-op pool stops scaling (and then collapses)
-        # long before 100+ threads on ops this small, so give the reference the thread count at
-        # which IT runs fastest on this box, and report that count.
-        best = (0.0, 1)
-        for cand in sorted(set(c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu)):
+        # "all the host threads it can use": ATen's intra-op pool stops scaling (and then collapses) long
+        # before 100+ threads on ops this small, so the reference gets the count at which IT is fastest.
+        for cand in sorted(set(c for c in (8, 16, 32, 64, ncpu) if c <= ncpu)):
             torch.set_num_threads(cand)
-            tr.train_step(batches[0])
+            step(batches[0])
             t0 = time.perf_counter()
-            tr.train_step(batches[1])
-            rate = 1.0 / (time.perf_counter() - t0)
-            if rate > best[0]:
-                best = (rate, cand)
-        threads = best[1]
+            for i in range(5):
+                step(batches[i % len(batches)])
+            sweep[cand] = batch * 5 / (time.perf_counter() - t0)
+        threads = max(sweep, key=sweep.get)
     torch.set_num_threads(threads)
     for i in range(warmup):
-        tr.train_step(batches[i % len(batches)])
+        step(batches[i % len(batches)])
     t0 = time.perf_counter()
     done = 0
     while True:
-        tr.train_step(batches[done % len(batches)])
+        step(batches[done % len(batches)])
         done += 1
         el = time.perf_counter() - t0
         if seconds is not None:
@@ -173,27 +263,71 @@ def cpu_reference_run(batch, steps, warmup, seconds=None, threads=None):
                 break
         elif done >= steps:
             break
-    return {"value": batch * done / el, "ms_per_step": 1e3 * el / done, "steps": done, "cores": threads, "host_cpus": ncpu}
+    return {"value": batch * done / el, "ms_per_step": 1e3 * el / done, "steps": done, "cores": threads,
+            "host_cpus": ncpu, "kind": kind, "sweep": {str(k): round(v, 1) for k, v in sweep.items()}}
+
+
+def cpu_baseline_entry(r, args, how):
+    what = ("the unmodified reference (baseline/_ref: model_zoo class + BaseModel.train_step)" if r["kind"] == "reference"
+            else "oracle port of the reference's ATen path")
+    return {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+            "sample": "%d train steps of batch %d %s on %d of %d host threads (fastest of the sweep %s); %s"
+                      % (r["steps"], args.batch, how, r["cores"], r["host_cpus"], r["sweep"], what)}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded: each step is one 4096-sample batch; cap the run at a few minutes
-    steps = min(args.steps, 400)
-    r = cpu_reference_run(args.batch, steps, min(args.warmup, 5))
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 5),
-            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+    steps = min(args.steps, 200)       # bounded: each step is one batch; the run ends within a few minutes
+    warm = min(args.warmup, 5)
+    r = cpu_reference_run(args, steps, warm)
+    line = {"impl": "reference", "metric": METRICS[args.workload], "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": warm, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak" if args.workload == "deepfm" else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
-            "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                             "sample": "%d train steps of batch %d on %d of %d host threads (fastest setting; oracle "
-                                       "port of the reference's ATen path)" % (r["steps"], args.batch, r["cores"],
-                                                                               r["host_cpus"])},
+            "cpu_baseline": cpu_baseline_entry(r, args, "(this run)"),
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def reference_gpu_eager(args, steps=30, warmup=5):
+    """The unmodified reference on the SAME B200, eager CUDA, no patching: the GPU-vs-GPU bar
+    (SURVEY.md 8d).  Reported with the `loss.item()` sync of train_epoch (rank_model.py:342) and without."""
+    from fuxictr_b200 import patch
+    patch.disable()
+    model, fm, torch = build_reference_model(args, 0)
+    batches = reference_batches(fm, [m.pin_memory() for m in make_batches(8, args.batch, vs=vocabs(args))])
+    out = {}
+    for sync in (True, False):
+        for i in range(warmup):
+            loss = model.train_step(batches[i % len(batches)])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss = model.train_step(batches[i % len(batches)])
+            if sync:
+                loss.item()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["with_loss_item_sync" if sync else "no_host_sync"] = {"ms_per_step": ms, "value": args.batch / ms * 1e3}
+    del model
+    torch.cuda.empty_cache()
+    return {"unit": "samples/s", "value": out["with_loss_item_sync"]["value"], "detail": out, "steps": steps,
+            "what": "unmodified reference model_zoo class + BaseModel.train_step, eager on cuda:0 (per-feature "
+                    ".to(device), aten embedding/cuBLAS kernels, torch.optim.Adam)"}
+
+
+def run_reference_gpu_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    r = reference_gpu_eager(args, steps=min(args.steps, 100), warmup=max(min(args.warmup, 10), 3))
+    print(json.dumps({"impl": "reference-gpu", "metric": METRICS[args.workload], "value": r["value"],
+                      "unit": "samples/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": workload_config(args, 1), "detail": r}))
 
 
 # ------------------------------------------------------------------------------------------
@@ -225,9 +359,54 @@ def time_kernel(fn, reps, stream_sync=None):
     return e0.elapsed_time(e1) / reps
 
 
+def profile_step_shares(pipe, dev_batch):
+    """Device time of every C-ABI launch of ONE eager step, in step order.  The step is enqueued behind
+    a long spin kernel so the whole launch sequence is resident before it starts (host launch cost
+    stays out of the event intervals); each call is bracketed by CUDA events on the launching stream."""
+    import torch
+    from fuxictr_b200 import _lib
+    records = []
+    orig_call = _lib.call
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = orig_call(name, *a)
+        e1.record()
+        records.append((name, e0, e1))
+        return rc
+
+    saved_graph = pipe.graph
+    pipe.graph = None
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(2.0e8))            # ~0.1 s at 2 GHz: the queue fills behind it
+    _lib.call = timed_call
+    try:
+        s0.record()
+        pipe.step_device(dev_batch)
+        s1.record()
+    finally:
+        _lib.call = orig_call
+        pipe.graph = saved_graph
+    torch.cuda.synchronize()
+    total_us = s0.elapsed_time(s1) * 1e3
+    agg = OrderedDict()
+    for name, e0, e1 in records:
+        ent = agg.setdefault(name, {"launches": 0, "us": 0.0})
+        ent["launches"] += 1
+        ent["us"] += e0.elapsed_time(e1) * 1e3
+    ours = sum(v["us"] for v in agg.values())
+    for v in agg.values():
+        v["share"] = v["us"] / total_us
+    return {"eager_step_us": total_us, "c_abi_us": ours, "other_us (torch fills/copies, NCCL)": total_us - ours,
+            "calls": agg}
+
+
 def kernel_rooflines(model, fm, dev_batch, peaks, args, with_gather=True):
-    """Per-kernel achieved bandwidth, measured live with CUDA events: the fused gather (north-star
-    kernel) and the dense clip+Adam pass (largest share of the step)."""
+    """Per-kernel achieved bandwidth / flops, measured live with CUDA events (graph-captured
+    back-to-back launches): the fused gather (north-star kernel), the dense clip+Adam pass and the
+    tensor-core GEMMs of the first MLP layer (forward, dgrad, wgrad shapes)."""
     import ctypes
     import torch
     from fuxictr_b200 import _lib, functional as F2
@@ -235,73 +414,93 @@ def kernel_rooflines(model, fm, dev_batch, peaks, args, with_gather=True):
     hbm = peaks["hbm_gbs"]
     X = OrderedDict((k, v) for k, v in fm.batch_dict(dev_batch).items() if k != "label")
     B = dev_batch.shape[0]
-    # fused multi-field gather, algorithmic bytes: F*8 (ids) + F*D*4 (rows) + F*D*4 (out)
+    nf = len(X)
     fed = model.embedding_layer.embedding_layer
     if with_gather:
         with torch.no_grad():
             ms = time_kernel(lambda: fed.forward_tensor(X), 50, None)
-        gbytes = B * (NF * 8 + 2 * NF * DIM * 4)
+        gbytes = B * (nf * 8 + 2 * nf * DIM * 4)   # F*8 (ids) + F*D*4 (rows) + F*D*4 (out) per sample
         out["embed_gather_fwd"] = {"ms": ms, "algorithmic_bytes": gbytes, "GBps": gbytes / ms / 1e6,
                                    "frac_of_measured_hbm": gbytes / ms / 1e6 / hbm,
-                                   "note": "B=%d: tables (64 MB) are L2-resident and the launch is latency-bound" % B}
-    # dense optimizer pass over the arena: 4 reads (p,g,m,v) + 4 writes (p,m,v, g=0) of fp32
+                                   "note": "B=%d, uniform ids; the launch is latency-bound at this size" % B}
     opt = model._fused_optimizer
     a = model._arena
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
     P, G, M, V = (ctypes.c_void_p(t.data_ptr()) for t in (a.P, a.G, opt.M, opt.V))
-    backup = (a.P.clone(), opt.M.clone(), opt.V.clone(), a.G.clone())
-    opt.step_dev.add_(1)
-    ms = time_kernel(lambda: _lib.call("b2_adam_step", P, G, M, V, a.numel, ctypes.c_void_p(opt.sumsq.data_ptr()),
-                                       10.0, 1e-3, 0.9, 0.999, 1e-8, ctypes.c_void_p(opt.step_dev.data_ptr()),
-                                       1, st()), 30, None)
-    abytes = a.numel * 4 * 8
-    out["adam_step"] = {"ms": ms, "algorithmic_bytes": abytes, "GBps": abytes / ms / 1e6,
-                        "frac_of_measured_hbm": abytes / ms / 1e6 / hbm}
-    ms = time_kernel(lambda: _lib.call("b2_sumsq", G, a.numel, ctypes.c_void_p(opt.sumsq.data_ptr()), st()), 30, None)
-    sbytes = a.numel * 4
-    out["grad_sumsq"] = {"ms": ms, "algorithmic_bytes": sbytes, "GBps": sbytes / ms / 1e6,
-                         "frac_of_measured_hbm": sbytes / ms / 1e6 / hbm}
-    a.P.copy_(backup[0]); opt.M.copy_(backup[1]); opt.V.copy_(backup[2]); a.G.copy_(backup[3])
-    opt.step_dev.sub_(1)
-    # the tensor-core GEMM of the first MLP layer (4096 x 300 x 624), the most frequent kernel of the step
+    if a.numel * 16 < 40e9:                  # the timing loop works on copies of the state: skip when they do not fit
+        backup = (a.P.clone(), opt.M.clone(), opt.V.clone(), a.G.clone())
+        opt.step_dev.add_(1)
+        ms = time_kernel(lambda: _lib.call("b2_adam_step", P, G, M, V, a.numel, ctypes.c_void_p(opt.sumsq.data_ptr()),
+                                           10.0, 1e-3, 0.9, 0.999, 1e-8, ctypes.c_void_p(opt.step_dev.data_ptr()),
+                                           1, st()), 10, None)
+        abytes = a.numel * 4 * 8             # 4 reads (p,g,m,v) + 4 writes (p,m,v, g=0) of fp32
+        out["adam_step"] = {"ms": ms, "algorithmic_bytes": abytes, "GBps": abytes / ms / 1e6,
+                            "frac_of_measured_hbm": abytes / ms / 1e6 / hbm}
+        ms = time_kernel(lambda: _lib.call("b2_sumsq", G, a.numel, ctypes.c_void_p(opt.sumsq.data_ptr()), st()), 10, None)
+        sbytes = a.numel * 4
+        out["grad_sumsq"] = {"ms": ms, "algorithmic_bytes": sbytes, "GBps": sbytes / ms / 1e6,
+                             "frac_of_measured_hbm": sbytes / ms / 1e6 / hbm}
+        a.P.copy_(backup[0]); opt.M.copy_(backup[1]); opt.V.copy_(backup[2]); a.G.copy_(backup[3])
+        opt.step_dev.sub_(1)
+        del backup
     mode = F2.get_matmul_precision()
     if mode != "fp32":
-        M_, N_, K_ = B, HIDDEN[0], NF * DIM
-        xa = torch.randn(M_, K_, device="cuda"); wb = torch.randn(N_, K_, device="cuda")
-        yo = torch.empty(M_, N_, device="cuda")
-        xs = F2.split_tf32(xa) if mode == "tf32x3" else None
-        ws = F2.split_tf32(wb) if mode == "tf32x3" else None
-        ms = time_kernel(lambda: F2.gemm_nt(xa, wb, yo, a_small=xs, b_small=ws), 30, None)
-        flops = 2.0 * M_ * N_ * K_ * (3 if mode == "tf32x3" else 1)
+        x3 = mode == "tf32x3"
         tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0       # dense TF32 = half the measured bf16 rate
-        out["gemm_tf32"] = {"ms": ms, "shape": [M_, N_, K_], "passes": 3 if mode == "tf32x3" else 1,
-                            "TFLOPs": flops / ms / 1e9, "frac_of_tf32_peak": flops / ms / 1e9 / tf32_peak,
-                            "note": "launch + L2->SM operand traffic bound at this size (128 CTAs, 20 k-blocks each)"}
+        widths = [nf * DIM] + (HIDDEN if args.workload == "deepfm" else DLRM_TOP)
+        if args.workload == "dlrm":
+            widths[0] = nf * (nf - 1) // 2
+        K_, N_ = widths[0], widths[1]
+        x = torch.randn(B, K_, device="cuda"); w = torch.randn(N_, K_, device="cuda"); dz = torch.randn(B, N_, device="cuda")
+        sm = (lambda t: F2.split_tf32(t) if x3 else None)
+        xs, ws, dzs = sm(x), sm(w), sm(dz)
+        y, dx, dw = torch.empty(B, N_, device="cuda"), torch.empty(B, K_, device="cuda"), torch.empty(N_, K_, device="cuda")
+        cases = {
+            "gemm_fwd  Y=X.W^T": (lambda: F2.gemm_ex(x, w, y, a_small=xs, b_small=ws), (B, N_, K_)),
+            "gemm_dgrad dX=dZ.W (W MN-major)": (lambda: F2.gemm_ex(dz, w, dx, b_mn=True, a_small=dzs, b_small=ws), (B, K_, N_)),
+            "gemm_wgrad dW=dZ^T.X (both MN-major)": (lambda: F2.gemm_ex(dz, x, dw, a_mn=True, b_mn=True, a_small=dzs, b_small=xs), (N_, K_, B)),
+        }
+        for name, (fn, (m_, n_, k_)) in cases.items():
+            if K_ % 4 or N_ % 4:
+                continue
+            ms = time_kernel(fn, 30, None)
+            flops = 2.0 * m_ * n_ * k_
+            out[name] = {"ms": ms, "shape_MNK": [m_, n_, k_], "passes": 3 if x3 else 1,
+                         "TFLOPs_algorithmic": flops / ms / 1e9,
+                         "frac_of_tf32_peak_algorithmic": flops / ms / 1e9 / tf32_peak,
+                         "frac_of_tf32_peak_counting_passes": flops * (3 if x3 else 1) / ms / 1e9 / tf32_peak,
+                         "tf32_peak_TFLOPs": tf32_peak}
     return out
 
 
-def gather_stress(peaks):
-    """The gather against a table set far larger than L2 (39 x 4 M rows x 64 B = 10 GB) at large
-    batch: the HBM-bound operating point BASELINE.md asks the 60 %-of-peak claim to be made on."""
+def gather_points(peaks, rows, vs_label):
+    """The fused multi-field gather (the metric's own kernel) at B in {4096, 65536, 524288}, uniform and
+    Zipf(1.05) ids, on F = 39 tables of `rows` rows x 64 B."""
     import torch
     from fuxictr_b200 import functional as F2
     res = []
-    rows, F_, D = 4_000_000, NF, DIM
+    F_, D = NF, DIM
     tables = [torch.empty(rows, D, device="cuda").normal_(0, 0.01) for _ in range(F_)]
     plan = F2.GatherPlan([F2.GatherField("C%d" % i, i, D, padding_idx=0) for i in range(F_)])
-    for B in (4096, 65536, 524288):
-        gen = torch.Generator(device="cuda").manual_seed(B)
-        mat = torch.randint(1, rows, (B, F_ + 1), device="cuda", generator=gen).double()
-        idx = [mat[:, i] for i in range(F_)]
-        with torch.no_grad():
-            ms = time_kernel(lambda: F2.embed_gather(plan, idx, tables), 20, None)
-        nbytes = B * (F_ * 8 + 2 * F_ * D * 4)
-        res.append({"batch": B, "ms": ms, "GBps": nbytes / ms / 1e6,
-                    "frac_of_measured_hbm": nbytes / ms / 1e6 / peaks["hbm_gbs"]})
-        del mat, idx
+    for dist_name in ("uniform", "zipf1.05"):
+        for B in (4096, 65536, 524288):
+            if dist_name == "uniform":
+                gen = torch.Generator(device="cuda").manual_seed(B)
+                mat = torch.randint(1, rows, (B, F_ + 1), device="cuda", generator=gen).double()
+            else:
+                mat = torch.cat([zipf_ids(B, [rows] * F_, 1.05, seed=B, device="cuda"),
+                                 torch.zeros(B, 1, device="cuda", dtype=torch.float64)], dim=1)
+            idx = [mat[:, i] for i in range(F_)]
+            with torch.no_grad():
+                ms = time_kernel(lambda: F2.embed_gather(plan, idx, tables), 20, None)
+            nbytes = B * (F_ * 8 + 2 * F_ * D * 4)
+            res.append({"ids": dist_name, "batch": B, "ms": ms, "GBps": nbytes / ms / 1e6,
+                        "frac_of_measured_hbm": nbytes / ms / 1e6 / peaks["hbm_gbs"]})
+            del mat, idx
     del tables
     torch.cuda.empty_cache()
-    return {"table_bytes": rows * D * 4 * F_, "points": res}
+    return {"tables": vs_label, "table_bytes": rows * D * 4 * F_, "algorithmic_bytes_per_sample": F_ * 8 + 2 * F_ * D * 4,
+            "points": res}
 
 
 def load_peaks():
@@ -312,6 +511,42 @@ def load_peaks():
         return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops", 1590.0)),
                 "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def build_model(args, local, world):
+    """The workload's model on this rank's GPU (row-sharded when world > 1), with the fused optimizer."""
+    import torch
+    from fuxictr_b200 import zoo
+    from fuxictr_b200.schema import FeatureMap
+    fm = FeatureMap.from_specs(make_specs(args), embedding_dim=DIM)
+    nf = len(fm.features)
+
+    def construct():
+        torch.manual_seed(2019)
+        # parameters are created directly in HBM: a 200 M-row table set is 12.8 GB, too much to stage
+        # through host memory once per rank
+        with torch.device("cuda:%d" % local):
+            if args.workload == "deepfm":
+                return zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
+            return zoo.DLRM(fm, gpu=local, embedding_dim=DIM, top_mlp_units=DLRM_TOP, interaction_op="dot")
+    model = construct()
+    sharded = world > 1 and not args.dp_only
+    if sharded:
+        try:
+            from fuxictr_b200.sharded import SymmPeerGroup
+            model.enable_sharding(SymmPeerGroup(), args.batch, nf + 1, torch.float64,
+                                  want_fm=(args.workload == "deepfm"))
+            torch.cuda.empty_cache()
+        except Exception as exc:   # no peer-mapped memory on this box: replicated tables + arena all-reduce
+            sys.stderr.write("[bench] row-sharding unavailable (%r); using --dp-only\n" % (exc,))
+            sharded = False
+            args.dp_only = True
+            model = construct()
+    opt = model.use_fused_optimizer(lazy_tables=bool(args.lazy_adam) and world == 1)
+    if world > 1 and not sharded:
+        opt.grad_allreduce = True
+    model.train()
+    return model, fm, sharded
 
 
 def run_b200_arm(args):
@@ -330,35 +565,25 @@ def run_b200_arm(args):
         __graft_entry__.build()
     if world > 1:
         dist.barrier()
-    from fuxictr_b200 import zoo, _lib, functional as F2
-    from fuxictr_b200.schema import FeatureMap
+    from fuxictr_b200 import _lib, functional as F2
     _lib.load()
     F2.set_matmul_precision(args.precision)
     peaks = load_peaks()
 
-    fm = FeatureMap.from_specs(make_specs(), embedding_dim=DIM)
-    torch.manual_seed(2019)
-    model = zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
-    sharded = world > 1 and not args.dp_only
-    if sharded:
-        try:
-            from fuxictr_b200.sharded import SymmPeerGroup
-            model.enable_sharding(SymmPeerGroup(), args.batch, NF + 1, torch.float64)
-        except Exception as exc:   # no peer-mapped memory on this box: replicated tables + arena all-reduce
-            sys.stderr.write("[bench r%d] row-sharding unavailable (%r); using --dp-only\n" % (rank, exc))
-            sharded = False
-            args.dp_only = True
-            torch.manual_seed(2019)
-            model = zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
-    opt = model.use_fused_optimizer(lazy_tables=bool(args.lazy_adam) and world == 1)
-    if world > 1 and not sharded:
-        opt.grad_allreduce = True
-    model.train()
-    host_batches = [m.pin_memory() for m in make_batches(args.nbatches, args.batch, seed=1000 + rank)]
+    def note(msg):
+        if os.environ.get("B2_BENCH_VERBOSE"):
+            sys.stderr.write("[bench r%d] %s\n" % (rank, msg))
+            sys.stderr.flush()
+
+    model, fm, sharded = build_model(args, local, world)
+    nf = len(fm.features)
+    vs = vocabs(args)
+    note("model built")
+    host_batches = [m.pin_memory() for m in make_batches(args.nbatches, args.batch, seed=1000 + rank, vs=vs)]
     dev_batches = [m.cuda(non_blocking=True) for m in host_batches]
     # launches per step (our kernels only): counted by wrapping the C-ABI call around one eager step
     from fuxictr_b200.pipeline import TrainPipeline
-    pipe = TrainPipeline(model, args.batch, NF + 1, torch.float64, graph=False)
+    pipe = TrainPipeline(model, args.batch, nf + 1, torch.float64, graph=False)
     pipe.prime(dev_batches[0])
     counter = {"n": 0}
     orig_call = _lib.call
@@ -367,13 +592,20 @@ def run_b200_arm(args):
         counter["n"] += 1
         return orig_call(name, *a)
 
-    if os.environ.get("B2_BENCH_VERBOSE"):
-        sys.stderr.write("[bench r%d] model built\n" % rank); sys.stderr.flush()
+    pipe.step_device(dev_batches[0])        # first step: lazy allocations, cuTensorMap entry point, ...
     _lib.call = counting_call
     pipe.step_device(dev_batches[0])
     torch.cuda.synchronize()
     launches = counter["n"]
     _lib.call = orig_call
+    shares = None
+    if world == 1 and not args.steps_only:
+        try:
+            shares = profile_step_shares(pipe, dev_batches[1 % len(dev_batches)])
+        except Exception as exc:
+            shares = {"error": repr(exc)}
+    if world > 1:
+        dist.barrier()
     if args.graph:
         try:
             pipe.capture(3)     # the constructor does this for graph=True; done late here to count launches first
@@ -381,9 +613,7 @@ def run_b200_arm(args):
             sys.stderr.write("[bench r%d] CUDA-graph capture failed (%r); timing the eager step\n" % (rank, exc))
             pipe.graph, pipe.loss_dev = None, None
             torch.cuda.synchronize()
-
-    if os.environ.get("B2_BENCH_VERBOSE"):
-        sys.stderr.write("[bench r%d] graph captured\n" % rank); sys.stderr.flush()
+    note("graph captured")
 
     def run_step(i, e2e):
         if e2e:     # the user-facing call: pinned host matrix -> async H2D (overlapping the previous
@@ -419,11 +649,6 @@ def run_b200_arm(args):
     ms_e2e = timed(True, args.steps, warmup)
     clocks = sampler.stop() if rank == 0 else None
     final_loss = pipe.loss()
-
-    def note(msg):
-        if os.environ.get("B2_BENCH_VERBOSE"):
-            sys.stderr.write("[bench r%d] %s\n" % (rank, msg))
-            sys.stderr.flush()
     note("timed regions done")
     if rank != 0:
         # Last collective done.  Leave without NCCL teardown: rank 0 still captures CUDA graphs for
@@ -433,30 +658,58 @@ def run_b200_arm(args):
     samples = args.batch * world * args.steps
     value = samples / (ms_total / 1e3)
     e2e_value = samples / (ms_e2e / 1e3)
+    step_ms = ms_total / args.steps
     if args.steps_only:
-        print(json.dumps({"value": value, "ms_per_step": ms_total / args.steps, "e2e": e2e_value,
+        print(json.dumps({"value": value, "ms_per_step": step_ms, "e2e": e2e_value, "workload": args.workload,
                           "gpu_launches_per_step": launches, "precision": args.precision, "n_gpus": world}))
         sys.stdout.flush()
         if world > 1:
             os._exit(0)
         return
     kernels = kernel_rooflines(model, fm, dev_batches[0], peaks, args, with_gather=not sharded)
-    dom = max([k for k in ("adam_step", "embed_gather_fwd", "grad_sumsq") if k in kernels],
-              key=lambda k: kernels[k]["ms"])
-    step_ms = ms_total / args.steps
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_step_kernels_traffic.json")
-    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
+    # dominant kernel = largest share of the profiled step among ALL C-ABI launches (GEMMs included)
+    group = {"b2_gemm_tc_ex": "gemm", "b2_gemm_tc": "gemm", "b2_adam_step": "adam_step", "b2_adam_step_sched": "adam_step",
+             "b2_sumsq": "grad_sumsq"}
+    by_group = {}
+    if shares and "calls" in shares:
+        for name, v in shares["calls"].items():
+            gname = group.get(name, name)
+            ent = by_group.setdefault(gname, {"us": 0.0, "launches": 0})
+            ent["us"] += v["us"]
+            ent["launches"] += v["launches"]
+    dom = max(by_group, key=lambda k: by_group[k]["us"]) if by_group else "adam_step"
+    share = (by_group[dom]["us"] / shares["eager_step_us"]) if by_group else None
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    if dom == "gemm":
+        gem = [v for k, v in kernels.items() if k.startswith("gemm_")]
+        flops = sum(2.0 * v["shape_MNK"][0] * v["shape_MNK"][1] * v["shape_MNK"][2] for v in gem)
+        ms = sum(v["ms"] for v in gem)
+        passes = gem[0]["passes"] if gem else 1
+        roofline = {"kernel": "gemm_tf32_kernel (first MLP layer: forward + dgrad + wgrad launches)", "bound": "tensor",
+                    "achieved": flops / ms / 1e9, "peak": tf32_peak, "unit": "TFLOP/s", "frac": flops / ms / 1e9 / tf32_peak,
+                    "frac_counting_3xTF32_passes": flops * passes / ms / 1e9 / tf32_peak, "passes": passes,
+                    "algorithmic_flops": flops, "traffic": None,
+                    "peak_source": peaks["source"] + ": dense TF32 = measured bf16 / 2"}
+    else:
+        key = dom if dom in kernels else "adam_step"
+        k = kernels.get(key)
+        roofline = {"kernel": key, "bound": "hbm", "achieved": k["GBps"] if k else None, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": k["frac_of_measured_hbm"] if k else None,
+                    "algorithmic_bytes": k["algorithmic_bytes"] if k else None, "traffic": None,
+                    "peak_source": peaks["source"]}
+    roofline["share_of_step"] = share
+    # dram__bytes_read+write of one `ncu --set full` capture of the same command, N = 1 only (a shard of
+    # the arena is a different launch: never reuse the N = 1 figure there)
+    tpath = os.path.join(ROOT, "profiles", "r2_step_kernels_traffic.json")
+    if world == 1 and args.workload == "deepfm" and os.path.exists(tpath):
         with open(tpath) as fd:
-            cap = json.load(fd).get({"adam_step": "adam_kernel", "grad_sumsq": "sumsq_kernel"}.get(dom, dom))
+            cap = json.load(fd).get({"adam_step": "adam_kernel", "gemm": "gemm_tf32_kernel"}.get(dom, dom))
         if cap:
-            traffic = (cap["dram_read_MB"] + cap["dram_write_MB"]) * 1e6
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": kernels[dom]["frac_of_measured_hbm"], "traffic": traffic,
-                "algorithmic_bytes": kernels[dom]["algorithmic_bytes"],
-                "peak_source": peaks["source"], "share_of_step": kernels[dom]["ms"] / step_ms}
-    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            roofline["traffic"] = (cap["dram_read_MB"] + cap["dram_write_MB"]) * 1e6
+            roofline["traffic_source"] = "profiles/r2_step_kernels_traffic.json (ncu --set full, per launch)"
+    line = {"metric": METRICS[args.workload], "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak" if args.workload == "deepfm" else "strong",
             "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core GEMMs, fp32 everything else)",
                       "tf32": "tf32 GEMMs, f32 elsewhere"}[args.precision],
@@ -469,18 +722,22 @@ def run_b200_arm(args):
                     "api": "fuxictr_b200.pipeline.TrainPipeline.step (double-buffered H2D on a copy stream)"},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
             "cuda_graph": pipe.graph is not None, "final_loss": final_loss,
-            "roofline": roofline, "kernels": kernels}
-    if world == 1:
+            "roofline": roofline, "kernels": kernels, "step_profile": shares}
+    if world == 1 and args.workload == "deepfm":
+        del pipe, model
+        torch.cuda.empty_cache()
         try:
-            line["gather_stress"] = gather_stress(peaks)
+            line["gather"] = {"c2": gather_points(peaks, VOCAB, "39 x 25,641 rows (64 MB: L2-resident)"),
+                              "stress": gather_points(peaks, 4_000_000, "39 x 4 M rows (10 GB >> L2)")}
         except Exception as exc:  # e.g. a smaller GPU: report, do not hide
-            line["gather_stress"] = {"error": str(exc)}
-        if not args.no_cpu_baseline:
-            r = cpu_reference_run(args.batch, 0, 3, seconds=args.cpu_seconds)
-            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                                    "sample": "%d train steps of batch %d in %.0f s on %d of %d host threads (fastest "
-                                              "setting; oracle port of the reference's ATen path)"
-                                              % (r["steps"], args.batch, args.cpu_seconds, r["cores"], r["host_cpus"])}
+            line["gather"] = {"error": str(exc)}
+        try:
+            line["reference_gpu_eager"] = reference_gpu_eager(args)
+        except Exception as exc:
+            line["reference_gpu_eager"] = {"unavailable": repr(exc)}
+    if world == 1 and not args.no_cpu_baseline and args.workload == "deepfm":
+        r = cpu_reference_run(args, 0, 3, seconds=args.cpu_seconds)
+        line["cpu_baseline"] = cpu_baseline_entry(r, args, "in %.0f s" % args.cpu_seconds)
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
@@ -491,5 +748,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.impl == "reference-gpu":
+        run_reference_gpu_arm(a)
     else:
         run_b200_arm(a)

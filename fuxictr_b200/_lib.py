@@ -51,6 +51,18 @@ class b2_field(ctypes.Structure):
 
 _FIELD_P = ctypes.POINTER(b2_field)
 
+
+class b2_gemm_desc(ctypes.Structure):
+    """struct b2_gemm_desc of include/fuxictr_b200.h."""
+    _fields_ = [
+        ("a", c_void_p), ("b", c_void_p), ("a_small", c_void_p), ("b_small", c_void_p),
+        ("c", c_void_p), ("c_small", c_void_p), ("bias", c_void_p), ("mul", c_void_p), ("add", c_void_p),
+        ("ybwd", c_void_p), ("colsum", c_void_p),
+        ("lda", c_int64), ("ldb", c_int64), ("ldc", c_int64), ("M", c_int64), ("N", c_int64), ("K", c_int64),
+        ("a_mn_major", c_int32), ("b_mn_major", c_int32), ("act", c_int32), ("act_bwd", c_int32),
+        ("beta_accumulate", c_int32), ("reserved_", c_int32),
+    ]
+
 # name -> (restype, argtypes); every symbol the header declares must appear here
 # (tests/test_abi.py cross-checks this table against the header text).
 SIGNATURES = {
@@ -106,7 +118,7 @@ SIGNATURES = {
     "b2_gemm_tc_supported": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64]),
     "b2_gemm_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                            c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
-    "b2_gemm_tc_set_debug": (c_int, [c_void_p]),
+    "b2_gemm_tc_ex": (c_int, [c_void_p, c_void_p]),
     "b2_split_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "b2_transpose_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "b2_prep_operand": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -114,6 +126,8 @@ SIGNATURES = {
     "b2_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "b2_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p]),
+    "b2_head_bwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b2_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "b2_logit_bce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import functional as F2
 
 
 class _Slot(object):
@@ -211,6 +212,7 @@ class FusedAdam(object):
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         if not torch.cuda.is_current_stream_capturing():
             self.count_step()
+        F2.bump_weight_epoch()        # parameters change through raw pointers: cached 3xTF32 weight splits are stale
         self.step_dev.add_(1)
         # Gradients produced by stock autograd ops (parameters our kernels do not own, e.g. Dice's
         # alpha or a Conv1d weight reached through a view) live in p.grad, not in the arena: bring

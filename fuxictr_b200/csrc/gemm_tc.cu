@@ -4,7 +4,11 @@
 // (fuxictr/pytorch/layers/interactions/cross_net.py:126-129) and CIN's 1x1 Conv1d
 // (fuxictr/pytorch/layers/interactions/compressed_interaction_net.py:72).
 //
-//   C[m, n] = epi( sum_k A[m, k] * B[n, k] )      A: (M, K) K-major fp32, B: (N, K) K-major fp32
+//   C[m, n] = epi( sum_k A(m, k) * B(n, k) )
+// Each operand is either K-major (memory (rows, K), K contiguous) or MN-major (memory (K, rows),
+// rows contiguous): the tensor core reads both through its shared-memory matrix descriptor, so
+// the dgrad (dX = dZ W) and wgrad (dW = dZ^T X) contractions of a Linear layer consume W, dZ and X
+// exactly as they lie in memory — no transpose pass.
 //
 // Arithmetic: tcgen05.mma kind::tf32 reads the fp32 operands straight from shared memory
 // (the tensor core ignores the low 13 mantissa bits) and accumulates in fp32 in TMEM.
@@ -20,6 +24,7 @@
 //   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias/act/mul/add -> global
 // Every mbarrier wait is bounded: a pipeline bug traps with a message instead of hanging the GPU.
 #include "b2_common.cuh"
+#include <string.h>
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time
 
 namespace tc {
@@ -31,17 +36,20 @@ constexpr int A_BYTES = BM * 128;
 constexpr int NTHREADS = 192;
 
 struct Params {
-  CUtensorMap map_a[3];
-  CUtensorMap map_b[3];
+  CUtensorMap map_a[2];   // [0] the operand, [1] its 3xTF32 small part
+  CUtensorMap map_b[2];
   float* c;
+  float* c_small;         // optional: tf32_small(C) for the consumer's 3xTF32 operand
   int64_t ldc;
   const float* bias;
   const float* mul;
   const float* add;
-  int M, N, K, bn, nseg, act, beta, kb_per_split;
+  const float* ybwd;      // optional (M, N) ld = ldc: C = act_bwd'(ybwd) * (...)   (activation backward)
+  float* colsum;          // optional (N): += column sums of C (bias gradient)
+  int M, N, K, bn, nseg, act, act_bwd, beta, kb_per_split;
+  int a_mn, b_mn;         // operand is MN-major (memory (K, rows))
   int nmain;      // TMEM accumulators for the main (big x big) product: its K range is cut in nmain chunks
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
-  long long* dbg; // diagnostic: 8 globaltimer stamps of CTA (0,0,0), or NULL
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -105,6 +113,27 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   d |= (uint64_t) 2 << 61;                   // layout: SWIZZLE_128B
   return d;
 }
+// MN-major, 128-byte swizzle: the tile is a row of [32 MN-elements x BK k-rows] boxes (what one TMA
+// box writes: k-row r at r * 128 B, 8-row groups 1024 B apart = SBO), boxes BK * 128 B apart = LBO.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t) ((addr & 0x3FFFFu) >> 4);      // start address  [0,14)
+  d |= (uint64_t) ((BK * 128) >> 4) << 16;       // leading byte offset [16,30): next 32-element MN block
+  d |= (uint64_t) (1024 >> 4) << 32;             // stride byte offset [32,46): next 8 k-rows
+  d |= (uint64_t) 1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t) 2 << 61;                       // layout: SWIZZLE_128B
+  return d;
+}
+// small(x) = rna_tf32(x - big(x)), big(x) = x with the 13 low mantissa bits cleared (what
+// kind::tf32 reads from a raw fp32 operand).  x - big(x) is exact; rounding it to a
+// tf32-representable value HERE (round-to-nearest) makes the hardware truncation of the small
+// operand a no-op, so the residual of the split is unbiased instead of always toward zero.
+__device__ __forceinline__ float tf32_small(float v) {
+  const float big = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - big));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -134,18 +163,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void stamp(const Params& p, int slot) {
-  if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    p.dbg[slot] = (long long) t;
-  }
-}
-
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
-  if (threadIdx.x == 0) stamp(p, 0);
   // 128B-swizzled tiles need 1024-byte aligned bases: align by hand (1 KB of slack is requested).
   // (pointer arithmetic on smem_raw keeps the shared address space visible to the compiler)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -191,7 +211,6 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) stamp(p, 1);
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -203,14 +222,22 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         const uint32_t a_dst = smem_base + stage * stage_bytes;
         const uint32_t full = full0 + 8 * stage;
         mbar_expect_tx(full, stage_bytes);
-        // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products
-        tma_load_2d(a_dst, &p.map_a[0], full, kb * BK, m0);
-        tma_load_2d(a_dst + off_b, &p.map_b[0], full, kb * BK, n0);
-        if (x3) {
-          tma_load_2d(a_dst + off_as, &p.map_a[1], full, kb * BK, m0);
-          tma_load_2d(a_dst + off_bs, &p.map_b[1], full, kb * BK, n0);
+        // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products.
+        // K-major operand: one box (BK k-columns x rows).  MN-major operand: one box per 32 rows
+        // (32 rows x BK k-rows, coordinates {row, k}); out-of-range boxes arrive zero-filled.
+        for (int s = 0; s < (x3 ? 2 : 1); ++s) {
+          const uint32_t a_t = a_dst + (s ? off_as : 0u), b_t = a_dst + (s ? off_bs : off_b);
+          if (!p.a_mn) {
+            tma_load_2d(a_t, &p.map_a[s], full, kb * BK, m0);
+          } else {
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_t + j * (BK * 128), &p.map_a[s], full, m0 + 32 * j, kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(b_t, &p.map_b[s], full, kb * BK, n0);
+          } else {
+            for (int j = 0; j < p.bn / 32; ++j) tma_load_2d(b_t + j * (BK * 128), &p.map_b[s], full, n0 + 32 * j, kb * BK);
+          }
         }
-        if (kb == kb_begin) stamp(p, 2);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -218,8 +245,13 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     // ---------------- MMA issuer (one thread) ----------------
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (p.bn >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (p.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t) (p.b_mn ? 1 : 0) << 16) | ((uint32_t) (p.bn >> 3) << 17) |
                              ((uint32_t) (BM >> 4) << 24);
+      // one instruction consumes 8 k-elements: 32 bytes along a K-major swizzle row (+2 in the
+      // (addr >> 4) field) or one 8-row group of an MN-major tile (+1024 B)
+      const uint64_t a_kstep = p.a_mn ? (uint64_t) (1024 >> 4) : (uint64_t) (UMMA_K_BYTES >> 4);
+      const uint64_t b_kstep = p.b_mn ? (uint64_t) (1024 >> 4) : (uint64_t) (UMMA_K_BYTES >> 4);
       // The tensor core adds each instruction's 8 products into the fp32 accumulator with
       // truncation, so rounding error grows with the length of one accumulation chain and with
       // the magnitude of the accumulator.  For 3xTF32 the K range of the main product is
@@ -231,38 +263,34 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(full0 + 8 * stage, phase, 1);
         tc_fence_after();
-        if (i == 0) stamp(p, 3);
         const int slot = (int) (((long long) i * nmain) / nkb);
         const bool first = (i == (int) (((long long) slot * nkb + nmain - 1) / nmain));
         const uint32_t d_main = tmem_base + (uint32_t) (slot * p.bn);
         const uint32_t d_corr = tmem_base + (uint32_t) (nmain * p.bn);
         const uint32_t a_addr = smem_base + stage * stage_bytes;
-        const uint64_t adesc = make_smem_desc(a_addr);
-        const uint64_t bdesc = make_smem_desc(a_addr + off_b);
-        const uint64_t asdesc = make_smem_desc(a_addr + off_as);
-        const uint64_t bsdesc = make_smem_desc(a_addr + off_bs);
+        const uint64_t adesc = p.a_mn ? make_smem_desc_mn(a_addr) : make_smem_desc(a_addr);
+        const uint64_t bdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_b) : make_smem_desc(a_addr + off_b);
+        const uint64_t asdesc = p.a_mn ? make_smem_desc_mn(a_addr + off_as) : make_smem_desc(a_addr + off_as);
+        const uint64_t bsdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_bs) : make_smem_desc(a_addr + off_bs);
 #pragma unroll
         for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
-          // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          const uint64_t ko = (uint64_t) (k * (UMMA_K_BYTES >> 4));
-          umma_tf32(d_main, adesc + ko, bdesc + ko, idesc, (!first || k > 0) ? 1u : 0u);      // A_big . B_big
+          const uint64_t ka = (uint64_t) k * a_kstep, kb_ = (uint64_t) k * b_kstep;
+          umma_tf32(d_main, adesc + ka, bdesc + kb_, idesc, (!first || k > 0) ? 1u : 0u);      // A_big . B_big
           if (x3) {
-            umma_tf32(d_corr, adesc + ko, bsdesc + ko, idesc, (i > 0 || k > 0) ? 1u : 0u);   // A_big . B_small
-            umma_tf32(d_corr, asdesc + ko, bdesc + ko, idesc, 1u);                            // A_small . B_big
+            umma_tf32(d_corr, adesc + ka, bsdesc + kb_, idesc, (i > 0 || k > 0) ? 1u : 0u);   // A_big . B_small
+            umma_tf32(d_corr, asdesc + ka, bdesc + kb_, idesc, 1u);                            // A_small . B_big
           }
         }
         umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full);  // accumulator complete
-      stamp(p, 4);
     }
   } else {
     // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----------------
     const int q = warp & 3;
     mbar_wait(tmem_full, 0, 2);
     tc_fence_after();
-    if (warp == 2 && lane == 0) stamp(p, 5);
     const bool split = gridDim.z > 1;
     const int nslots = nmain + (p.nseg > 1 ? 1 : 0);
     // The pipeline buffers are idle now (every MMA has retired): each epilogue warp borrows a
@@ -316,6 +344,21 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 #pragma unroll
             for (int r = 0; r < 32; ++r) t[r] = 1.f / (1.f + expf(-t[r]));
           }
+          if (p.ybwd != nullptr) {   // activation backward of the PRODUCER of this gradient, fused
+            const float* yp = p.ybwd + (int64_t) mrow0 * p.ldc + n;
+            if (p.act_bwd == B2_ACT_RELU) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r)
+                if (mrow0 + r < p.M) t[r] = (__ldg(yp + (int64_t) r * p.ldc) > 0.f) ? t[r] : 0.f;
+            } else if (p.act_bwd == B2_ACT_SIGMOID) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r)
+                if (mrow0 + r < p.M) {
+                  const float yv = __ldg(yp + (int64_t) r * p.ldc);
+                  t[r] = t[r] * ((1.f - yv) * yv);
+                }
+            }
+          }
           if (p.beta) {
 #pragma unroll
             for (int r = 0; r < 32; ++r)
@@ -324,14 +367,25 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 #pragma unroll
           for (int r = 0; r < 32; ++r)
             if (mrow0 + r < p.M) cp[(int64_t) r * p.ldc] = t[r];   // 128 contiguous bytes per row
+          if (p.c_small != nullptr) {   // the consumer's 3xTF32 small part, produced where C is produced
+            float* sp = p.c_small + (int64_t) mrow0 * p.ldc + n;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (mrow0 + r < p.M) sp[(int64_t) r * p.ldc] = tf32_small(t[r]);
+          }
+          if (p.colsum != nullptr) {    // bias gradient: this lane owns column n of 32 rows
+            float cs = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (mrow0 + r < p.M) cs += t[r];
+            b2_red_add(p.colsum + n, cs);
+          }
         }
       }
     }
   }
-  if (warp == 2 && lane == 0) stamp(p, 6);
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) stamp(p, 7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -340,16 +394,6 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   }
 }
 
-// small(x) = rna_tf32(x - big(x)), big(x) = x with the 13 low mantissa bits cleared (what
-// kind::tf32 reads from a raw fp32 operand).  x - big(x) is exact; rounding it to a
-// tf32-representable value HERE (round-to-nearest) makes the hardware truncation of the small
-// operand a no-op, so the residual of the split is unbiased instead of always toward zero.
-__device__ __forceinline__ float tf32_small(float v) {
-  const float big = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - big));
-  return __uint_as_float(r);
-}
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, float* __restrict__ small, int64_t n) {
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -443,6 +487,9 @@ prep_operand_kernel(const float* __restrict__ x, const float* __restrict__ y, in
 // MMA tile would be 1/128 full, so it is a warp-per-row GEMV forward and one fused backward:
 //   fwd: y[m] = act(<x[m,:], w> + b)
 //   bwd: gz = act'(y) * gy;  gx[m,:] = gz[m] * w;  gw += sum_m gz[m] * x[m,:];  gb += sum_m gz[m]
+//   With prev_act != NONE the head's input x IS the previous layer's activation output, so that
+//   layer's activation backward is fused here: gx <- prev_act'(x) * gx (= dZ of the previous layer),
+//   together with its 3xTF32 small part (gx_small) and its bias gradient gb_prev[k] = sum_m gx[m,k].
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
@@ -468,10 +515,12 @@ head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ y,
                 const float* __restrict__ gy, int64_t M, int K, int act, int64_t rows_per_cta,
-                float* __restrict__ gx, float* __restrict__ gw, float* __restrict__ gb) {
-  extern __shared__ float sgw[];  // K partial sums
+                float* __restrict__ gx, float* __restrict__ gw, float* __restrict__ gb, int prev_act,
+                float* __restrict__ gx_small, float* __restrict__ gb_prev) {
+  extern __shared__ float sgw[];  // K partial sums of gw, then K partial sums of gb_prev
   __shared__ float red[32];
-  for (int k = threadIdx.x; k < K; k += blockDim.x) sgw[k] = 0.f;
+  float* sgp = sgw + K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) { sgw[k] = 0.f; sgp[k] = 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r0 = (int64_t) blockIdx.x * rows_per_cta;
@@ -479,9 +528,9 @@ head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   float gb_acc = 0.f;
   // each warp keeps per-lane partials of gw for its k-strided columns over its rows
   for (int kb = 0; kb < K; kb += 32 * 8) {       // 8 columns per lane per pass
-    float part[8];
+    float part[8], cs[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) part[j] = 0.f;
+    for (int j = 0; j < 8; ++j) { part[j] = 0.f; cs[j] = 0.f; }
     for (int64_t m = r0 + warp; m < r1; m += 8) {
       float gz = __ldg(gy + m);
       if (y != nullptr) {
@@ -494,20 +543,33 @@ head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       for (int j = 0; j < 8; ++j) {
         const int k = kb + j * 32 + lane;
         if (k < K) {
-          if (gx != nullptr) gx[m * K + k] = gz * __ldg(w + k);
-          part[j] = fmaf(gz, __ldg(x + m * K + k), part[j]);
+          const float xv = __ldg(x + m * K + k);
+          if (gx != nullptr) {
+            float val = gz * __ldg(w + k);
+            if (prev_act == B2_ACT_RELU) val = (xv > 0.f) ? val : 0.f;
+            else if (prev_act == B2_ACT_SIGMOID) val = val * ((1.f - xv) * xv);
+            gx[m * K + k] = val;
+            if (gx_small != nullptr) gx_small[m * K + k] = tf32_small(val);
+            cs[j] += val;
+          }
+          part[j] = fmaf(gz, xv, part[j]);
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = kb + j * 32 + lane;
-      if (k < K) atomicAdd(sgw + k, part[j]);
+      if (k < K) {
+        atomicAdd(sgw + k, part[j]);
+        if (gb_prev != nullptr) atomicAdd(sgp + k, cs[j]);
+      }
     }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x)
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
     if (sgw[k] != 0.f) b2_red_add(gw + k, sgw[k]);
+    if (gb_prev != nullptr && sgp[k] != 0.f) b2_red_add(gb_prev + k, sgp[k]);
+  }
   if (gb != nullptr) {
     const float t = b2_block_sum(gb_acc, red);
     if (threadIdx.x == 0 && t != 0.f) b2_red_add(gb, t);
@@ -535,28 +597,25 @@ static b2_encode_tiled_fn b2_get_encode() {
   return fn;
 }
 
-// (rows, K) fp32, K contiguous, leading dimension ld; box = 32 columns (128 B) x box_rows rows.
-static int encode_kmajor(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld,
-                         int box_rows) {
+// K-major operand: memory (rows, K), K contiguous, leading dimension ld; box = 32 k (128 B) x box_rows.
+// MN-major operand: memory (K, rows), rows contiguous, leading dimension ld; box = 32 rows (128 B) x BK k.
+static int encode_operand(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld,
+                          int mn_major, int box_rows) {
   b2_encode_tiled_fn enc = b2_get_encode();
   if (enc == nullptr) return b2_fail(B2_E_CUDA, "cuTensorMapEncodeTiled is unavailable in this driver");
-  cuuint64_t dims[2] = {(cuuint64_t) K, (cuuint64_t) rows};
-  cuuint64_t strides[1] = {(cuuint64_t) ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t) tc::BK, (cuuint32_t) box_rows};
-  cuuint32_t estr[2] = {1, 1};
+  cuuint64_t dims[2], strides[1] = {(cuuint64_t) ld * 4};
+  cuuint32_t box[2], estr[2] = {1, 1};
+  if (!mn_major) {
+    dims[0] = (cuuint64_t) K; dims[1] = (cuuint64_t) rows;
+    box[0] = (cuuint32_t) tc::BK; box[1] = (cuuint32_t) box_rows;
+  } else {
+    dims[0] = (cuuint64_t) rows; dims[1] = (cuuint64_t) K;
+    box[0] = 32; box[1] = (cuuint32_t) tc::BK;
+  }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return b2_fail(B2_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
-  return B2_OK;
-}
-
-static long long* g_tc_debug = nullptr;
-// Diagnostic hook: subsequent b2_gemm_tc launches write 8 globaltimer stamps (ns) of CTA (0,0,0)
-// into buf: 0 entry, 1 setup done, 2 first TMA issued, 3 first tile landed, 4 last MMA committed,
-// 5 accumulator visible to the epilogue, 6 epilogue stored, 7 all warps done.  NULL disables.
-extern "C" B2_API int b2_gemm_tc_set_debug(long long* buf) {
-  g_tc_debug = buf;
   return B2_OK;
 }
 
@@ -570,16 +629,19 @@ extern "C" B2_API int b2_gemm_tc_supported(const float* a, int64_t lda, const fl
           N < (1ll << 31) && K < (1ll << 31)) ? 1 : 0;
 }
 
-extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
-                                 int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int act,
-                                 const float* mul, const float* add, int beta_accumulate,
-                                 const float* a_small, const float* b_small, void* stream) {
+extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
+  B2_REQUIRE(d != nullptr, "NULL descriptor");
+  const float* a = d->a; const float* b = d->b; float* c = d->c;
+  const int64_t M = d->M, N = d->N, K = d->K, lda = d->lda, ldb = d->ldb, ldc = d->ldc;
   B2_REQUIRE(a && b && c, "NULL operand");
-  B2_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N && lda >= K && ldb >= K, "bad shape");
-  B2_REQUIRE(act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad activation code %d", act);
-  B2_REQUIRE((a_small == nullptr) == (b_small == nullptr), "3xTF32 needs both small operands");
+  B2_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N, "bad shape");
+  B2_REQUIRE(lda >= (d->a_mn_major ? M : K) && ldb >= (d->b_mn_major ? N : K), "leading dimension too small");
+  B2_REQUIRE(d->act >= B2_ACT_NONE && d->act <= B2_ACT_SIGMOID, "bad activation code %d", d->act);
+  B2_REQUIRE(d->act_bwd >= B2_ACT_NONE && d->act_bwd <= B2_ACT_SIGMOID, "bad act_bwd code %d", d->act_bwd);
+  B2_REQUIRE(d->act_bwd == B2_ACT_NONE || d->ybwd != nullptr, "act_bwd needs ybwd");
+  B2_REQUIRE((d->a_small == nullptr) == (d->b_small == nullptr), "3xTF32 needs both small operands");
   if (!b2_gemm_tc_supported(a, lda, b, ldb, M, N, K) ||
-      (a_small != nullptr && !(tma_ok(a_small, lda) && tma_ok(b_small, ldb))))
+      (d->a_small != nullptr && !(tma_ok(d->a_small, lda) && tma_ok(d->b_small, ldb))))
     return b2_fail(B2_E_UNSUPPORTED, "operands are not TMA-addressable (16-byte base, ld %% 4 == 0)");
   cudaStream_t st = (cudaStream_t) stream;
 
@@ -587,10 +649,12 @@ extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, in
   // so minimise waves x per-CTA operand bytes, where one wave = 148 CTAs (one per SM).
   const int64_t tiles_m = b2_ceil_div(M, tc::BM);
   const int64_t num_kb = b2_ceil_div(K, tc::BK);
-  const bool linear = (act == B2_ACT_NONE && mul == nullptr && add == nullptr);
+  // split-K adds partial tiles with red.global: only for a plain linear epilogue
+  const bool linear = (d->act == B2_ACT_NONE && d->mul == nullptr && d->add == nullptr && d->ybwd == nullptr &&
+                       d->c_small == nullptr && d->colsum == nullptr);
   int best_bn = 32, best_split = 1;
   double best_cost = 1e300;
-  const int bn_max = (a_small != nullptr) ? 128 : 256;  // 3xTF32 keeps >= 4 accumulator ranges in TMEM
+  const int bn_max = (d->a_small != nullptr) ? 128 : 256;  // 3xTF32 keeps >= 4 accumulator ranges in TMEM
   for (int bn = 32; bn <= bn_max; bn += 32) {
     const int64_t tiles_n = b2_ceil_div(N, bn);
     for (int split = 1; split <= 32; split *= 2) {
@@ -604,20 +668,22 @@ extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, in
     }
   }
   tc::Params p;
-  const int nseg = (a_small != nullptr) ? 3 : 1;
-  const float* as[2] = {a, a_small};
-  const float* bs[2] = {b, b_small};
+  const int nseg = (d->a_small != nullptr) ? 3 : 1;
+  const float* as[2] = {a, d->a_small};
+  const float* bs[2] = {b, d->b_small};
   for (int s = 0; s < (nseg > 1 ? 2 : 1); ++s) {
-    int rc = encode_kmajor(&p.map_a[s], as[s], M, K, lda, tc::BM);
+    int rc = encode_operand(&p.map_a[s], as[s], M, K, lda, d->a_mn_major, tc::BM);
     if (rc != B2_OK) return rc;
-    rc = encode_kmajor(&p.map_b[s], bs[s], N, K, ldb, best_bn);
+    rc = encode_operand(&p.map_b[s], bs[s], N, K, ldb, d->b_mn_major, best_bn);
     if (rc != B2_OK) return rc;
   }
-  p.c = c; p.ldc = ldc; p.bias = bias; p.mul = mul; p.add = add;
-  p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.act = act;
-  p.beta = beta_accumulate ? 1 : 0;
+  p.c = c; p.c_small = d->c_small; p.ldc = ldc; p.bias = d->bias; p.mul = d->mul; p.add = d->add;
+  p.ybwd = d->ybwd; p.colsum = d->colsum;
+  p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.act = d->act;
+  p.act_bwd = d->act_bwd;
+  p.a_mn = d->a_mn_major ? 1 : 0; p.b_mn = d->b_mn_major ? 1 : 0;
+  p.beta = d->beta_accumulate ? 1 : 0;
   p.kb_per_split = (int) b2_ceil_div(num_kb, best_split);
-  p.dbg = g_tc_debug;
   if (nseg == 1) {
     p.nmain = 1;
   } else {
@@ -636,19 +702,34 @@ extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, in
     cudaError_t e = cudaMemset2DAsync(c, (size_t) ldc * 4, 0, (size_t) N * 4, (size_t) M, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
-  const size_t smem = (nseg > 1 ? (size_t) 3 * 2 : (size_t) 4) * (tc::A_BYTES + (size_t) best_bn * 128) + 1024 + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) (4 * (tc::A_BYTES + 256 * 128) + 1024 + 128));
-    if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  if (d->colsum != nullptr) {
+    cudaError_t e = cudaMemsetAsync(d->colsum, 0, sizeof(float) * (size_t) N, st);
+    if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
+  const size_t smem = (nseg > 1 ? (size_t) 3 * 2 : (size_t) 4) * (tc::A_BYTES + (size_t) best_bn * 128) + 1024 + 128;
+  // opt-in to > 48 KB of dynamic shared memory: an idempotent per-process property of the kernel
+  // (C++11 guarantees the initialiser runs once, thread-safely)
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(
+      tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (4 * (tc::A_BYTES + 256 * 128) + 1024 + 128));
+  if (attr_rc != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(attr_rc));
   dim3 grid((unsigned) tiles_m, (unsigned) b2_ceil_div(N, best_bn), (unsigned) splits);
   B2_REQUIRE(grid.y <= 65535, "N too large for this launch geometry");
   tc::gemm_tf32_kernel<<<grid, tc::NTHREADS, smem, st>>>(p);
   B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
   return B2_OK;
+}
+
+extern "C" B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
+                                 int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int act,
+                                 const float* mul, const float* add, int beta_accumulate,
+                                 const float* a_small, const float* b_small, void* stream) {
+  b2_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a = a; d.b = b; d.a_small = a_small; d.b_small = b_small; d.c = c;
+  d.bias = bias; d.mul = mul; d.add = add;
+  d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.M = M; d.N = N; d.K = K;
+  d.act = act; d.beta_accumulate = beta_accumulate;
+  return b2_gemm_tc_ex(&d, stream);
 }
 
 extern "C" B2_API int b2_split_tf32(const float* x, float* small, int64_t n, void* stream) {
@@ -706,11 +787,21 @@ extern "C" B2_API int b2_head_fwd(const float* x, const float* w, const float* b
 
 extern "C" B2_API int b2_head_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M,
                                   int K, int act, float* gx, float* gw, float* gb, void* stream) {
+  return b2_head_bwd_ex(x, w, y, gy, M, K, act, gx, gw, gb, B2_ACT_NONE, nullptr, nullptr, stream);
+}
+
+extern "C" B2_API int b2_head_bwd_ex(const float* x, const float* w, const float* y, const float* gy, int64_t M,
+                                     int K, int act, float* gx, float* gw, float* gb, int prev_act,
+                                     float* gx_small, float* gb_prev, void* stream) {
   B2_REQUIRE(x && w && gy && gw, "NULL pointer");
-  B2_REQUIRE(K >= 1 && K <= 12288 && act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad K/act");
+  B2_REQUIRE(K >= 1 && K <= 6144 && act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad K/act");
+  B2_REQUIRE(prev_act >= B2_ACT_NONE && prev_act <= B2_ACT_SIGMOID, "bad prev_act");
   B2_REQUIRE(act == B2_ACT_NONE || y != nullptr, "activation backward needs y");
+  B2_REQUIRE(gx != nullptr || (gx_small == nullptr && gb_prev == nullptr && prev_act == B2_ACT_NONE),
+             "prev_act / gx_small / gb_prev need gx");
   cudaStream_t st = (cudaStream_t) stream;
   cudaError_t e = cudaMemsetAsync(gw, 0, sizeof(float) * (size_t) K, st);
+  if (e == cudaSuccess && gb_prev != nullptr) e = cudaMemsetAsync(gb_prev, 0, sizeof(float) * (size_t) K, st);
   if (e == cudaSuccess && gb != nullptr) e = cudaMemsetAsync(gb, 0, sizeof(float), st);
   if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_head_bwd: memset: %s", cudaGetErrorString(e));
   if (M <= 0) return B2_OK;
@@ -718,8 +809,8 @@ extern "C" B2_API int b2_head_bwd(const float* x, const float* w, const float* y
   if (ctas > b2_ceil_div(M, 8)) ctas = b2_ceil_div(M, 8);
   const int64_t rows_per_cta = b2_ceil_div(M, ctas);
   ctas = b2_ceil_div(M, rows_per_cta);
-  tc::head_bwd_kernel<<<(int) ctas, 256, sizeof(float) * (size_t) K, st>>>(x, w, (act == B2_ACT_NONE) ? nullptr : y,
-                                                                         gy, M, K, act, rows_per_cta, gx, gw, gb);
+  tc::head_bwd_kernel<<<(int) ctas, 256, 2 * sizeof(float) * (size_t) K, st>>>(
+      x, w, (act == B2_ACT_NONE) ? nullptr : y, gy, M, K, act, rows_per_cta, gx, gw, gb, prev_act, gx_small, gb_prev);
   B2_CUDA_LAUNCH_CHECK("b2_head_bwd");
   return B2_OK;
 }

@@ -5,6 +5,7 @@ tape; all arithmetic happens in libfuxictr_b200.so.  Every function requires CUD
 tensors and raises otherwise — there is no eager/CPU fallback on this path.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -397,14 +398,51 @@ def transpose_f32(t, want_small):
     return out, small
 
 
+def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=None, act=B2_ACT_NONE,
+            mul=None, add=None, ybwd=None, act_bwd=B2_ACT_NONE, out_small=None, colsum=None, accumulate=False):
+    """out (M,N) = epi(sum_k A(m,k) B(n,k)) on the tcgen05 kernel (b2_gemm_tc_ex).  a is (M,K), or (K,M) when
+    a_mn (MN-major: the tensor is consumed as it lies, no transpose); b is (N,K), or (K,N) when b_mn.
+    a_small / b_small: the operands' 3xTF32 small parts (both or neither).  Epilogue extras: ybwd/act_bwd
+    (activation backward of the gradient's producer), out_small (3xTF32 small part of out), colsum (N)."""
+    d = _lib.b2_gemm_desc()
+    K, M = (a.shape if a_mn else a.shape[::-1])
+    K2, N = (b.shape if b_mn else b.shape[::-1])
+    if K != K2 or tuple(out.shape) != (M, N) or out.stride(1) != 1 or a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError("gemm_ex shape mismatch: a%s b%s out%s" % (tuple(a.shape), tuple(b.shape), tuple(out.shape)))
+    for t in (mul, add, ybwd, out_small):
+        if t is not None and (tuple(t.shape) != (M, N) or t.stride(0) != out.stride(0) or t.stride(1) != 1):
+            raise ValueError("gemm_ex: epilogue tensors must share out's shape and leading dimension")
+    for t, ref in ((a_small, a), (b_small, b)):
+        if t is not None and (t.shape != ref.shape or t.stride() != ref.stride()):
+            raise ValueError("gemm_ex: small parts must share their operand's layout")
+    d.a, d.b = a.data_ptr(), b.data_ptr()
+    d.a_small = a_small.data_ptr() if a_small is not None else None
+    d.b_small = b_small.data_ptr() if b_small is not None else None
+    d.c = out.data_ptr()
+    d.c_small = out_small.data_ptr() if out_small is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.mul = mul.data_ptr() if mul is not None else None
+    d.add = add.data_ptr() if add is not None else None
+    d.ybwd = ybwd.data_ptr() if ybwd is not None else None
+    d.colsum = colsum.data_ptr() if colsum is not None else None
+    d.lda, d.ldb, d.ldc = a.stride(0), b.stride(0), out.stride(0)
+    d.M, d.N, d.K = M, N, K
+    d.a_mn_major, d.b_mn_major = int(bool(a_mn)), int(bool(b_mn))
+    d.act, d.act_bwd = act, (act_bwd if ybwd is not None else B2_ACT_NONE)
+    d.beta_accumulate = 1 if accumulate else 0
+    _lib.call("b2_gemm_tc_ex", ctypes.byref(d), _stream())
+    return out
+
+
 def gemm_nt(a, b, out, bias=None, act=B2_ACT_NONE, mul=None, add=None, accumulate=False,
             a_small=None, b_small=None):
     """out (M,N) = epi(a (M,K) @ b (N,K)^T) in the configured matmul precision."""
     mode = _MATMUL["mode"]
-    M, K = a.shape
     N = b.shape[0]
     use_tc = (mode != "fp32" and N >= 16 and _tc_operand_ok(a) and _tc_operand_ok(b) and out.stride(1) == 1)
-    if use_tc and mode == "tf32x3":
+    if not use_tc:
+        return gemm_f32(a, b, out, b_t=True, bias=bias, act=act, mul=mul, add=add, accumulate=accumulate)
+    if mode == "tf32x3":
         if a_small is None:
             if not a.is_contiguous():
                 a = a.contiguous()
@@ -413,14 +451,34 @@ def gemm_nt(a, b, out, bias=None, act=B2_ACT_NONE, mul=None, add=None, accumulat
             if not b.is_contiguous():
                 b = b.contiguous()
             b_small = split_tf32(b)
-    if not use_tc:
-        return gemm_f32(a, b, out, b_t=True, bias=bias, act=act, mul=mul, add=add, accumulate=accumulate)
-    if mode == "tf32":
+    else:
         a_small = b_small = None
-    _lib.call("b2_gemm_tc", _ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K,
-              _ptr(bias), act, _ptr(mul), _ptr(add), 1 if accumulate else 0, _ptr(a_small), _ptr(b_small),
-              _stream())
-    return out
+    return gemm_ex(a, b, out, a_small=a_small, b_small=b_small, bias=bias, act=act, mul=mul, add=add,
+                   accumulate=accumulate)
+
+
+# ---- 3xTF32 small parts of WEIGHTS: one split per weight per optimizer step -------------------
+# A weight changes once per step; its small part is cached until the weight's version changes.
+# torch bumps `_version` for in-place ops; updates through raw pointers (the fused arena optimizer,
+# CUDA-graph replays of it) are announced with bump_weight_epoch().
+_WEIGHT_EPOCH = [0]
+_SMALL_CACHE = weakref.WeakKeyDictionary()
+
+
+def bump_weight_epoch():
+    _WEIGHT_EPOCH[0] += 1
+
+
+def weight_small(w):
+    if not w.is_contiguous():
+        raise RuntimeError("tensor-core GEMM weights must be contiguous")
+    key = (w.data_ptr(), w._version, _WEIGHT_EPOCH[0], tuple(w.shape))
+    ent = _SMALL_CACHE.get(w)
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    small = split_tf32(w.detach())
+    _SMALL_CACHE[w] = (key, small)
+    return small
 
 
 def prep_operand(x, y=None, act=B2_ACT_NONE, want_out=False, want_small=False, want_t=False,
@@ -437,13 +495,21 @@ def prep_operand(x, y=None, act=B2_ACT_NONE, want_out=False, want_small=False, w
     return out, small, out_t, t_small
 
 
+def _tc_layer_ok(weight):
+    """nn.Linear weight (N, K) usable by the tensor-core kernel in all three contractions
+    (Y = X W^T, dX = dZ W, dW = dZ^T X): TMA needs 16-byte bases and leading dimensions % 4."""
+    N, K = weight.shape
+    return (_MATMUL["mode"] != "fp32" and N >= 16 and K >= 16 and N % 4 == 0 and K % 4 == 0
+            and weight.is_contiguous() and weight.data_ptr() % 16 == 0)
+
+
 class _LinearAct(torch.autograd.Function):
     """y = act(x W^T + b): nn.Linear (+ReLU/Sigmoid) of MLP_Block (mlp_block.py:74-80).
 
     Three arithmetic paths: the N = 1 output head (GEMV kernels), the tcgen05 tensor-core GEMM
-    (TF32 / 3xTF32; operands are prepared K-major by ONE b2_prep_operand pass each), and the fp32
-    SIMT GEMM.  The backward fuses activation-backward, the transposes/splits and the bias gradient
-    into a single pass over dY."""
+    (TF32 / 3xTF32; dX and dW consume W, dZ and X as they lie in memory through MN-major operand
+    descriptors — no transposes), and the fp32 SIMT GEMM.  The backward fuses activation-backward,
+    the 3xTF32 split and the bias gradient into a single pass over dY."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, act):
@@ -453,24 +519,17 @@ class _LinearAct(torch.autograd.Function):
         mode = _MATMUL["mode"]
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         ctx.act, ctx.bias, ctx.has_bias = act, bias, bias is not None
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)
         if N == 1 and weight.is_contiguous():
             ctx.kind = "head"
             _lib.call("b2_head_fwd", _ptr(x), _ptr(weight), _ptr(bias), M, K, act, _ptr(y), _stream())
             ctx.save_for_backward(x, weight, y if act != B2_ACT_NONE else None)
             return y
-        tc = (mode != "fp32" and N >= 16 and K >= 16 and N % 4 == 0 and K % 4 == 0 and M % 4 == 0
-              and _tc_operand_ok(x) and weight.is_contiguous() and weight.data_ptr() % 16 == 0)
-        if tc:
+        if _tc_layer_ok(weight) and x.data_ptr() % 16 == 0:
             ctx.kind = "tc"
             x3 = mode == "tf32x3"
-            # one pass per operand: 3xTF32 small parts now, K-major transposes for the backward
-            _, w_small, w_t, w_t_small = prep_operand(weight, want_small=x3, want_t=need_grad,
-                                                      want_t_small=need_grad and x3)
-            _, x_small, x_t, x_t_small = prep_operand(x, want_small=x3, want_t=need_grad,
-                                                      want_t_small=need_grad and x3)
-            gemm_nt(x, weight, y, bias=bias, act=act, a_small=x_small, b_small=w_small)
-            ctx.extra = (w_t, w_t_small, x_t, x_t_small)
+            x_small = split_tf32(x) if x3 else None
+            gemm_ex(x, weight, y, a_small=x_small, b_small=weight_small(weight) if x3 else None, bias=bias, act=act)
+            ctx.x_small = x_small
             ctx.save_for_backward(x, weight, y if act != B2_ACT_NONE else None)
             return y
         ctx.kind = "simt"
@@ -483,7 +542,6 @@ class _LinearAct(torch.autograd.Function):
         x, weight, y = ctx.saved_tensors
         gy = _f32c(gy)
         M, K = x.shape
-        N = weight.shape[0]
         act = ctx.act
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
@@ -496,28 +554,22 @@ class _LinearAct(torch.autograd.Function):
                       _ptr(gb), _stream())
             return gx, gw, gb, None
         gb = _grad_buffer(ctx.bias, zero=False) if need_b else None
+        fused = act != B2_ACT_NONE
         if ctx.kind == "tc":
-            x3 = _MATMUL["mode"] == "tf32x3"
-            w_t, w_t_small, x_t, x_t_small = ctx.extra
-            if w_t is None:   # forward ran without grad bookkeeping (should not happen under autograd)
-                _, _, w_t, w_t_small = prep_operand(weight, want_t=True, want_t_small=x3)
-                _, _, x_t, x_t_small = prep_operand(x, want_t=True, want_t_small=x3)
-            fused = act != B2_ACT_NONE
-            # dZ = act'(Y) * dY, its small part, its transpose (+small) and the bias gradient: one pass
-            gz, gz_small, gz_t, gz_t_small = prep_operand(gy, y if fused else None, act, want_out=fused,
-                                                          want_small=x3 and need_x, want_t=need_w,
-                                                          want_t_small=x3 and need_w, colsum=gb)
+            x3 = ctx.x_small is not None
+            # dZ = act'(Y) * dY, its 3xTF32 small part and the bias gradient: one pass over dY
+            gz, gz_small, _, _ = prep_operand(gy, y if fused else None, act, want_out=fused, want_small=x3, colsum=gb)
             if not fused:
                 gz = gy
             if need_x:
                 gx = torch.empty((M, K), dtype=torch.float32, device=x.device)
-                gemm_nt(gz, w_t, gx, a_small=gz_small, b_small=w_t_small)            # dX = dZ W
+                gemm_ex(gz, weight, gx, b_mn=True, a_small=gz_small,
+                        b_small=weight_small(weight) if x3 else None)                        # dX = dZ W
             if need_w:
                 gw = _grad_buffer(weight, zero=False)
-                gemm_nt(gz_t, x_t, gw, a_small=gz_t_small, b_small=x_t_small)        # dW = dZ^T X
+                gemm_ex(gz, x, gw, a_mn=True, b_mn=True, a_small=gz_small, b_small=ctx.x_small)    # dW = dZ^T X
             return gx, gw, gb, None
         # fp32 SIMT path
-        fused = act != B2_ACT_NONE
         gz = gy
         if fused or gb is not None:
             out, _, _, _ = prep_operand(gy, y if fused else None, act, want_out=fused, colsum=gb)
@@ -530,6 +582,146 @@ class _LinearAct(torch.autograd.Function):
             gw = _grad_buffer(weight, zero=False)
             gemm_f32(gz, x, gw, a_t=True)
         return gx, gw, gb, None
+
+
+class _MLPChain(torch.autograd.Function):
+    """A whole Linear(+ReLU/Sigmoid) chain of MLP_Block (mlp_block.py:64-85) as ONE autograd node, so that
+    work can move across layer boundaries: the forward epilogue of layer i writes the 3xTF32 small part
+    layer i+1 consumes; the dgrad GEMM of layer i+1 applies layer i's activation backward in its
+    epilogue and emits dZ_i, its small part and layer i's bias gradient directly (the N = 1 head does
+    the same in its fused backward).  Launches per 3-hidden-layer MLP step: 15 (was 26)."""
+
+    @staticmethod
+    def forward(ctx, x, acts, *params):
+        x = _f32c(x)
+        M = x.shape[0]
+        L = len(acts)
+        Ws, bs = params[0::2], params[1::2]
+        x3 = _MATMUL["mode"] == "tf32x3"
+        kinds = []
+        for W in Ws:
+            if W.shape[0] == 1 and W.is_contiguous():
+                kinds.append("head")
+            elif _tc_layer_ok(W):
+                kinds.append("tc")
+            else:
+                kinds.append("simt")
+        hs = [x]
+        smalls = [split_tf32(x) if (x3 and kinds[0] == "tc") else None]
+        for i in range(L):
+            W, b, act = Ws[i], bs[i], acts[i]
+            N, K = W.shape
+            h = hs[-1]
+            y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            want_small = x3 and i + 1 < L and kinds[i + 1] == "tc"
+            y_small = None
+            if kinds[i] == "head":
+                _lib.call("b2_head_fwd", _ptr(h), _ptr(W), _ptr(b), M, K, act, _ptr(y), _stream())
+            elif kinds[i] == "tc" and h.data_ptr() % 16 == 0:
+                y_small = torch.empty_like(y) if want_small else None
+                gemm_ex(h, W, y, a_small=smalls[-1], b_small=weight_small(W) if x3 else None, bias=b, act=act,
+                        out_small=y_small)
+            else:
+                kinds[i] = "simt"
+                gemm_f32(h, W, y, b_t=True, bias=b, act=act)
+            if want_small and y_small is None:
+                y_small = split_tf32(y)
+            hs.append(y)
+            smalls.append(y_small)
+        ctx.acts, ctx.kinds, ctx.smalls, ctx.params = acts, kinds, smalls, params
+        ctx.save_for_backward(*hs)
+        return hs[-1]
+
+    @staticmethod
+    def backward(ctx, gy):
+        hs = ctx.saved_tensors
+        acts, kinds, smalls, params = ctx.acts, ctx.kinds, ctx.smalls, ctx.params
+        Ws, bs = params[0::2], params[1::2]
+        L = len(acts)
+        M = hs[0].shape[0]
+        dev = hs[0].device
+        x3 = _MATMUL["mode"] == "tf32x3"
+        grads = [None] * len(params)
+
+        def bias_buf(i):
+            b = bs[i]
+            return _grad_buffer(b, zero=False) if (b is not None and b.requires_grad) else None
+
+        g, g_small, g_is_dz = _f32c(gy), None, False     # g: gradient w.r.t. y_i; g_is_dz: already dZ_i (+ db_i done)
+        for i in range(L - 1, -1, -1):
+            W, act, h, y = Ws[i], acts[i], hs[i], hs[i + 1]
+            N, K = W.shape
+            need_gx = i > 0 or ctx.needs_input_grad[0]
+            fuse_prev = i > 0                       # fold layer i-1's activation backward / bias grad into this dgrad
+            prev_small = fuse_prev and x3 and kinds[i - 1] == "tc"
+            gx = torch.empty((M, K), dtype=torch.float32, device=dev) if need_gx else None
+            gx_small = torch.empty_like(gx) if (prev_small and gx is not None) else None
+            gb_prev = None
+            if kinds[i] == "head":
+                gw = _grad_buffer(W, zero=False)
+                gb = None if g_is_dz else bias_buf(i)          # g already dZ_i: activation backward and db_i are done
+                gb_prev = bias_buf(i - 1) if fuse_prev else None
+                _lib.call("b2_head_bwd_ex", _ptr(h), _ptr(W), None if g_is_dz else _ptr(y), _ptr(g), M, K,
+                          B2_ACT_NONE if g_is_dz else act, _ptr(gx), _ptr(gw), _ptr(gb),
+                          acts[i - 1] if fuse_prev else B2_ACT_NONE, _ptr(gx_small), _ptr(gb_prev), _stream())
+                grads[2 * i] = gw
+                if not g_is_dz:
+                    grads[2 * i + 1] = gb
+                if fuse_prev:
+                    grads[2 * (i - 1) + 1] = gb_prev
+                g, g_small, g_is_dz = gx, gx_small, fuse_prev
+                continue
+            if not g_is_dz:     # top of the chain (or below a non-fusing layer): one explicit pass over dY
+                gb = bias_buf(i)
+                fused = act != B2_ACT_NONE
+                out, sm, _, _ = prep_operand(g, y if fused else None, act, want_out=fused,
+                                             want_small=x3 and kinds[i] == "tc", colsum=gb)
+                gz, gz_small = (out if fused else g), sm
+                grads[2 * i + 1] = gb
+            else:
+                gz, gz_small = g, g_small
+            if kinds[i] == "tc":
+                if gx is not None:
+                    prev_act = acts[i - 1] if fuse_prev else B2_ACT_NONE
+                    gb_prev = bias_buf(i - 1) if fuse_prev else None
+                    gemm_ex(gz, W, gx, b_mn=True, a_small=gz_small, b_small=weight_small(W) if x3 else None,
+                            ybwd=hs[i] if (fuse_prev and prev_act != B2_ACT_NONE) else None, act_bwd=prev_act,
+                            out_small=gx_small, colsum=gb_prev)                                   # dX (= dZ_{i-1})
+                if W.requires_grad:
+                    gw = _grad_buffer(W, zero=False)
+                    gemm_ex(gz, h, gw, a_mn=True, b_mn=True, a_small=gz_small, b_small=smalls[i])     # dW = dZ^T X
+                    grads[2 * i] = gw
+                g, g_small, g_is_dz = gx, gx_small, fuse_prev
+            else:               # fp32 SIMT layer inside a chain (odd shapes)
+                if gx is not None:
+                    gemm_f32(gz, W, gx)
+                if W.requires_grad:
+                    gw = _grad_buffer(W, zero=False)
+                    gemm_f32(gz, h, gw, a_t=True)
+                    grads[2 * i] = gw
+                g, g_small, g_is_dz = gx, None, False    # layer i-1 takes the explicit pass (its own db)
+                continue
+            if fuse_prev:
+                grads[2 * (i - 1) + 1] = gb_prev
+        return (g if ctx.needs_input_grad[0] else None, None) + tuple(grads)
+
+
+def mlp_chain_supported():
+    return _MATMUL["mode"] != "fp32"
+
+
+def mlp_chain(x, layers):
+    """layers: list of (weight, bias or None, act code).  Returns act_L(...act_0(x W_0^T + b_0)...)."""
+    _require_cuda(x)
+    acts = tuple(a for _, _, a in layers)
+    flat = []
+    for w, b, _ in layers:
+        _require_cuda(w, b)
+        flat += [w, b]
+    if x.dim() != 2:
+        lead = x.shape[:-1]
+        return _MLPChain.apply(x.reshape(-1, x.shape[-1]), acts, *flat).view(*lead, -1)
+    return _MLPChain.apply(x, acts, *flat)
 
 
 def linear_act(x, weight, bias=None, act=B2_ACT_NONE):

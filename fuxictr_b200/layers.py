@@ -553,6 +553,22 @@ class MLP_Block(nn.Module):
     def forward(self, inputs):
         mods = list(self.mlp)
         x = inputs
+        if F2.mlp_chain_supported() and inputs.is_cuda:
+            # a pure Linear(+ReLU/Sigmoid) stack runs as ONE autograd node (cross-layer epilogue fusion)
+            layers, i, pure = [], 0, len(mods) > 0
+            while i < len(mods):
+                if type(mods[i]) != nn.Linear:
+                    pure = False
+                    break
+                act = B2_ACT_NONE
+                if i + 1 < len(mods) and type(mods[i + 1]) == nn.ReLU:
+                    act = B2_ACT_RELU
+                elif i + 1 < len(mods) and type(mods[i + 1]) == nn.Sigmoid:
+                    act = B2_ACT_SIGMOID
+                layers.append((mods[i].weight, mods[i].bias, act))
+                i += 2 if act != B2_ACT_NONE else 1
+            if pure:
+                return F2.mlp_chain(x, layers)
         i = 0
         while i < len(mods):
             m = mods[i]

@@ -17,6 +17,8 @@ Nothing here computes: it is stream/event plumbing around the C-ABI kernels.
 """
 import torch
 
+from . import functional as F2
+
 
 class TrainPipeline(object):
     """model: a fuxictr_b200.zoo.RankModel after use_fused_optimizer().
@@ -81,6 +83,7 @@ class TrainPipeline(object):
     def _run(self):
         if self.graph is not None:
             self.model._fused_optimizer.count_step()      # a replay is one optimizer step (host-side bound check)
+            F2.bump_weight_epoch()                        # ... that moved the weights behind torch's back
             self.graph.replay()
             return self.loss_dev
         self.loss_dev = self._eager().detach()

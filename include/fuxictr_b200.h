@@ -351,9 +351,45 @@ B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, int64_t ldb, 
                       int64_t M, int64_t N, int64_t K, const float* bias, int act, const float* mul,
                       const float* add, int beta_accumulate, const float* a_small,
                       const float* b_small, void* stream);
-/* Diagnostic: later b2_gemm_tc launches record 8 %globaltimer stamps (ns) of CTA (0,0,0) in buf
- * (device int64[8]); NULL disables. */
-B2_API int b2_gemm_tc_set_debug(long long* buf);
+
+/*
+ * The general tensor-core contraction:  C[m,n] = epi( sum_k A(m,k) * B(n,k) ).
+ * Operand layouts (the tensor core reads either through its shared-memory matrix descriptor, so
+ * no transpose pass is ever needed):
+ *   a_mn_major == 0:  A in memory (M, K), k contiguous, leading dimension lda   ("K-major")
+ *   a_mn_major != 0:  A in memory (K, M), m contiguous, leading dimension lda   ("MN-major")
+ *   likewise b_mn_major for B: (N, K) or (K, N).
+ * This covers the three contractions of nn.Linear (mlp_block.py:74, autograd of F.linear) on the
+ * tensors as they lie in memory:  Y = X W^T (both K-major);  dX = dZ W (B = W MN-major);
+ * dW = dZ^T X (A = dZ and B = X MN-major).
+ * Epilogue, in this order:  v = acc + bias[n];  v = add + mul * v;  v = act(v);
+ *   v = act_bwd'(ybwd[m,n]) * v   (ybwd = the activation OUTPUT whose backward is fused: the dgrad
+ *                                  GEMM of layer i+1 emits dZ_i directly; threshold_backward /
+ *                                  sigmoid_backward of the reference's autograd);
+ *   C = v (+ C if beta_accumulate);  c_small = v - tf32_trunc(v) (the consumer's 3xTF32 operand);
+ *   colsum[n] = sum_m v  (bias gradient; the call zeroes colsum first).
+ * mul, add, ybwd, c_small share C's leading dimension.  a_small/b_small: 3xTF32 small parts of the
+ * operands (same layout as the operands) or both NULL for single-pass TF32.
+ */
+typedef struct b2_gemm_desc {
+  const float* a;
+  const float* b;
+  const float* a_small;
+  const float* b_small;
+  float* c;
+  float* c_small;
+  const float* bias;
+  const float* mul;
+  const float* add;
+  const float* ybwd;
+  float* colsum;
+  int64_t lda, ldb, ldc;
+  int64_t M, N, K;
+  int32_t a_mn_major, b_mn_major;
+  int32_t act, act_bwd;
+  int32_t beta_accumulate, reserved_;
+} b2_gemm_desc;
+B2_API int b2_gemm_tc_ex(const b2_gemm_desc* desc, void* stream);
 /* small[i] = x[i] - (x[i] with the 13 low mantissa bits cleared). */
 B2_API int b2_split_tf32(const float* x, float* small, int64_t n, void* stream);
 /* out (cols, rows; ld_out) = in (rows, cols; ld_in)^T; if out_small != NULL it also receives the
@@ -378,6 +414,12 @@ B2_API int b2_head_fwd(const float* x, const float* w, const float* b, int64_t M
                        void* stream);
 B2_API int b2_head_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M, int K,
                        int act, float* gx, float* gw, float* gb, void* stream);
+/* Same, fused with the activation backward of the layer that PRODUCED x (x is that layer's
+ * activation output, mlp_block.py:78-80): gx <- prev_act'(x) * gx, gx_small = its 3xTF32 small part
+ * (or NULL), gb_prev (K) = sum_m gx[m,:] = that layer's bias gradient (or NULL). */
+B2_API int b2_head_bwd_ex(const float* x, const float* w, const float* y, const float* gy, int64_t M, int K,
+                          int act, float* gx, float* gw, float* gb, int prev_act, float* gx_small,
+                          float* gb_prev, void* stream);
 /* Elementwise helpers used by the dense backward.
  * b2_act_bwd: gx = gy * act'(y) where y is the activation OUTPUT (relu, sigmoid). */
 B2_API int b2_act_bwd(const float* y, const float* gy, float* gx, int64_t n, int act, void* stream);

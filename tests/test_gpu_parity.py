@@ -1,6 +1,7 @@
 """Parity of the sm_100a kernels (called through the C-ABI) against the reference goldens
 and the CPU oracle.  Bar (BASELINE.json north_star): index gather bit-exact; logits and
 gradients within 1e-5 relative fp32."""
+import copy
 import ctypes
 import sys
 from collections import OrderedDict
@@ -553,6 +554,103 @@ def test_gemm_tc_epilogues():
         assert close(out, base.double() + a.double() @ b.double().t(), RTOL)
     finally:
         F2.set_matmul_precision("fp32")
+
+
+MN_SHAPES = [(128, 32, 32), (300, 624, 4096), (4096, 624, 300), (624, 300, 8192), (77, 44, 36), (129, 260, 1000),
+             (64, 64, 432)]
+
+
+@pytest.mark.parametrize("M,N,K", MN_SHAPES)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
+def test_gemm_tc_mn_major_operands_vs_fp64(M, N, K, a_mn, b_mn, mode):
+    """The contraction reads operands as they lie in memory: A stored (K, M) and/or B stored (K, N)
+    (the dgrad / wgrad layouts of nn.Linear) through MN-major matrix descriptors — no transpose."""
+    from fuxictr_b200 import functional as F2
+    gen = torch.Generator().manual_seed(M + 3 * N + 7 * K + a_mn + 2 * b_mn)
+    a = torch.randn(M, K, generator=gen)
+    b = torch.randn(N, K, generator=gen)
+    ref = a.double() @ b.double().t()
+    a_dev = (a.t().contiguous() if a_mn else a).cuda()
+    b_dev = (b.t().contiguous() if b_mn else b).cuda()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    x3 = mode == "tf32x3"
+    F2.gemm_ex(a_dev, b_dev, out, a_mn=a_mn, b_mn=b_mn, a_small=F2.split_tf32(a_dev) if x3 else None,
+               b_small=F2.split_tf32(b_dev) if x3 else None)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    err = rel_err(out, ref)
+    assert err <= (3e-3 if mode == "tf32" else 2e-6), err
+
+
+@pytest.mark.parametrize("act_bwd", ["none", "relu", "sigmoid"])
+def test_gemm_tc_fused_backward_epilogue(act_bwd):
+    """dgrad epilogue = activation backward of the producer + 3xTF32 small part + bias gradient."""
+    from fuxictr_b200 import functional as F2
+    from fuxictr_b200._lib import B2_ACT_NONE, B2_ACT_RELU, B2_ACT_SIGMOID
+    code = {"none": B2_ACT_NONE, "relu": B2_ACT_RELU, "sigmoid": B2_ACT_SIGMOID}[act_bwd]
+    gen = torch.Generator().manual_seed(11)
+    M, N, K = 700, 200, 96            # dX (M, N) = dZ (M, K) @ W (K, N): W is the MN-major B operand
+    dz, w = torch.randn(M, K, generator=gen), torch.randn(K, N, generator=gen)
+    y = torch.rand(M, N, generator=gen) - (0.5 if act_bwd == "relu" else 0.0)
+    acc = dz.double() @ w.double()
+    if act_bwd == "relu":
+        want = torch.where(y.double() > 0, acc, torch.zeros_like(acc))
+    elif act_bwd == "sigmoid":
+        want = acc * ((1 - y.double()) * y.double())
+    else:
+        want = acc
+    dzc, wc = dz.cuda(), w.cuda()
+    out = torch.empty(M, N, device="cuda")
+    out_small = torch.full((M, N), float("nan"), device="cuda")
+    colsum = torch.full((N,), float("nan"), device="cuda")
+    F2.gemm_ex(dzc, wc, out, b_mn=True, a_small=F2.split_tf32(dzc), b_small=F2.split_tf32(wc),
+               ybwd=y.cuda() if code != B2_ACT_NONE else None, act_bwd=code, out_small=out_small, colsum=colsum)
+    assert close(out, want, RTOL)
+    assert torch.equal(out_small, F2.split_tf32(out))                       # exactly the consumer's small part
+    assert close(colsum, want.sum(dim=0), RTOL, atol=1e-5 * float(want.abs().sum(dim=0).max()))
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("dims,acts,B", [((624, 300, 300, 300, 1), ("relu", "relu", "relu", None), 4096),
+                                         ((325, 64, 64, 64, 1), ("relu", "relu", "relu", "sigmoid"), 1000),
+                                         ((128, 64, 1), ("sigmoid", None), 777),
+                                         ((432, 500, 500, 500), ("relu", "relu", "relu"), 2048),
+                                         ((40, 18, 36, 1), ("relu", None, None), 130)])
+def test_mlp_chain_matches_torch_autograd(mode, dims, acts, B):
+    """MLP_Block as one autograd node (cross-layer fused epilogues, MN-major dgrad/wgrad, fused head)
+    against the reference's ops (nn.Linear / ReLU / Sigmoid autograd) in float64."""
+    from fuxictr_b200 import layers, functional as F2
+    torch.manual_seed(sum(dims) + B)
+    hidden = list(dims[1:-1]) if dims[-1] == 1 else list(dims[1:])
+    out_dim = 1 if dims[-1] == 1 else None
+    hid_acts = [({"relu": "ReLU", "sigmoid": "Sigmoid", None: None}[a]) for a in acts[:len(hidden)]]
+    out_act = None
+    if out_dim is not None and acts[-1] is not None:
+        out_act = {"relu": "ReLU", "sigmoid": "Sigmoid"}[acts[-1]]
+    mlp = layers.MLP_Block(input_dim=dims[0], hidden_units=hidden, hidden_activations=hid_acts, output_dim=out_dim,
+                           output_activation=out_act)
+    ref = copy.deepcopy(mlp).double()
+    mlp = mlp.cuda()
+    gen = torch.Generator().manual_seed(B)
+    x = torch.randn(B, dims[0], generator=gen)
+    gout = torch.randn(B, dims[-1], generator=gen)
+    xr = x.double().requires_grad_(True)
+    yr = ref.mlp(xr)
+    yr.backward(gout.double())
+    xg = x.cuda().requires_grad_(True)
+    F2.set_matmul_precision(mode)
+    try:
+        yg = mlp(xg)
+        assert type(yg.grad_fn).__name__.startswith("_MLPChain")
+        yg.backward(gout.cuda())
+    finally:
+        F2.set_matmul_precision("fp32")
+    tol = RTOL if mode == "tf32x3" else 5e-3
+    assert close(yg, yr, tol)
+    assert close(xg.grad, xr.grad, tol, atol=tol * float(xr.grad.abs().max()))
+    for (k, pg), (_, pr) in zip(mlp.named_parameters(), ref.named_parameters()):
+        assert close(pg.grad, pr.grad, tol, atol=tol * float(pr.grad.abs().max())), k
 
 
 @pytest.mark.parametrize("name", ["DeepFM", "DCNv2", "DLRM", "xDeepFM", "DIN"])
