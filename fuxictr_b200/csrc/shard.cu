@@ -12,9 +12,13 @@
 //   requesting rank's `emb`/`lrw` (P2P stores, 16 B per lane).  Each (sample, field) slot has
 //   exactly one owner, so the stores never collide and exactly (world-1)/world of B*F*D*4 bytes
 //   cross NVLink — the volume of an ideal all-to-all, with the gather fused into the transfer.
-// Backward `shard_pull_kernel`: the owner pulls the gradient row of every (sample, field) it
-//   owns from the requesting rank's `gemb` (P2P loads) and scatter-adds it (warp-aggregated
-//   `red.global.add.v4.f32`) into its local dense-gradient shard.
+// While pushing, the owner appends every (requester, sample, field, local row) it served to a local
+//   list (warp-aggregated append): ~B_local*F entries, its exact share of the global batch.
+// Backward `shard_pull_kernel`: the owner walks THAT LIST (not world*B*F candidates, and no second
+//   pass over the peers' id matrices), pulls each gradient row from the requesting rank's `gemb`
+//   (P2P loads) and scatter-adds it (warp-aggregated `red.global.add.v4.f32`) into its local
+//   dense-gradient shard.
+// `shard_bcast_kernel`: one launch stores this rank's batch matrix into its slot on every peer.
 // Replaces, for sharded tables, FeatureEmbedding/LogisticRegression lookups and their autograd
 // (fuxictr/pytorch/layers/embeddings/feature_embedding.py:261-297,
 //  fuxictr/pytorch/layers/blocks/logistic_regression.py:55-58); the reference has no multi-GPU path.
@@ -30,12 +34,17 @@ struct PeerPtrs {
   const float* glogit[16];
 };
 
+// flags packed next to the field index in an owned-list entry
+#define B2_OWN_EMB (1 << 17)
+#define B2_OWN_LR (1 << 16)
+
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 shard_push_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant__ B2FieldPack lr,
                   const __grid_constant__ PeerPtrs peers, int64_t batch_local, int64_t ids_stride,
                   int dim, int lpr_log2, int has_lr, int world, int rank,
-                  int32_t* __restrict__ status) {
+                  int32_t* __restrict__ status, int4* __restrict__ owned, int32_t* __restrict__ owned_count,
+                  int32_t owned_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemFields sf = b2_stage_fields(emb, smem_raw);
   SmemFields lf;
@@ -44,44 +53,72 @@ shard_push_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant
   if (has_lr) lf = b2_stage_fields(lr, smem_raw + ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15));
   const int F = emb.nfields;
   const int LPR = 1 << lpr_log2;
-  const int sub = threadIdx.x & (LPR - 1);
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPR - 1);
+  const int my_group = lane >> lpr_log2;
   const int e = sub * 4;
   const int64_t per_rank = batch_local * (int64_t) F;
   const int64_t nitems = per_rank * world;
   const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> lpr_log2;
   const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> lpr_log2;
+  const int64_t warp_first = group - my_group;
   const int64_t FD = (int64_t) F * dim;
-  for (int64_t item = group; item < nitems; item += ngroups) {
-    const int p = (int) (item / per_rank);           // requesting rank
-    const int64_t rem = item - (int64_t) p * per_rank;
-    const int64_t b = rem / F;
-    const int f = (int) (rem - b * F);
-    const b2_field& fd = sf.f[f];
-    // fd.idx_stride carries the COLUMN of this field inside the batch matrix
-    const int64_t row = b2_load_index<IdxT>(peers.ids[p], b * ids_stride + fd.idx_stride);
-    if (row < 0 || row >= fd.vocab) {
-      if (status != nullptr && sub == 0 && p == rank) atomicMax(status, f + 1);
-      if (e < dim && (row < 0 ? 0 : (int) (row % world)) == rank)  // keep the slot defined: zero row
-        *reinterpret_cast<float4*>(peers.emb[p] + b * FD + (int64_t) f * dim + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_lr && sub == 0 && (row < 0 ? 0 : (int) (row % world)) == rank) peers.lrw[p][b * F + f] = 0.f;
-      continue;
+  for (int64_t wbase = warp_first; wbase < nitems; wbase += ngroups) {   // warp-uniform trip count
+    const int64_t item = wbase + my_group;
+    int4 entry = make_int4(0, 0, 0, 0);
+    bool append = false;
+    if (item < nitems) {
+      const int p = (int) (item / per_rank);           // requesting rank
+      const int64_t rem = item - (int64_t) p * per_rank;
+      const int64_t b = rem / F;
+      const int f = (int) (rem - b * F);
+      const b2_field& fd = sf.f[f];
+      // fd.idx_stride carries the COLUMN of this field inside the batch matrix
+      const int64_t row = b2_load_index<IdxT>(peers.ids[p], b * ids_stride + fd.idx_stride);
+      if (row < 0 || row >= fd.vocab) {
+        if (status != nullptr && sub == 0 && p == rank) atomicMax(status, f + 1);
+        if ((row < 0 ? 0 : (int) (row % world)) == rank) {  // keep the slot defined: zero row
+          if (e < dim)
+            *reinterpret_cast<float4*>(peers.emb[p] + b * FD + (int64_t) f * dim + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_lr && sub == 0) peers.lrw[p][b * F + f] = 0.f;
+        }
+      } else if ((int) (row % world) == rank) {          // my row
+        const int64_t lrow = row / world;
+        if (e < dim) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(fd.table) + lrow * dim + e));
+          *reinterpret_cast<float4*>(peers.emb[p] + b * FD + (int64_t) f * dim + e) = v;   // P2P store
+        }
+        if (has_lr && sub == 0)
+          peers.lrw[p][b * F + f] = __ldg(reinterpret_cast<const float*>(lf.f[f].table) + lrow);
+        if (owned != nullptr && sub == 0) {
+          int flags = (row != (int64_t) fd.padding_idx) ? B2_OWN_EMB : 0;     // padding rows get no gradient
+          if (has_lr && row != (int64_t) lf.f[f].padding_idx) flags |= B2_OWN_LR;
+          if (flags != 0) {
+            entry = make_int4(p, (int) rem, (int) lrow, f | flags);
+            append = true;
+          }
+        }
+      }
     }
-    if ((int) (row % world) != rank) continue;       // not my row
-    const int64_t lrow = row / world;
-    if (e < dim) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(fd.table) + lrow * dim + e));
-      *reinterpret_cast<float4*>(peers.emb[p] + b * FD + (int64_t) f * dim + e) = v;   // P2P store
+    if (owned != nullptr) {      // warp-aggregated append: one atomic per warp
+      const unsigned m = __ballot_sync(0xffffffffu, append);
+      if (m != 0u) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(owned_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (append) {
+          const int pos = base + __popc(m & ((1u << lane) - 1u));
+          if (pos < owned_cap) owned[pos] = entry;
+        }
+      }
     }
-    if (has_lr && sub == 0)
-      peers.lrw[p][b * F + f] = __ldg(reinterpret_cast<const float*>(lf.f[f].table) + lrow);
   }
 }
 
-template <typename IdxT>
 __global__ void __launch_bounds__(256)
 shard_pull_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant__ B2FieldPack lr,
-                  const __grid_constant__ PeerPtrs peers, int64_t batch_local, int64_t ids_stride,
-                  int dim, int lpr_log2, int has_lr, int world, int rank, float scale) {
+                  const __grid_constant__ PeerPtrs peers, int dim, int lpr_log2, int has_lr, float scale,
+                  const int4* __restrict__ owned, const int32_t* __restrict__ owned_count, int32_t owned_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemFields sf = b2_stage_fields(emb, smem_raw);
   SmemFields lf;
@@ -95,35 +132,30 @@ shard_pull_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant
   const int my_group = lane >> lpr_log2;
   const int groups_per_warp = 32 >> lpr_log2;
   const int e = sub * 4;
-  const int64_t per_rank = batch_local * (int64_t) F;
-  const int64_t nitems = per_rank * world;
+  const int64_t nitems = min(*owned_count, owned_cap);
   const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> lpr_log2;
   const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> lpr_log2;
   const int64_t warp_first = group - my_group;
-  const int64_t FD = (int64_t) F * dim;
   for (int64_t wbase = warp_first; wbase < nitems; wbase += ngroups) {
     const int64_t item = wbase + my_group;
     float* drow = nullptr;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (item < nitems) {
-      const int p = (int) (item / per_rank);
-      const int64_t rem = item - (int64_t) p * per_rank;
-      const int64_t b = rem / F;
-      const int f = (int) (rem - b * F);
+      const int4 it = __ldg(owned + item);
+      const int p = it.x, f = it.w & 0xffff;
+      const int64_t bf = it.y, lrow = it.z;
       const b2_field& fd = sf.f[f];
-      const int64_t row = b2_load_index<IdxT>(peers.ids[p], b * ids_stride + fd.idx_stride);
-      if (row >= 0 && row < fd.vocab && (int) (row % world) == rank && row != (int64_t) fd.padding_idx) {
-        const int64_t lrow = row / world;
-        if (fd.table != nullptr) drow = reinterpret_cast<float*>(const_cast<void*>(fd.table)) + lrow * dim;
-        if (drow != nullptr && e < dim) {
-          v = *reinterpret_cast<const float4*>(peers.gemb[p] + b * FD + (int64_t) f * dim + e);  // P2P load
+      if ((it.w & B2_OWN_EMB) && fd.table != nullptr) {
+        drow = reinterpret_cast<float*>(const_cast<void*>(fd.table)) + lrow * dim;
+        if (e < dim) {
+          v = *reinterpret_cast<const float4*>(peers.gemb[p] + bf * dim + e);  // P2P load
           v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
         }
-        if (has_lr && sub == 0) {
-          const b2_field& ld = lf.f[f];
-          if (ld.table != nullptr && row != (int64_t) ld.padding_idx)
-            b2_red_add(reinterpret_cast<float*>(const_cast<void*>(ld.table)) + lrow, peers.glogit[p][b] * scale);
-        }
+      }
+      if (has_lr && sub == 0 && (it.w & B2_OWN_LR)) {
+        const b2_field& ld = lf.f[f];
+        if (ld.table != nullptr)
+          b2_red_add(reinterpret_cast<float*>(const_cast<void*>(ld.table)) + lrow, peers.glogit[p][bf / F] * scale);
       }
     }
     const unsigned peers_mask = __match_any_sync(0xffffffffu, (unsigned long long) drow);
@@ -145,6 +177,24 @@ shard_pull_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant
       v = acc;
     }
     if (leader && e < dim) b2_red_add_v4(drow + e, v);
+  }
+}
+
+// One launch: this rank's buffer -> the same slot on every peer (P2P stores, 16 B per thread-iteration).
+struct BcastDst { void* p[16]; };
+__global__ void __launch_bounds__(256)
+shard_bcast_kernel(const void* __restrict__ src, int64_t nbytes, const __grid_constant__ BcastDst dst, int world) {
+  const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t) gridDim.x * blockDim.x;
+  const int64_t n16 = nbytes >> 4;
+  const int4* s16 = reinterpret_cast<const int4*>(src);
+  for (int64_t i = tid; i < n16; i += nth) {
+    const int4 v = __ldg(s16 + i);
+    for (int p = 0; p < world; ++p) reinterpret_cast<int4*>(dst.p[p])[i] = v;
+  }
+  const int64_t tail0 = n16 << 4;
+  for (int64_t i = tail0 + tid * 4; i + 4 <= nbytes; i += nth * 4) {
+    const int32_t v = *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(src) + i);
+    for (int p = 0; p < world; ++p) *reinterpret_cast<int32_t*>(reinterpret_cast<char*>(dst.p[p]) + i) = v;
   }
 }
 
@@ -245,10 +295,19 @@ int check_shard_args(const b2_field* emb, int nfields, int world, int rank) {
 extern "C" B2_API int b2_shard_push(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
                                     int64_t batch_local, int world, int rank, const void* const* peer_ids,
                                     int idx_dtype, int64_t ids_stride, float* const* peer_emb,
-                                    float* const* peer_lrw, int32_t* status, void* stream) {
+                                    float* const* peer_lrw, int32_t* status, int32_t* owned,
+                                    int32_t* owned_count, int32_t owned_capacity, void* stream) {
   int rc = check_shard_args(emb_fields, nfields, world, rank);
   if (rc != B2_OK) return rc;
   B2_REQUIRE(peer_ids && peer_emb && (lr_fields == nullptr || peer_lrw != nullptr), "NULL peer pointer array");
+  B2_REQUIRE(owned == nullptr || (owned_count != nullptr && owned_capacity >= 1), "owned list needs a counter and a capacity");
+  B2_REQUIRE(owned == nullptr || ((uintptr_t) owned % 16) == 0, "owned list must be 16-byte aligned");
+  B2_REQUIRE(batch_local * (int64_t) nfields < (1ll << 31), "batch_local * nfields must fit 31 bits");
+  cudaStream_t st = (cudaStream_t) stream;
+  if (owned != nullptr) {
+    cudaError_t e = cudaMemsetAsync(owned_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_shard_push: memset: %s", cudaGetErrorString(e));
+  }
   if (batch_local <= 0) return B2_OK;
   static thread_local B2FieldPack epack, lpack;
   fill_pack_cols(epack, emb_fields, nfields);
@@ -266,11 +325,11 @@ extern "C" B2_API int b2_shard_push(const b2_field* emb_fields, const b2_field* 
   const int lpr_log2 = next_pow2_log2((dim + 3) / 4);
   const size_t smem = ((pack_smem_bytes(nfields) + 15) & ~(size_t) 15) + pack_smem_bytes(nfields) + 16;
   const int grid = grid_for((batch_local * (int64_t) nfields * world) << lpr_log2, 256);
-  cudaStream_t st = (cudaStream_t) stream;
+  int4* ow = reinterpret_cast<int4*>(owned);
   switch (idx_dtype) {
-    case B2_F64: shard_push_kernel<double><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, status); break;
-    case B2_I64: shard_push_kernel<int64_t><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, status); break;
-    case B2_I32: shard_push_kernel<int32_t><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, status); break;
+    case B2_F64: shard_push_kernel<double><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, status, ow, owned_count, owned_capacity); break;
+    case B2_I64: shard_push_kernel<int64_t><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, status, ow, owned_count, owned_capacity); break;
+    case B2_I32: shard_push_kernel<int32_t><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, status, ow, owned_count, owned_capacity); break;
     default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
   }
   B2_CUDA_LAUNCH_CHECK("b2_shard_push");
@@ -278,12 +337,13 @@ extern "C" B2_API int b2_shard_push(const b2_field* emb_fields, const b2_field* 
 }
 
 extern "C" B2_API int b2_shard_pull(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
-                                    int64_t batch_local, int world, int rank, const void* const* peer_ids,
-                                    int idx_dtype, int64_t ids_stride, const float* const* peer_gemb,
-                                    const float* const* peer_glogit, float scale, void* stream) {
+                                    int64_t batch_local, int world, int rank, const float* const* peer_gemb,
+                                    const float* const* peer_glogit, float scale, const int32_t* owned,
+                                    const int32_t* owned_count, int32_t owned_capacity, void* stream) {
   int rc = check_shard_args(emb_fields, nfields, world, rank);
   if (rc != B2_OK) return rc;
-  B2_REQUIRE(peer_ids && peer_gemb && (lr_fields == nullptr || peer_glogit != nullptr), "NULL peer pointer array");
+  B2_REQUIRE(peer_gemb && (lr_fields == nullptr || peer_glogit != nullptr), "NULL peer pointer array");
+  B2_REQUIRE(owned && owned_count && owned_capacity >= 1 && ((uintptr_t) owned % 16) == 0, "bad owned list");
   if (batch_local <= 0) return B2_OK;
   static thread_local B2FieldPack epack, lpack;
   fill_pack_cols(epack, emb_fields, nfields);
@@ -291,7 +351,7 @@ extern "C" B2_API int b2_shard_pull(const b2_field* emb_fields, const b2_field* 
   if (has_lr) fill_pack_cols(lpack, lr_fields, nfields); else lpack.nfields = 0;
   PeerPtrs pp;
   for (int i = 0; i < world; ++i) {
-    pp.ids[i] = peer_ids[i];
+    pp.ids[i] = nullptr;
     pp.emb[i] = nullptr;
     pp.lrw[i] = nullptr;
     pp.gemb[i] = peer_gemb[i];
@@ -300,15 +360,30 @@ extern "C" B2_API int b2_shard_pull(const b2_field* emb_fields, const b2_field* 
   const int dim = emb_fields[0].dim;
   const int lpr_log2 = next_pow2_log2((dim + 3) / 4);
   const size_t smem = ((pack_smem_bytes(nfields) + 15) & ~(size_t) 15) + pack_smem_bytes(nfields) + 16;
-  const int grid = grid_for((batch_local * (int64_t) nfields * world) << lpr_log2, 256);
-  cudaStream_t st = (cudaStream_t) stream;
-  switch (idx_dtype) {
-    case B2_F64: shard_pull_kernel<double><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, scale); break;
-    case B2_I64: shard_pull_kernel<int64_t><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, scale); break;
-    case B2_I32: shard_pull_kernel<int32_t><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, scale); break;
-    default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
-  }
+  // the list holds ~batch_local * nfields entries on a balanced batch (this rank's share of the global batch)
+  int64_t expect = batch_local * (int64_t) nfields * 2;
+  if (expect > owned_capacity) expect = owned_capacity;
+  const int grid = grid_for(expect << lpr_log2, 256);
+  shard_pull_kernel<<<grid, 256, smem, (cudaStream_t) stream>>>(epack, lpack, pp, dim, lpr_log2, has_lr, scale,
+                                                               reinterpret_cast<const int4*>(owned), owned_count,
+                                                               owned_capacity);
   B2_CUDA_LAUNCH_CHECK("b2_shard_pull");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_peer_bcast(const void* src, int64_t nbytes, void* const* peer_dst, int world, void* stream) {
+  B2_REQUIRE(src && peer_dst && world >= 1 && world <= 16, "bad argument");
+  B2_REQUIRE(nbytes >= 0 && nbytes % 4 == 0 && ((uintptr_t) src % 16) == 0, "buffer must be 16-byte aligned, a multiple of 4 bytes");
+  if (nbytes == 0) return B2_OK;
+  BcastDst d;
+  for (int i = 0; i < 16; ++i) d.p[i] = nullptr;
+  for (int i = 0; i < world; ++i) {
+    B2_REQUIRE(peer_dst[i] != nullptr && ((uintptr_t) peer_dst[i] % 16) == 0, "peer_dst[%d] NULL or misaligned", i);
+    d.p[i] = peer_dst[i];
+  }
+  const int grid = grid_for(nbytes >> 4, 256);
+  shard_bcast_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(src, nbytes, d, world);
+  B2_CUDA_LAUNCH_CHECK("b2_peer_bcast");
   return B2_OK;
 }
 

@@ -136,10 +136,17 @@ class ShardedFront(object):
         self.idx_code = F2._IDX_CODE[idx_dtype]
         g = group
         # ids_all[p] = batch matrix of rank p: every rank BROADCASTS its ids into slot `rank` of all
-        # peers (bulk P2P copies), so the push/pull kernels walk local memory only.
-        self.ids_all, _, self._ids_peer = g.alloc("ids_all", (g.world, batch_local, matrix_width), idx_dtype)
+        # peers (one launch of P2P stores), so the push kernel walks local memory only.
+        self.ids_all, self._ids_all_ptrs, self._ids_peer = g.alloc("ids_all", (g.world, batch_local, matrix_width),
+                                                                   idx_dtype)
         esz = self.ids_all.element_size()
-        self.ids_ptrs = [self.ids_all.data_ptr() + p * batch_local * matrix_width * esz for p in range(g.world)]
+        self._slot_bytes = batch_local * matrix_width * esz
+        self.ids_ptrs = [self.ids_all.data_ptr() + p * self._slot_bytes for p in range(g.world)]
+        self._ids_src = torch.empty((batch_local, matrix_width), dtype=idx_dtype, device="cuda")
+        # rows this rank served in the forward (filled by the push, walked by the pull): int32[4] entries
+        self.owned_cap = g.world * batch_local * self.F
+        self.owned = torch.empty((self.owned_cap, 4), dtype=torch.int32, device="cuda")
+        self.owned_count = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.emb, self.emb_ptrs, _ = g.alloc("emb", (batch_local, self.F * dim), torch.float32)
         self.lrw, self.lrw_ptrs, _ = g.alloc("lrw", (batch_local, self.F), torch.float32)
         self.gemb, self.gemb_ptrs, _ = g.alloc("gemb", (batch_local, self.F * dim), torch.float32)
@@ -158,15 +165,21 @@ class ShardedFront(object):
 
     # -- forward phases -------------------------------------------------------------------------
     def phase_ids(self, batch_matrix):
-        for p in range(self.group.world):
-            self._ids_peer(p)[self.group.rank].copy_(batch_matrix)      # P2P store of 8*B*W bytes per peer
+        g = self.group
+        src = batch_matrix
+        if (not src.is_contiguous()) or src.data_ptr() % 16 != 0:
+            self._ids_src.copy_(batch_matrix)
+            src = self._ids_src
+        dst = [int(base) + g.rank * self._slot_bytes for base in self._ids_all_ptrs]     # my slot on every rank
+        _lib.call("b2_peer_bcast", F2._ptr(src), self._slot_bytes, _ptr_array(dst), g.world, F2._stream())
 
     def phase_push(self):
         g = self.group
         lr = self._descs(self.lr_tables, 1) if self.lr_tables else None
         _lib.call("b2_shard_push", self._descs(self.emb_tables, self.dim), lr, self.F, self.B, g.world, g.rank,
                   _ptr_array(self.ids_ptrs), self.idx_code, self.W, _ptr_array(self.emb_ptrs),
-                  _ptr_array(self.lrw_ptrs) if lr is not None else None, F2._ptr(self.status), F2._stream())
+                  _ptr_array(self.lrw_ptrs) if lr is not None else None, F2._ptr(self.status),
+                  F2._ptr(self.owned), F2._ptr(self.owned_count), self.owned_cap, F2._stream())
 
     def phase_reduce(self):
         """Local: logit (B,1) and field sums from the landed rows.  Returns (emb copy, logit, sums)."""
@@ -190,12 +203,17 @@ class ShardedFront(object):
         g = self.group
         lr = self._descs(lr_grads, 1) if lr_grads else None
         _lib.call("b2_shard_pull", self._descs(emb_grads, self.dim), lr, self.F, self.B, g.world, g.rank,
-                  _ptr_array(self.ids_ptrs), self.idx_code, self.W, _ptr_array(self.gemb_ptrs),
-                  _ptr_array(self.glogit_ptrs) if lr is not None else None, 1.0 / g.world, F2._stream())
+                  _ptr_array(self.gemb_ptrs), _ptr_array(self.glogit_ptrs) if lr is not None else None,
+                  1.0 / g.world, F2._ptr(self.owned), F2._ptr(self.owned_count), self.owned_cap, F2._stream())
 
 
 class _ShardedFrontFn(torch.autograd.Function):
-    """(emb (B,F,D), logit (B,1)) with sharded tables; 2 barriers forward, 2 backward."""
+    """(emb (B,F,D), logit (B,1)) with sharded tables; 2 barriers forward, 1 backward.
+
+    No closing barrier: a peer buffer of this step is next written only behind the NEXT step's first
+    barrier (ids visible), which no rank passes before every rank has finished this step's backward
+    on its stream — and the pull walks the local owned-row list, not the peers' id matrices, so the
+    early overwrite of `ids_all` by the next step's broadcast cannot race with it."""
 
     @staticmethod
     def forward(ctx, front, batch_matrix, bias, *tables):
@@ -222,7 +240,6 @@ class _ShardedFrontFn(torch.autograd.Function):
         egrads = [(F2._grad_buffer(t, zero=True) if t.requires_grad else None) for t in tables[:n]]
         lgrads = [(F2._grad_buffer(t, zero=True) if t.requires_grad else None) for t in tables[n:]]
         front.phase_pull(egrads, lgrads if front.lr_tables else None)
-        g.barrier()                      # peers are done reading my buffers (safe to overwrite)
         gbias = None
         if bias is not None and bias.requires_grad:
             gbias = F2._grad_buffer(bias, zero=False)

@@ -228,18 +228,26 @@ B2_API int b2_lazy_materialize(const b2_lazy_table* tables_dev, int ntables, int
  *   peer_emb[p]   (B_local, F*D) fp32 embedding output of rank p     (peer-mapped, written)
  *   peer_lrw[p]   (B_local, F)   fp32 LR weights of rank p's samples (peer-mapped, written)
  * b2_shard_push gathers the rows THIS rank owns for every rank's samples and stores them into the
- * requester's buffers; b2_shard_pull reads the requester's gradient rows peer_gemb[p] (B_local,
- * F*D) / peer_glogit[p] (B_local) for the rows this rank owns and scatter-adds `scale *` them
- * into the local gradient shards.  Cross-rank ordering is the caller's barrier.  world <= 16.
+ * requester's buffers.  With `owned` != NULL it also records every (requester, sample*F+field, local
+ * row, field|flags) it served as one int32[4] entry of `owned` (16-byte aligned, `owned_capacity`
+ * entries; world * B_local * F can never overflow) and the entry count in `owned_count` (zeroed by
+ * the call).  b2_shard_pull walks that list: it reads the requester's gradient rows peer_gemb[p]
+ * (B_local, F*D) / peer_glogit[p] (B_local) and scatter-adds `scale *` them into the local gradient
+ * shards — ~B_local*F entries instead of world*B_local*F candidates, and no second pass over the
+ * peers' ids.  Cross-rank ordering is the caller's barrier.  world <= 16.
+ * b2_peer_bcast: one launch copies `nbytes` (multiple of 4, 16-byte aligned buffers) from src into
+ * peer_dst[p] for every p < world (P2P stores): the batch-matrix exchange.
  */
 B2_API int b2_shard_push(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
                          int64_t batch_local, int world, int rank, const void* const* peer_ids,
                          int idx_dtype, int64_t ids_stride, float* const* peer_emb,
-                         float* const* peer_lrw, int32_t* status, void* stream);
+                         float* const* peer_lrw, int32_t* status, int32_t* owned, int32_t* owned_count,
+                         int32_t owned_capacity, void* stream);
 B2_API int b2_shard_pull(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
-                         int64_t batch_local, int world, int rank, const void* const* peer_ids,
-                         int idx_dtype, int64_t ids_stride, const float* const* peer_gemb,
-                         const float* const* peer_glogit, float scale, void* stream);
+                         int64_t batch_local, int world, int rank, const float* const* peer_gemb,
+                         const float* const* peer_glogit, float scale, const int32_t* owned,
+                         const int32_t* owned_count, int32_t owned_capacity, void* stream);
+B2_API int b2_peer_bcast(const void* src, int64_t nbytes, void* const* peer_dst, int world, void* stream);
 /* After the push: logit[b] = [FM product_sum of emb[b]] (if want_fm) + sum_f lrw[b,f] + bias;
  * sums[b,:] = sum_f emb[b,f,:] (saved for the backward). */
 B2_API int b2_front_reduce(const float* emb, const float* lrw, const float* bias, int64_t batch,
