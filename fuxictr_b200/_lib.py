@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libfuxictr_b200.so")
 B2_F32, B2_BF16, B2_F64, B2_I64, B2_I32 = 0, 1, 2, 3, 4
 B2_POOL_NONE, B2_POOL_SUM, B2_POOL_MEAN = 0, 1, 2
 B2_ACT_NONE, B2_ACT_RELU, B2_ACT_SIGMOID = 0, 1, 2
+B2_PREP_MUL = 3
 B2_MAX_FIELDS = 128
 FM_PRODUCT_SUM, FM_BI_INTERACTION, FM_INNER_PRODUCT = 0, 1, 2
 
@@ -56,7 +57,7 @@ class b2_gemm_desc(ctypes.Structure):
     """struct b2_gemm_desc of include/fuxictr_b200.h."""
     _fields_ = [
         ("a", c_void_p), ("b", c_void_p), ("a_small", c_void_p), ("b_small", c_void_p),
-        ("c", c_void_p), ("c_small", c_void_p), ("bias", c_void_p), ("mul", c_void_p), ("add", c_void_p),
+        ("c", c_void_p), ("c_small", c_void_p), ("c_pre", c_void_p), ("bias", c_void_p), ("mul", c_void_p), ("add", c_void_p),
         ("ybwd", c_void_p), ("colsum", c_void_p),
         ("lda", c_int64), ("ldb", c_int64), ("ldc", c_int64), ("M", c_int64), ("N", c_int64), ("K", c_int64),
         ("a_mn_major", c_int32), ("b_mn_major", c_int32), ("act", c_int32), ("act_bwd", c_int32),

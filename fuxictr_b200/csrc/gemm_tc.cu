@@ -40,6 +40,7 @@ struct Params {
   CUtensorMap map_b[2];
   float* c;
   float* c_small;         // optional: tf32_small(C) for the consumer's 3xTF32 operand
+  float* c_pre;           // optional: acc + bias BEFORE mul/add/act (CrossNetV2 saves it for its backward)
   int64_t ldc;
   const float* bias;
   const float* mul;
@@ -325,6 +326,12 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
           for (int r = 0; r < 32; ++r)
             if (mrow0 + r < p.M) b2_red_add(cp + (int64_t) r * p.ldc, t[r]);
         } else {
+          if (p.c_pre != nullptr) {
+            float* pp = p.c_pre + (int64_t) mrow0 * p.ldc + n;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (mrow0 + r < p.M) pp[(int64_t) r * p.ldc] = t[r];
+          }
           if (p.mul != nullptr) {
             const float* mp = p.mul + (int64_t) mrow0 * p.ldc + n;
 #pragma unroll
@@ -453,6 +460,7 @@ prep_operand_kernel(const float* __restrict__ x, const float* __restrict__ y, in
         const float yv = __ldg(y + r * ld_in + c);
         if (act == B2_ACT_RELU) v = (yv > 0.f) ? v : 0.f;
         else if (act == B2_ACT_SIGMOID) v = v * ((1.f - yv) * yv);
+        else if (act == B2_PREP_MUL) v = v * yv;
       }
       if (out != nullptr) out[r * C + c] = v;
       if (out_small != nullptr) out_small[r * C + c] = tf32_small(v);
@@ -651,7 +659,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   const int64_t num_kb = b2_ceil_div(K, tc::BK);
   // split-K adds partial tiles with red.global: only for a plain linear epilogue
   const bool linear = (d->act == B2_ACT_NONE && d->mul == nullptr && d->add == nullptr && d->ybwd == nullptr &&
-                       d->c_small == nullptr && d->colsum == nullptr);
+                       d->c_small == nullptr && d->c_pre == nullptr && d->colsum == nullptr);
   int best_bn = 32, best_split = 1;
   double best_cost = 1e300;
   const int bn_max = (d->a_small != nullptr) ? 128 : 256;  // 3xTF32 keeps >= 4 accumulator ranges in TMEM
@@ -677,7 +685,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     rc = encode_operand(&p.map_b[s], bs[s], N, K, ldb, d->b_mn_major, best_bn);
     if (rc != B2_OK) return rc;
   }
-  p.c = c; p.c_small = d->c_small; p.ldc = ldc; p.bias = d->bias; p.mul = d->mul; p.add = d->add;
+  p.c = c; p.c_small = d->c_small; p.c_pre = d->c_pre; p.ldc = ldc; p.bias = d->bias; p.mul = d->mul; p.add = d->add;
   p.ybwd = d->ybwd; p.colsum = d->colsum;
   p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.act = d->act;
   p.act_bwd = d->act_bwd;
@@ -759,7 +767,7 @@ extern "C" B2_API int b2_prep_operand(const float* x, const float* y, int act, i
                                       float* colsum, void* stream) {
   B2_REQUIRE(x != nullptr, "NULL input");
   B2_REQUIRE(R >= 0 && C >= 0, "bad shape");
-  B2_REQUIRE(act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad activation code %d", act);
+  B2_REQUIRE((act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID) || act == B2_PREP_MUL, "bad activation code %d", act);
   cudaStream_t st = (cudaStream_t) stream;
   if (colsum != nullptr) {
     cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t) C, st);

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import (B2_F32, B2_F64, B2_I32, B2_I64, B2_POOL_NONE, B2_POOL_SUM, B2_POOL_MEAN,
-                   B2_ACT_NONE, B2_ACT_RELU, B2_ACT_SIGMOID, b2_field)
+                   B2_ACT_NONE, B2_ACT_RELU, B2_ACT_SIGMOID, B2_PREP_MUL, b2_field)
 
 _IDX_CODE = {torch.float64: B2_F64, torch.int64: B2_I64, torch.int32: B2_I32}
 ACT_CODE = {None: B2_ACT_NONE, "none": B2_ACT_NONE, "relu": B2_ACT_RELU, "sigmoid": B2_ACT_SIGMOID}
@@ -399,7 +399,8 @@ def transpose_f32(t, want_small):
 
 
 def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=None, act=B2_ACT_NONE,
-            mul=None, add=None, ybwd=None, act_bwd=B2_ACT_NONE, out_small=None, colsum=None, accumulate=False):
+            mul=None, add=None, ybwd=None, act_bwd=B2_ACT_NONE, out_small=None, colsum=None, accumulate=False,
+            out_pre=None):
     """out (M,N) = epi(sum_k A(m,k) B(n,k)) on the tcgen05 kernel (b2_gemm_tc_ex).  a is (M,K), or (K,M) when
     a_mn (MN-major: the tensor is consumed as it lies, no transpose); b is (N,K), or (K,N) when b_mn.
     a_small / b_small: the operands' 3xTF32 small parts (both or neither).  Epilogue extras: ybwd/act_bwd
@@ -409,7 +410,7 @@ def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=
     K2, N = (b.shape if b_mn else b.shape[::-1])
     if K != K2 or tuple(out.shape) != (M, N) or out.stride(1) != 1 or a.stride(1) != 1 or b.stride(1) != 1:
         raise ValueError("gemm_ex shape mismatch: a%s b%s out%s" % (tuple(a.shape), tuple(b.shape), tuple(out.shape)))
-    for t in (mul, add, ybwd, out_small):
+    for t in (mul, add, ybwd, out_small, out_pre):
         if t is not None and (tuple(t.shape) != (M, N) or t.stride(0) != out.stride(0) or t.stride(1) != 1):
             raise ValueError("gemm_ex: epilogue tensors must share out's shape and leading dimension")
     for t, ref in ((a_small, a), (b_small, b)):
@@ -420,6 +421,7 @@ def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=
     d.b_small = b_small.data_ptr() if b_small is not None else None
     d.c = out.data_ptr()
     d.c_small = out_small.data_ptr() if out_small is not None else None
+    d.c_pre = out_pre.data_ptr() if out_pre is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
     d.mul = mul.data_ptr() if mul is not None else None
     d.add = add.data_ptr() if add is not None else None
@@ -704,6 +706,61 @@ class _MLPChain(torch.autograd.Function):
             if fuse_prev:
                 grads[2 * (i - 1) + 1] = gb_prev
         return (g if ctx.needs_input_grad[0] else None, None) + tuple(grads)
+
+
+class _CrossV2Layer(torch.autograd.Function):
+    """One CrossNetV2 layer, x_next = x_i + x_0 * (x_i W^T + b) (cross_net.py:126-129): the GEMM epilogue
+    applies `add + mul * (acc + bias)` and keeps lin = acc + bias for the backward — no elementwise pass.
+    Backward: dlin = g * x_0 (one pass: value, 3xTF32 small part, bias gradient), dW = dlin^T x_i,
+    dx_i = g + dlin W (epilogue add), dx_0 = g * lin."""
+
+    @staticmethod
+    def forward(ctx, x0, xi, weight, bias):
+        x0, xi = _f32c(x0), _f32c(xi)
+        M, d = xi.shape
+        out = torch.empty_like(xi)
+        lin = torch.empty_like(xi)
+        ctx.tc = (_tc_layer_ok(weight) and weight.shape[0] == weight.shape[1] == d
+                  and xi.data_ptr() % 16 == 0 and x0.data_ptr() % 16 == 0)
+        ctx.xi_small = None
+        if ctx.tc:
+            x3 = _MATMUL["mode"] == "tf32x3"
+            ctx.xi_small = split_tf32(xi) if x3 else None
+            gemm_ex(xi, weight, out, a_small=ctx.xi_small, b_small=weight_small(weight) if x3 else None, bias=bias,
+                    mul=x0, add=xi, out_pre=lin)
+        else:
+            gemm_f32(xi, weight, lin, b_t=True, bias=bias)
+            torch.addcmul(xi, x0, lin, out=out)
+        ctx.save_for_backward(x0, xi, lin, weight)
+        ctx.bias = bias
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x0, xi, lin, weight = ctx.saved_tensors
+        g = _f32c(g)
+        bias = ctx.bias
+        gb = _grad_buffer(bias, zero=False) if (bias is not None and bias.requires_grad) else None
+        x3 = ctx.xi_small is not None
+        dlin, dlin_small, _, _ = prep_operand(g, x0, B2_PREP_MUL, want_out=True, want_small=x3 and ctx.tc, colsum=gb)
+        gxi = torch.empty_like(xi)
+        gw = _grad_buffer(weight, zero=False) if weight.requires_grad else None
+        if ctx.tc:
+            gemm_ex(dlin, weight, gxi, b_mn=True, a_small=dlin_small, b_small=weight_small(weight) if x3 else None,
+                    add=g)                                                                   # dx_i = g + dlin W
+            if gw is not None:
+                gemm_ex(dlin, xi, gw, a_mn=True, b_mn=True, a_small=dlin_small, b_small=ctx.xi_small)
+        else:
+            gemm_f32(dlin, weight, gxi, add=g)
+            if gw is not None:
+                gemm_f32(dlin, xi, gw, a_t=True)
+        gx0 = g * lin if ctx.needs_input_grad[0] else None
+        return gx0, gxi, gw, gb
+
+
+def cross_v2_layer(x0, xi, weight, bias):
+    _require_cuda(x0, xi, weight, bias)
+    return _CrossV2Layer.apply(x0, xi, weight, bias)
 
 
 def mlp_chain_supported():

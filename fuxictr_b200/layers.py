@@ -35,87 +35,85 @@ layers = sys.modules[__name__]  # so feature_encoder strings like "layers.Masked
 
 
 def not_in_whitelist(element, whitelist=[]):
-    """fuxictr/utils.py: whitelist test used by the feature filters."""
+    """fuxictr/utils.py: an empty whitelist admits everything; a scalar whitelist is a 1-list."""
     if not whitelist:
         return False
-    if not isinstance(whitelist, list):
-        whitelist = [whitelist]
-    return element not in whitelist
+    allowed = whitelist if isinstance(whitelist, list) else [whitelist]
+    return element not in allowed
 
 
 def get_initializer(initializer):
-    """torch_utils.py:175-194: initializer strings are evaluated."""
-    if isinstance(initializer, str):
-        try:
-            initializer = eval(initializer)
-        except Exception:
-            raise ValueError("initializer={} is not supported.".format(initializer))
-    return initializer
+    """torch_utils.py:175-194: the YAML carries initializers as Python expressions over `nn` / `partial`."""
+    if not isinstance(initializer, str):
+        return initializer
+    try:
+        return eval(initializer)
+    except Exception:
+        raise ValueError("initializer={} is not supported.".format(initializer))
+
+
+_NAMED_ACTIVATIONS = {
+    "relu": lambda units: nn.ReLU(),
+    "sigmoid": lambda units: nn.Sigmoid(),
+    "tanh": lambda units: nn.Tanh(),
+    "softmax": lambda units: nn.Softmax(dim=-1),
+    "prelu": lambda units: nn.PReLU(units, init=0.1),
+    "dice": lambda units: Dice(units),
+}
 
 
 def get_activation(activation, hidden_units=None):
-    """torch_utils.py:137-173."""
-    if isinstance(activation, str):
-        if activation.lower() in ["prelu", "dice"]:
-            assert type(hidden_units) == int
-        if activation.lower() == "relu":
-            return nn.ReLU()
-        elif activation.lower() == "sigmoid":
-            return nn.Sigmoid()
-        elif activation.lower() == "tanh":
-            return nn.Tanh()
-        elif activation.lower() == "softmax":
-            return nn.Softmax(dim=-1)
-        elif activation.lower() == "prelu":
-            return nn.PReLU(hidden_units, init=0.1)
-        elif activation.lower() == "dice":
-            return Dice(hidden_units)
-        else:
-            return getattr(nn, activation)()
-    elif isinstance(activation, list):
-        if hidden_units is not None:
-            assert len(activation) == len(hidden_units)
-            return [get_activation(act, units) for act, units in zip(activation, hidden_units)]
-        else:
-            return [get_activation(act) for act in activation]
-    return activation
+    """torch_utils.py:137-173: name -> module; a list of names maps element-wise (per-layer widths
+    for the two activations that own parameters); anything else (a module, None) passes through."""
+    if isinstance(activation, list):
+        if hidden_units is None:
+            return [get_activation(a) for a in activation]
+        assert len(activation) == len(hidden_units)
+        return [get_activation(a, u) for a, u in zip(activation, hidden_units)]
+    if not isinstance(activation, str):
+        return activation
+    key = activation.lower()
+    if key in ("prelu", "dice"):
+        assert type(hidden_units) == int
+    make = _NAMED_ACTIVATIONS.get(key)
+    return make(hidden_units) if make is not None else getattr(nn, activation)()
 
 
 # --------------------------------------------------------------------------------------
 # Pooling encoders (fused into the gather when used as a feature_encoder)
 # --------------------------------------------------------------------------------------
 class MaskedAveragePooling(nn.Module):
-    def __init__(self):
-        super(MaskedAveragePooling, self).__init__()
+    """pooling.py:33-49.  As a sequence feature's encoder it is fused into the gather; called directly on
+    a materialised (B, L, D) tensor these are glue ops.  Positions count when their VECTOR is non-zero."""
 
     def forward(self, embedding_matrix, mask=None):
-        # stand-alone use on an already materialised (B, L, D) tensor: glue ops
-        sum_out = torch.sum(embedding_matrix, dim=1)
         if mask is None:
             mask = embedding_matrix.sum(dim=-1) != 0
-        return sum_out / (mask.float().sum(-1, keepdim=True) + 1e-12)
+        count = mask.float().sum(-1, keepdim=True)
+        return embedding_matrix.sum(dim=1) / (count + 1e-12)
 
 
 class MaskedSumPooling(nn.Module):
-    def __init__(self):
-        super(MaskedSumPooling, self).__init__()
+    """pooling.py:62-73."""
 
     def forward(self, embedding_matrix):
-        return torch.sum(embedding_matrix, dim=1)
+        return embedding_matrix.sum(dim=1)
 
 
 # --------------------------------------------------------------------------------------
 # Embeddings
 # --------------------------------------------------------------------------------------
 class FeatureEmbeddingDict(nn.Module):
-    def __init__(self,
-                 feature_map,
-                 embedding_dim,
+    """feature_embedding.py:91-297.  Construction contract (pinned seed-for-seed against the live
+    reference by tests/test_host_logic.py): features are visited in FeatureMap order; a feature's
+    encoder module (if any) is registered BEFORE its table; a `share_embedding` feature aliases the
+    earlier feature's module; LR mode (embedding_dim == 1 without pretrain+sharing) forces width 1
+    and sum-pools sequences; afterwards every owned nn.Embedding is re-initialised (padding row kept)."""
+
+    def __init__(self, feature_map, embedding_dim,
                  embedding_initializer="partial(nn.init.normal_, std=1e-4)",
-                 required_feature_columns=None,
-                 not_required_feature_columns=None,
-                 use_pretrain=True,
-                 use_sharing=True):
+                 required_feature_columns=None, not_required_feature_columns=None,
+                 use_pretrain=True, use_sharing=True):
         super(FeatureEmbeddingDict, self).__init__()
         self._feature_map = feature_map
         self.required_feature_columns = required_feature_columns
@@ -125,101 +123,114 @@ class FeatureEmbeddingDict(nn.Module):
         self.embedding_layers = nn.ModuleDict()
         self.feature_encoders = nn.ModuleDict()
         self._plans = {}
-        for feature, feature_spec in self._feature_map.features.items():
-            if self.is_required(feature):
-                if not (use_pretrain and use_sharing) and embedding_dim == 1:
-                    feat_dim = 1  # in case for LR
-                    if feature_spec["type"] == "sequence":
-                        self.feature_encoders[feature] = MaskedSumPooling()
-                else:
-                    feat_dim = feature_spec.get("embedding_dim", embedding_dim)
-                    if feature_spec.get("feature_encoder", None):
-                        self.feature_encoders[feature] = self.get_feature_encoder(feature_spec["feature_encoder"])
-                    else:
-                        if feature_spec["type"] == "embedding":
-                            pretrain_dim = feature_spec.get("pretrain_dim", feat_dim)
-                            self.feature_encoders[feature] = nn.Linear(pretrain_dim, feat_dim, bias=False)
-
-                if use_sharing and feature_spec.get("share_embedding") in self.embedding_layers:
-                    self.embedding_layers[feature] = self.embedding_layers[feature_spec["share_embedding"]]
-                    continue
-
-                if feature_spec["type"] == "numeric":
-                    self.embedding_layers[feature] = nn.Linear(1, feat_dim, bias=False)
-                elif feature_spec["type"] in ["categorical", "sequence"]:
-                    if use_pretrain and "pretrained_emb" in feature_spec:
-                        raise NotImplementedError(
-                            "feature %s: pretrained_emb is outside the B200 hot path "
-                            "(SURVEY.md section 2 row 2); keep the reference module for it" % feature)
-                    padding_idx = feature_spec.get("padding_idx", None)
-                    self.embedding_layers[feature] = nn.Embedding(feature_spec["vocab_size"],
-                                                                  feat_dim,
-                                                                  padding_idx=padding_idx)
-                elif feature_spec["type"] == "embedding":
-                    self.embedding_layers[feature] = nn.Identity()
+        lr_mode = embedding_dim == 1 and not (use_pretrain and use_sharing)
+        for name, spec in feature_map.features.items():
+            if not self.is_required(name):
+                continue
+            kind = spec["type"]
+            width = 1 if lr_mode else spec.get("embedding_dim", embedding_dim)
+            encoder = self._make_encoder(spec, kind, width, lr_mode)
+            if encoder is not None:
+                self.feature_encoders[name] = encoder
+            donor = spec.get("share_embedding") if use_sharing else None
+            if donor is not None and donor in self.embedding_layers:
+                self.embedding_layers[name] = self.embedding_layers[donor]     # one module, two names
+                continue
+            table = self._make_table(name, spec, kind, width)
+            if table is not None:
+                self.embedding_layers[name] = table
         self.init_weights()
 
+    def _make_encoder(self, spec, kind, width, lr_mode):
+        if lr_mode:
+            return MaskedSumPooling() if kind == "sequence" else None
+        if spec.get("feature_encoder", None):
+            return self.get_feature_encoder(spec["feature_encoder"])
+        if kind == "embedding":     # a dense vector feature is projected to the embedding width
+            return nn.Linear(spec.get("pretrain_dim", width), width, bias=False)
+        return None
+
+    def _make_table(self, name, spec, kind, width):
+        if kind == "numeric":
+            return nn.Linear(1, width, bias=False)
+        if kind == "embedding":
+            return nn.Identity()
+        if kind in ("categorical", "sequence"):
+            if self.use_pretrain and "pretrained_emb" in spec:
+                raise NotImplementedError(
+                    "feature %s: pretrained_emb is outside the B200 hot path "
+                    "(SURVEY.md section 2 row 2); keep the reference module for it" % name)
+            return nn.Embedding(spec["vocab_size"], width, padding_idx=spec.get("padding_idx", None))
+        return None
+
     def get_feature_encoder(self, encoder):
+        """Encoder strings are Python expressions over this module (`layers.MaskedSumPooling()`, `nn.*`)."""
         try:
             if type(encoder) == list:
-                encoder_layer = nn.Sequential(*[eval(enc) for enc in encoder])
-            else:
-                encoder_layer = eval(encoder)
-            return encoder_layer
+                return nn.Sequential(*[eval(expr) for expr in encoder])
+            return eval(encoder)
         except Exception:
             raise ValueError("feature_encoder={} is not supported.".format(encoder))
 
     def init_weights(self):
-        for k, v in self.embedding_layers.items():
-            if "share_embedding" in self._feature_map.features[k]:
+        specs = self._feature_map.features
+        for name, module in self.embedding_layers.items():
+            if "share_embedding" in specs[name] or type(module) != nn.Embedding:
                 continue
-            if type(v) == nn.Embedding:
-                if v.padding_idx is not None:
-                    self.embedding_initializer(v.weight[1:, :])  # set padding_idx to zero
-                else:
-                    self.embedding_initializer(v.weight)
+            # rows 1.. only when a padding row exists (the reference assumes padding_idx == 0)
+            target = module.weight if module.padding_idx is None else module.weight[1:, :]
+            self.embedding_initializer(target)
 
     def is_required(self, feature):
-        feature_spec = self._feature_map.features[feature]
-        if feature_spec["type"] == "meta":
+        if self._feature_map.features[feature]["type"] == "meta":
             return False
-        elif self.required_feature_columns and (feature not in self.required_feature_columns):
+        wanted, unwanted = self.required_feature_columns, self.not_required_feature_columns
+        if wanted and feature not in wanted:
             return False
-        elif self.not_required_feature_columns and (feature in self.not_required_feature_columns):
-            return False
-        else:
-            return True
+        return not (unwanted and feature in unwanted)
 
     def dict2tensor(self, embedding_dict, flatten_emb=False, feature_list=[], feature_source=[],
                     feature_type=[]):
-        feature_emb_list = []
-        for feature, feature_spec in self._feature_map.features.items():
-            if feature_list and not_in_whitelist(feature, feature_list):
+        """FeatureMap order, three optional whitelists; concat on the last dim or stack on dim 1."""
+        picked = []
+        for name, spec in self._feature_map.features.items():
+            if name not in embedding_dict:
                 continue
-            if feature_source and not_in_whitelist(feature_spec["source"], feature_source):
+            if (feature_list and not_in_whitelist(name, feature_list)) or \
+                    (feature_source and not_in_whitelist(spec["source"], feature_source)) or \
+                    (feature_type and not_in_whitelist(spec["type"], feature_type)):
                 continue
-            if feature_type and not_in_whitelist(feature_spec["type"], feature_type):
-                continue
-            if feature in embedding_dict:
-                feature_emb_list.append(embedding_dict[feature])
-        if flatten_emb:
-            feature_emb = torch.cat(feature_emb_list, dim=-1)
-        else:
-            feature_emb = torch.stack(feature_emb_list, dim=1)
-        return feature_emb
+            picked.append(embedding_dict[name])
+        return torch.cat(picked, dim=-1) if flatten_emb else torch.stack(picked, dim=1)
 
     # ---- fused path -------------------------------------------------------------------
     def _active_features(self, inputs, feature_source, feature_type):
-        names = []
-        for feature in inputs.keys():
-            feature_spec = self._feature_map.features[feature]
-            if feature_source and not_in_whitelist(feature_spec["source"], feature_source):
-                continue
-            if feature_type and not_in_whitelist(feature_spec["type"], feature_type):
-                continue
-            if feature in self.embedding_layers:
-                names.append(feature)
-        return names
+        """Input keys (caller's order) that own a table and pass the source / type whitelists."""
+        specs = self._feature_map.features
+
+        def admitted(name):
+            if name not in self.embedding_layers:
+                return False
+            spec = specs[name]
+            return not ((feature_source and not_in_whitelist(spec["source"], feature_source)) or
+                        (feature_type and not_in_whitelist(spec["type"], feature_type)))
+        return [name for name in inputs.keys() if admitted(name)]
+
+    # value transform the reference applies before a feature's table, by feature type
+    # (feature_embedding.py:279-291); only features OUTSIDE the fused kernel go through it
+    _CASTS = {
+        "numeric": lambda t: t.float().view(-1, 1),
+        "categorical": lambda t: t.long(),
+        "sequence": lambda t: t.long(),
+        "embedding": lambda t: t.float(),
+    }
+
+    def _unfused_lookup(self, name, column):
+        kind = self._feature_map.features[name]["type"]
+        if kind not in self._CASTS:
+            raise NotImplementedError
+        out = self.embedding_layers[name](self._CASTS[kind](column))
+        return self.feature_encoders[name](out) if name in self.feature_encoders else out
 
     def _is_fusable(self, feature):
         """Plain nn.Embedding lookup, optionally followed by a Masked{Sum,Average}Pooling."""
@@ -279,24 +290,8 @@ class FeatureEmbeddingDict(nn.Module):
                 if field.seq_len > 1 and field.pool == B2_POOL_NONE:
                     part = part.reshape(B, field.seq_len, field.dim)
                 fused_out[field.name] = part
-        for feature in names:
-            if feature in fused_out:
-                feature_emb_dict[feature] = fused_out[feature]
-                continue
-            # features outside the fused kernel (numeric / embedding-type / custom encoders):
-            # the reference's own per-feature ops (feature_embedding.py:279-295)
-            feature_spec = self._feature_map.features[feature]
-            if feature_spec["type"] == "numeric":
-                embeddings = self.embedding_layers[feature](inputs[feature].float().view(-1, 1))
-            elif feature_spec["type"] in ("categorical", "sequence"):
-                embeddings = self.embedding_layers[feature](inputs[feature].long())
-            elif feature_spec["type"] == "embedding":
-                embeddings = self.embedding_layers[feature](inputs[feature].float())
-            else:
-                raise NotImplementedError
-            if feature in self.feature_encoders:
-                embeddings = self.feature_encoders[feature](embeddings)
-            feature_emb_dict[feature] = embeddings
+        for name in names:      # numeric / embedding-type / custom-encoder features: stock module calls
+            feature_emb_dict[name] = fused_out[name] if name in fused_out else self._unfused_lookup(name, inputs[name])
         return feature_emb_dict
 
     def forward_tensor(self, inputs, feature_source=[], feature_type=[], flatten_emb=False):
@@ -343,22 +338,18 @@ def fused_front(embedding_layer, lr_layer, X, want_fm):
 
 
 class FeatureEmbedding(nn.Module):
-    def __init__(self,
-                 feature_map,
-                 embedding_dim,
-                 embedding_initializer="partial(nn.init.normal_, std=1e-4)",
-                 required_feature_columns=None,
-                 not_required_feature_columns=None,
-                 use_pretrain=True,
+    """feature_embedding.py:30-88: a FeatureEmbeddingDict (child name `embedding_layer`) whose forward
+    returns the stacked / concatenated tensor."""
+
+    def __init__(self, feature_map, embedding_dim, embedding_initializer="partial(nn.init.normal_, std=1e-4)",
+                 required_feature_columns=None, not_required_feature_columns=None, use_pretrain=True,
                  use_sharing=True):
         super(FeatureEmbedding, self).__init__()
-        self.embedding_layer = FeatureEmbeddingDict(feature_map,
-                                                    embedding_dim,
-                                                    embedding_initializer=embedding_initializer,
-                                                    required_feature_columns=required_feature_columns,
-                                                    not_required_feature_columns=not_required_feature_columns,
-                                                    use_pretrain=use_pretrain,
-                                                    use_sharing=use_sharing)
+        self.embedding_layer = FeatureEmbeddingDict(
+            feature_map, embedding_dim, embedding_initializer=embedding_initializer,
+            required_feature_columns=required_feature_columns,
+            not_required_feature_columns=not_required_feature_columns,
+            use_pretrain=use_pretrain, use_sharing=use_sharing)
 
     def forward(self, X, feature_source=[], feature_type=[], flatten_emb=False):
         return self.embedding_layer.forward_tensor(X, feature_source=feature_source,
@@ -369,10 +360,12 @@ class FeatureEmbedding(nn.Module):
 # LR / FM
 # --------------------------------------------------------------------------------------
 class LogisticRegression(nn.Module):
+    """logistic_regression.py:24-59: first-order term = width-1 embedding tables summed over the fields
+    (+ bias).  `bias` is registered before the tables (state_dict / RNG order of the reference)."""
+
     def __init__(self, feature_map, use_bias=True):
         super(LogisticRegression, self).__init__()
         self.bias = nn.Parameter(torch.zeros(1), requires_grad=True) if use_bias else None
-        # A trick for quick one-hot encoding in LR
         self.embedding_layer = FeatureEmbedding(feature_map, 1, use_pretrain=False, use_sharing=False)
         self._lr_plans = {}
 
@@ -394,23 +387,24 @@ class LogisticRegression(nn.Module):
 
 
 class InnerProductInteraction(nn.Module):
-    """ output: product_sum (bs x 1),
-                bi_interaction (bs * dim),
-                inner_product (bs x f^2/2),
-                elementwise_product (bs x f^2/2 x emb_dim)
-    """
+    """inner_product.py:23-70.  output: product_sum (B,1) | bi_interaction (B,D) | inner_product
+    (B, F(F-1)/2) | elementwise_product (B, F(F-1)/2, D).  The pair-selection buffers are frozen
+    Parameters like the reference's (they appear in state_dict)."""
+
+    _OUTPUTS = ("product_sum", "bi_interaction", "inner_product", "elementwise_product")
+
     def __init__(self, num_fields, output="product_sum"):
         super(InnerProductInteraction, self).__init__()
-        self._output_type = output
-        if output not in ["product_sum", "bi_interaction", "inner_product", "elementwise_product"]:
+        if output not in self._OUTPUTS:
             raise ValueError("InnerProductInteraction output={} is not supported.".format(output))
+        self._output_type = output
         if output == "inner_product":
             self.interaction_units = int(num_fields * (num_fields - 1) / 2)
-            self.triu_mask = nn.Parameter(torch.triu(torch.ones(num_fields, num_fields), 1).bool(),
-                                          requires_grad=False)
+            upper = torch.triu(torch.ones(num_fields, num_fields), 1).bool()
+            self.triu_mask = nn.Parameter(upper, requires_grad=False)
         elif output == "elementwise_product":
-            self.triu_index = nn.Parameter(torch.triu_indices(num_fields, num_fields, offset=1),
-                                           requires_grad=False)
+            pairs = torch.triu_indices(num_fields, num_fields, offset=1)
+            self.triu_index = nn.Parameter(pairs, requires_grad=False)
 
     def forward(self, feature_emb):
         if self._output_type == "product_sum":
@@ -426,37 +420,40 @@ class InnerProductInteraction(nn.Module):
 
 
 class FactorizationMachine(nn.Module):
+    """factorization_machine.py:25-59: second-order product_sum + LogisticRegression."""
+
     def __init__(self, feature_map):
         super(FactorizationMachine, self).__init__()
         self.fm_layer = InnerProductInteraction(feature_map.num_fields, output="product_sum")
         self.lr_layer = LogisticRegression(feature_map, use_bias=True)
 
     def forward(self, X, feature_emb):
-        lr_out = self.lr_layer(X)
-        fm_out = self.fm_layer(feature_emb)
-        return fm_out + lr_out
+        return self.fm_layer(feature_emb) + self.lr_layer(X)
 
 
 # --------------------------------------------------------------------------------------
 # Cross networks
 # --------------------------------------------------------------------------------------
 class CrossInteraction(nn.Module):
+    """cross_net.py:24-55: one rank-1 cross layer; parameters `weight` (Linear(d, 1), no bias) and `bias` (d)."""
+
     def __init__(self, input_dim):
         super(CrossInteraction, self).__init__()
         self.weight = nn.Linear(input_dim, 1, bias=False)
         self.bias = nn.Parameter(torch.zeros(input_dim))
 
     def forward(self, X_0, X_i):
-        # stand-alone use (CrossNet fuses all its CrossInteraction layers into one launch)
+        # stand-alone use only: CrossNet runs all of its CrossInteraction layers in one launch
         return F2.linear_act(X_i, self.weight.weight, None, B2_ACT_NONE) * X_0 + self.bias
 
 
 class CrossNet(nn.Module):
+    """cross_net.py:58-92: x_{i+1} = x_i + (w_i . x_i) x_0 + b_i; all layers in one kernel each way."""
+
     def __init__(self, input_dim, num_layers):
         super(CrossNet, self).__init__()
         self.num_layers = num_layers
-        self.cross_net = nn.ModuleList(CrossInteraction(input_dim)
-                                       for _ in range(self.num_layers))
+        self.cross_net = nn.ModuleList([CrossInteraction(input_dim) for _ in range(num_layers)])
 
     def forward(self, X_0):
         if self.num_layers == 0:
@@ -467,18 +464,18 @@ class CrossNet(nn.Module):
 
 
 class CrossNetV2(nn.Module):
+    """cross_net.py:95-129: x_{i+1} = x_i + x_0 * (W_i x_i + b_i); each layer is ONE GEMM whose epilogue
+    applies the cross (add + mul * (acc + bias))."""
+
     def __init__(self, input_dim, num_layers):
         super(CrossNetV2, self).__init__()
         self.num_layers = num_layers
-        self.cross_layers = nn.ModuleList(nn.Linear(input_dim, input_dim)
-                                          for _ in range(self.num_layers))
+        self.cross_layers = nn.ModuleList([nn.Linear(input_dim, input_dim) for _ in range(num_layers)])
 
     def forward(self, X_0):
-        X_i = X_0  # b x dim
-        for i in range(self.num_layers):
-            layer = self.cross_layers[i]
-            lin = F2.linear_act(X_i, layer.weight, layer.bias, B2_ACT_NONE)
-            X_i = X_i + X_0 * lin
+        X_i = X_0
+        for layer in self.cross_layers:
+            X_i = F2.cross_v2_layer(X_0, X_i, layer.weight, layer.bias)
         return X_i
 
 
@@ -486,15 +483,18 @@ class CrossNetV2(nn.Module):
 # CIN
 # --------------------------------------------------------------------------------------
 class CompressedInteractionNet(nn.Module):
+    """compressed_interaction_net.py:23-76.  Layer k is a 1x1 Conv1d over the F * H_{k-1} outer-product
+    channels (H_0 = F); `fc` over the concatenated sum-pooled maps is registered first."""
+
     def __init__(self, num_fields, cin_hidden_units, output_dim=1):
         super(CompressedInteractionNet, self).__init__()
         self.cin_hidden_units = cin_hidden_units
         self.fc = nn.Linear(sum(cin_hidden_units), output_dim)
         self.cin_layer = nn.ModuleDict()
-        for i, unit in enumerate(self.cin_hidden_units):
-            in_channels = num_fields * self.cin_hidden_units[i - 1] if i > 0 else num_fields ** 2
-            out_channels = unit
-            self.cin_layer["layer_" + str(i + 1)] = nn.Conv1d(in_channels, out_channels, kernel_size=1)
+        width_in = num_fields
+        for k, width_out in enumerate(cin_hidden_units, start=1):
+            self.cin_layer["layer_%d" % k] = nn.Conv1d(num_fields * width_in, width_out, kernel_size=1)
+            width_in = width_out
 
     def forward(self, feature_emb):
         return F2.cin_forward(feature_emb,
@@ -506,6 +506,9 @@ class CompressedInteractionNet(nn.Module):
 # Dice / MLP / DIN attention
 # --------------------------------------------------------------------------------------
 class Dice(nn.Module):
+    """activations.py:24-51: p = sigmoid(BN(x)) with a non-affine BatchNorm1d(eps, momentum 0.01);
+    out = p x + alpha (1 - p) x.  Statistics + gate are one kernel each way."""
+
     def __init__(self, input_dim, eps=1e-9):
         super(Dice, self).__init__()
         self.bn = nn.BatchNorm1d(input_dim, affine=False, eps=eps, momentum=0.01)
@@ -516,39 +519,33 @@ class Dice(nn.Module):
 
 
 class MLP_Block(nn.Module):
-    def __init__(self,
-                 input_dim,
-                 hidden_units=[],
-                 hidden_activations="ReLU",
-                 output_dim=None,
-                 output_activation=None,
-                 dropout_rates=0.0,
-                 batch_norm=False,
-                 bn_only_once=False,  # Set True for inference speed up
+    """mlp_block.py:24-96.  `self.mlp` is the reference's Sequential: optional leading BatchNorm1d
+    (`bn_only_once`), then per hidden layer Linear -> [BatchNorm1d] -> [activation] -> [Dropout], then the
+    optional output Linear and output activation — module order fixes state_dict keys and init order."""
+
+    def __init__(self, input_dim, hidden_units=[], hidden_activations="ReLU", output_dim=None,
+                 output_activation=None, dropout_rates=0.0, batch_norm=False, bn_only_once=False,
                  use_bias=True):
         super(MLP_Block, self).__init__()
-        dense_layers = []
-        if not isinstance(dropout_rates, list):
-            dropout_rates = [dropout_rates] * len(hidden_units)
-        if not isinstance(hidden_activations, list):
-            hidden_activations = [hidden_activations] * len(hidden_units)
-        hidden_activations = get_activation(hidden_activations, hidden_units)
-        hidden_units = [input_dim] + hidden_units
-        if batch_norm and bn_only_once:
-            dense_layers.append(nn.BatchNorm1d(input_dim))
-        for idx in range(len(hidden_units) - 1):
-            dense_layers.append(nn.Linear(hidden_units[idx], hidden_units[idx + 1], bias=use_bias))
+        depth = len(hidden_units)
+        rates = dropout_rates if isinstance(dropout_rates, list) else [dropout_rates] * depth
+        names = hidden_activations if isinstance(hidden_activations, list) else [hidden_activations] * depth
+        acts = get_activation(names, hidden_units)
+        widths = [input_dim] + hidden_units
+        stack = [nn.BatchNorm1d(input_dim)] if (batch_norm and bn_only_once) else []
+        for k in range(depth):
+            stack.append(nn.Linear(widths[k], widths[k + 1], bias=use_bias))
             if batch_norm and not bn_only_once:
-                dense_layers.append(nn.BatchNorm1d(hidden_units[idx + 1]))
-            if hidden_activations[idx]:
-                dense_layers.append(hidden_activations[idx])
-            if dropout_rates[idx] > 0:
-                dense_layers.append(nn.Dropout(p=dropout_rates[idx]))
+                stack.append(nn.BatchNorm1d(widths[k + 1]))
+            if acts[k]:
+                stack.append(acts[k])
+            if rates[k] > 0:
+                stack.append(nn.Dropout(p=rates[k]))
         if output_dim is not None:
-            dense_layers.append(nn.Linear(hidden_units[-1], output_dim, bias=use_bias))
+            stack.append(nn.Linear(widths[-1], output_dim, bias=use_bias))
         if output_activation is not None:
-            dense_layers.append(get_activation(output_activation))
-        self.mlp = nn.Sequential(*dense_layers)  # * used to unpack list
+            stack.append(get_activation(output_activation))
+        self.mlp = nn.Sequential(*stack)
 
     def forward(self, inputs):
         mods = list(self.mlp)
@@ -589,26 +586,19 @@ class MLP_Block(nn.Module):
 
 
 class DIN_Attention(nn.Module):
-    def __init__(self,
-                 embedding_dim=64,
-                 attention_units=[32],
-                 hidden_activations="ReLU",
-                 output_activation=None,
-                 dropout_rate=0,
-                 batch_norm=False,
-                 use_softmax=False):
+    """target_attention.py:26-92: scores = MLP([t, h, t-h, t*h]) per history position, masked (optionally
+    softmaxed), weighted sum of the history.  "Dice" builds one Dice per attention layer."""
+
+    def __init__(self, embedding_dim=64, attention_units=[32], hidden_activations="ReLU", output_activation=None,
+                 dropout_rate=0, batch_norm=False, use_softmax=False):
         super(DIN_Attention, self).__init__()
         self.embedding_dim = embedding_dim
         self.use_softmax = use_softmax
         if isinstance(hidden_activations, str) and hidden_activations.lower() == "dice":
-            hidden_activations = [Dice(units) for units in attention_units]
-        self.attention_layer = MLP_Block(input_dim=4 * embedding_dim,
-                                         output_dim=1,
-                                         hidden_units=attention_units,
-                                         hidden_activations=hidden_activations,
-                                         output_activation=output_activation,
-                                         dropout_rates=dropout_rate,
-                                         batch_norm=batch_norm)
+            hidden_activations = [Dice(width) for width in attention_units]
+        self.attention_layer = MLP_Block(input_dim=4 * embedding_dim, output_dim=1, hidden_units=attention_units,
+                                         hidden_activations=hidden_activations, output_activation=output_activation,
+                                         dropout_rates=dropout_rate, batch_norm=batch_norm)
 
     def forward(self, target_item, history_sequence, mask=None):
         return F2.din_attention(self, target_item, history_sequence, mask)

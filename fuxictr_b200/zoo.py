@@ -35,102 +35,103 @@ def _flatten(items):
 
 
 class RankModel(nn.Module):
-    """Device placement, input/label extraction, loss and one optimisation step."""
+    """The slice of BaseModel a training step touches: device placement, input/label extraction, loss,
+    regularisation and one optimisation step (rank_model.py:84-189, 307-323)."""
+
+    _LOSSES = ("bce", "binary_crossentropy", "binary_cross_entropy")
 
     def __init__(self, feature_map, model_id="RankModel", task="binary_classification", gpu=-1,
                  embedding_regularizer=None, net_regularizer=None, **kwargs):
         super(RankModel, self).__init__()
-        self.device = torch.device("cuda:%d" % gpu) if gpu >= 0 and torch.cuda.is_available() \
-            else torch.device("cpu")
-        self.feature_map = feature_map
-        self.model_id = model_id
-        self._embedding_regularizer = embedding_regularizer
-        self._net_regularizer = net_regularizer
+        on_gpu = gpu >= 0 and torch.cuda.is_available()
+        self.device = torch.device("cuda:%d" % gpu if on_gpu else "cpu")
+        self.feature_map, self.model_id = feature_map, model_id
+        self._embedding_regularizer, self._net_regularizer = embedding_regularizer, net_regularizer
         self._max_gradient_norm = 10.0
-        if task == "binary_classification":
-            self.output_activation = nn.Sigmoid()
-        elif task == "regression":
-            self.output_activation = nn.Identity()
-        else:
+        heads = {"binary_classification": nn.Sigmoid, "regression": nn.Identity}
+        if task not in heads:
             raise NotImplementedError("task={} is not supported.".format(task))
+        self.output_activation = heads[task]()
         self._arena = None
         self._fused_optimizer = None
 
-    # -- rank_model.py:84-93 ------------------------------------------------------------
+    def _finish(self, kwargs, learning_rate):
+        """Tail of every reference model constructor: compile (the optimizer is built over the CPU
+        parameters), THEN re-initialise, THEN move — this order fixes RNG consumption and keeps the
+        optimizer's Parameter objects valid (rank_model.py:92, 146-167; DeepFM.py:69-71)."""
+        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
+        self.reset_parameters()
+        self.model_to_device()
+
     def compile(self, optimizer="adam", loss="binary_crossentropy", lr=1e-3):
-        name = "Adam" if str(optimizer).lower() == "adam" else optimizer
         self._lr = lr
-        self._optimizer_name = name
-        self.optimizer = getattr(torch.optim, name)(self.parameters(), lr=lr)
-        if loss not in ("bce", "binary_crossentropy", "binary_cross_entropy"):
+        self._optimizer_name = "Adam" if str(optimizer).lower() == "adam" else optimizer
+        self.optimizer = getattr(torch.optim, self._optimizer_name)(self.parameters(), lr=lr)
+        if loss not in self._LOSSES:
             raise NotImplementedError("loss={} is not supported on the B200 path.".format(loss))
         self.loss_fn = torch.nn.functional.binary_cross_entropy
 
-    # -- rank_model.py:146-167 --------------------------------------------------------------
     def reset_parameters(self):
-        def default_reset(m):
-            if type(m) in [nn.Linear, nn.Conv1d]:
+        """Two passes in module order: xavier-normal weights / zero biases for modules that are EXACTLY
+        nn.Linear or nn.Conv1d, then every module's own `init_weights` (rank_model.py:146-167)."""
+        for m in self.modules():
+            if type(m) in (nn.Linear, nn.Conv1d):
                 nn.init.xavier_normal_(m.weight)
                 if m.bias is not None:
                     m.bias.data.fill_(0)
-
-        def custom_reset(m):
+        for m in self.modules():
             if hasattr(m, "init_weights"):
                 m.init_weights()
-        self.apply(default_reset)
-        self.apply(custom_reset)
 
     def model_to_device(self):
         self.to(device=self.device)
 
-    # -- rank_model.py:169-203 --------------------------------------------------------------
     def get_inputs(self, inputs, feature_source=None):
+        """Every non-label, non-meta column the caller passed (optionally filtered by source), moved to
+        the model's device (rank_model.py:169-189)."""
+        specs, labels = self.feature_map.features, self.feature_map.labels
         X = dict()
-        for feature in inputs.keys():
-            if feature in self.feature_map.labels:
+        for name, column in inputs.items():
+            if name in labels or specs[name]["type"] == "meta":
                 continue
-            spec = self.feature_map.features[feature]
-            if spec["type"] == "meta":
+            if feature_source and not_in_whitelist(specs[name]["source"], feature_source):
                 continue
-            if feature_source and not_in_whitelist(spec["source"], feature_source):
-                continue
-            X[feature] = inputs[feature].to(self.device)
+            X[name] = column.to(self.device)
         return X
 
     def get_labels(self, inputs):
         y = inputs[self.feature_map.labels[0]].to(self.device)
         return y.float().view(-1, 1)
 
-    # -- rank_model.py:95-131 ---------------------------------------------------------------
     def regularization_loss(self):
-        reg = 0
+        """Sum of (lambda / p) * ||param||_p^p: embedding regulariser on the parameters of modules whose
+        type is EXACTLY FeatureEmbeddingDict, net regulariser on everything else (rank_model.py:95-118)."""
         if not (self._embedding_regularizer or self._net_regularizer):
-            return reg
-        emb_reg = _parse_regularizer(self._embedding_regularizer)
-        net_reg = _parse_regularizer(self._net_regularizer)
-        emb_params = set()
-        for m_name, module in self.named_modules():
-            if type(module) == FeatureEmbeddingDict:
-                for p_name, param in module.named_parameters():
-                    if param.requires_grad:
-                        emb_params.add(".".join([m_name, p_name]))
-                        for p, lam in emb_reg:
-                            reg = reg + (lam / p) * torch.norm(param, p) ** p
+            return 0
+        emb_terms = _parse_regularizer(self._embedding_regularizer)
+        net_terms = _parse_regularizer(self._net_regularizer)
+        total, emb_names = 0, set()
+        for mod_name, module in self.named_modules():
+            if type(module) != FeatureEmbeddingDict:
+                continue
+            for p_name, param in module.named_parameters():
+                if param.requires_grad:
+                    emb_names.add(mod_name + "." + p_name)
+                    for p, lam in emb_terms:
+                        total = total + (lam / p) * torch.norm(param, p) ** p
         for name, param in self.named_parameters():
-            if param.requires_grad and name not in emb_params:
-                for p, lam in net_reg:
-                    reg = reg + (lam / p) * torch.norm(param, p) ** p
-        return reg
+            if param.requires_grad and name not in emb_names:
+                for p, lam in net_terms:
+                    total = total + (lam / p) * torch.norm(param, p) ** p
+        return total
 
     def compute_loss(self, return_dict, y_true):
         return self.loss_fn(return_dict["y_pred"], y_true, reduction="mean") + self.regularization_loss()
 
-    # -- rank_model.py:307-323 ---------------------------------------------------------------
     def train_step(self, batch_data):
+        """rank_model.py:307-323 with torch's own optimizer (the parity path of the tests)."""
         self.optimizer.zero_grad()
-        return_dict = self.forward(batch_data)
-        y_true = self.get_labels(batch_data)
-        loss = self.compute_loss(return_dict, y_true)
+        loss = self.compute_loss(self.forward(batch_data), self.get_labels(batch_data))
         loss.backward()
         nn.utils.clip_grad_norm_(self.parameters(), self._max_gradient_norm)
         self.optimizer.step()
@@ -285,22 +286,21 @@ def _parse_regularizer(reg):
 
 
 class DeepFM(RankModel):
+    """model_zoo/DeepFM/DeepFM_torch/src/DeepFM.py:41-88: y = sigmoid(FM(X, E) + MLP(flatten(E)))."""
     _routes_sharded_front = True
 
     def __init__(self, feature_map, model_id="DeepFM", gpu=-1, learning_rate=1e-3, embedding_dim=10,
                  hidden_units=[64, 64, 64], hidden_activations="ReLU", net_dropout=0, batch_norm=False,
                  embedding_regularizer=None, net_regularizer=None, **kwargs):
         super(DeepFM, self).__init__(feature_map, model_id=model_id, gpu=gpu,
-                                     embedding_regularizer=embedding_regularizer,
-                                     net_regularizer=net_regularizer, **kwargs)
+                                     embedding_regularizer=embedding_regularizer, net_regularizer=net_regularizer,
+                                     **kwargs)
         self.embedding_layer = FeatureEmbedding(feature_map, embedding_dim)
         self.fm = FactorizationMachine(feature_map)
-        self.mlp = MLP_Block(input_dim=feature_map.sum_emb_out_dim(), output_dim=1,
-                             hidden_units=hidden_units, hidden_activations=hidden_activations,
-                             output_activation=None, dropout_rates=net_dropout, batch_norm=batch_norm)
-        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
-        self.reset_parameters()
-        self.model_to_device()
+        self.mlp = MLP_Block(feature_map.sum_emb_out_dim(), hidden_units=hidden_units,
+                             hidden_activations=hidden_activations, output_dim=1, output_activation=None,
+                             dropout_rates=net_dropout, batch_norm=batch_norm)
+        self._finish(kwargs, learning_rate)
 
     def forward_logits(self, inputs):
         if getattr(self, "_sharded_front", None) is not None:   # row-sharded tables, P2P push/pull
@@ -327,53 +327,51 @@ class DeepFM(RankModel):
 
 
 class DCNv2(RankModel):
+    """model_zoo/DCNv2/src/DCNv2.py:47-132: CrossNetV2 and DNN towers combined per `model_structure`
+    (crossnet_only | stacked | parallel | stacked_parallel), one Linear to the logit."""
+    _STRUCTURES = ("crossnet_only", "stacked", "parallel", "stacked_parallel")
+
     def __init__(self, feature_map, model_id="DCNv2", gpu=-1, model_structure="parallel",
                  use_low_rank_mixture=False, low_rank=32, num_experts=4, learning_rate=1e-3,
                  embedding_dim=10, stacked_dnn_hidden_units=[], parallel_dnn_hidden_units=[],
                  dnn_activations="ReLU", num_cross_layers=3, net_dropout=0, batch_norm=False,
                  embedding_regularizer=None, net_regularizer=None, **kwargs):
         super(DCNv2, self).__init__(feature_map, model_id=model_id, gpu=gpu,
-                                    embedding_regularizer=embedding_regularizer,
-                                    net_regularizer=net_regularizer, **kwargs)
+                                    embedding_regularizer=embedding_regularizer, net_regularizer=net_regularizer,
+                                    **kwargs)
         if use_low_rank_mixture:
             raise NotImplementedError("CrossNetMix is outside the B200 hot path (SURVEY.md section 2 row 6)")
-        if model_structure not in ["crossnet_only", "stacked", "parallel", "stacked_parallel"]:
+        if model_structure not in self._STRUCTURES:
             raise AssertionError("model_structure={} not supported!".format(model_structure))
         self.model_structure = model_structure
+        has_stacked = model_structure in ("stacked", "stacked_parallel")
+        has_parallel = model_structure in ("parallel", "stacked_parallel")
         self.embedding_layer = FeatureEmbedding(feature_map, embedding_dim)
-        input_dim = feature_map.sum_emb_out_dim()
-        self.crossnet = CrossNetV2(input_dim, num_cross_layers)
-        final_dim = input_dim
-        if model_structure in ["stacked", "stacked_parallel"]:
-            self.stacked_dnn = MLP_Block(input_dim=input_dim, output_dim=None,
-                                         hidden_units=stacked_dnn_hidden_units,
-                                         hidden_activations=dnn_activations, output_activation=None,
-                                         dropout_rates=net_dropout, batch_norm=batch_norm)
-            final_dim = stacked_dnn_hidden_units[-1]
-        if model_structure in ["parallel", "stacked_parallel"]:
-            self.parallel_dnn = MLP_Block(input_dim=input_dim, output_dim=None,
-                                          hidden_units=parallel_dnn_hidden_units,
-                                          hidden_activations=dnn_activations, output_activation=None,
-                                          dropout_rates=net_dropout, batch_norm=batch_norm)
-            final_dim = input_dim + parallel_dnn_hidden_units[-1]
-        if model_structure == "stacked_parallel":
-            final_dim = stacked_dnn_hidden_units[-1] + parallel_dnn_hidden_units[-1]
-        self.fc = nn.Linear(final_dim, 1)
-        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
-        self.reset_parameters()
-        self.model_to_device()
+        width = feature_map.sum_emb_out_dim()
+        self.crossnet = CrossNetV2(width, num_cross_layers)
+
+        def tower(units):
+            return MLP_Block(width, hidden_units=units, hidden_activations=dnn_activations, output_dim=None,
+                             output_activation=None, dropout_rates=net_dropout, batch_norm=batch_norm)
+        left = width                                    # what the cross (or stacked) branch hands to fc
+        if has_stacked:
+            self.stacked_dnn = tower(stacked_dnn_hidden_units)
+            left = stacked_dnn_hidden_units[-1]
+        right = 0
+        if has_parallel:
+            self.parallel_dnn = tower(parallel_dnn_hidden_units)
+            right = parallel_dnn_hidden_units[-1]
+        self.fc = nn.Linear(left + right, 1)
+        self._finish(kwargs, learning_rate)
 
     def _final_out(self, inputs):
-        X = self.get_inputs(inputs)
-        feature_emb = self.embedding_layer(X, flatten_emb=True)
-        cross_out = self.crossnet(feature_emb)
-        if self.model_structure == "crossnet_only":
-            return cross_out
-        if self.model_structure == "stacked":
-            return self.stacked_dnn(cross_out)
-        if self.model_structure == "parallel":
-            return torch.cat([cross_out, self.parallel_dnn(feature_emb)], dim=-1)
-        return torch.cat([self.stacked_dnn(cross_out), self.parallel_dnn(feature_emb)], dim=-1)
+        """DCNv2.py:108-128: what the last Linear sees for each model_structure."""
+        emb = self.embedding_layer(self.get_inputs(inputs), flatten_emb=True)
+        cross = self.crossnet(emb)
+        left = self.stacked_dnn(cross) if hasattr(self, "stacked_dnn") else cross
+        if not hasattr(self, "parallel_dnn"):
+            return left
+        return torch.cat([left, self.parallel_dnn(emb)], dim=-1)
 
     def forward_logits(self, inputs):
         final_out = self._final_out(inputs)
@@ -385,6 +383,9 @@ class DCNv2(RankModel):
 
 
 class DLRM(RankModel):
+    """model_zoo/DLRM/src/DLRM.py:43-123: embeddings of the non-numeric fields (+ a bottom MLP over the
+    numeric ones as one more "field"), pairwise dot (or concat) interaction, top MLP with the output
+    activation inside it."""
     _routes_sharded_front = True
 
     def __init__(self, feature_map, model_id="DLRM", gpu=-1, learning_rate=1e-3, embedding_dim=10,
@@ -393,35 +394,31 @@ class DLRM(RankModel):
                  interaction_op="dot", batch_norm=False, embedding_regularizer=None,
                  net_regularizer=None, **kwargs):
         super(DLRM, self).__init__(feature_map, model_id=model_id, gpu=gpu,
-                                   embedding_regularizer=embedding_regularizer,
-                                   net_regularizer=net_regularizer, **kwargs)
-        self.dense_feats = [f for f, spec in feature_map.features.items() if spec["type"] == "numeric"]
+                                   embedding_regularizer=embedding_regularizer, net_regularizer=net_regularizer,
+                                   **kwargs)
+        self.dense_feats = [name for name, spec in feature_map.features.items() if spec["type"] == "numeric"]
+        has_dense = len(self.dense_feats) > 0
         self.embedding_layer = FeatureEmbedding(feature_map, embedding_dim,
                                                 not_required_feature_columns=self.dense_feats)
-        n_fields = feature_map.num_fields
-        if self.dense_feats:
-            n_fields = feature_map.num_fields - len(self.dense_feats) + 1
-            self.bottom_mlp = MLP_Block(input_dim=len(self.dense_feats), output_dim=embedding_dim,
-                                        hidden_units=bottom_mlp_units,
-                                        hidden_activations=bottom_mlp_activations,
+        n_fields = feature_map.num_fields - len(self.dense_feats) + int(has_dense)
+        if has_dense:
+            self.bottom_mlp = MLP_Block(len(self.dense_feats), hidden_units=bottom_mlp_units,
+                                        hidden_activations=bottom_mlp_activations, output_dim=embedding_dim,
                                         output_activation=bottom_mlp_activations,
                                         dropout_rates=bottom_mlp_dropout, batch_norm=batch_norm)
         self.interaction_op = interaction_op
         if interaction_op == "dot":
             self.interact = InnerProductInteraction(num_fields=n_fields, output="inner_product")
-            top_input_dim = (n_fields * (n_fields - 1)) // 2 + embedding_dim * int(len(self.dense_feats) > 0)
+            top_in = n_fields * (n_fields - 1) // 2 + (embedding_dim if has_dense else 0)
         elif interaction_op == "cat":
             self.interact = nn.Flatten(start_dim=1)
-            top_input_dim = n_fields * embedding_dim
+            top_in = n_fields * embedding_dim
         else:
             raise ValueError("interaction_op={} not supported.".format(interaction_op))
-        self.top_mlp = MLP_Block(input_dim=top_input_dim, output_dim=1, hidden_units=top_mlp_units,
-                                 hidden_activations=top_mlp_activations,
-                                 output_activation=self.output_activation,
+        self.top_mlp = MLP_Block(top_in, hidden_units=top_mlp_units, hidden_activations=top_mlp_activations,
+                                 output_dim=1, output_activation=self.output_activation,
                                  dropout_rates=top_mlp_dropout, batch_norm=batch_norm)
-        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
-        self.reset_parameters()
-        self.model_to_device()
+        self._finish(kwargs, learning_rate)
 
     def forward(self, inputs):
         X = self.get_inputs(inputs)
@@ -430,17 +427,20 @@ class DLRM(RankModel):
             feat_emb, _ = sharded_front(self._sharded_front, self._batch_matrix(inputs))
         else:
             feat_emb = self.embedding_layer(X)
-        if self.dense_feats:
-            dense_x = torch.cat([X[k] for k in self.dense_feats], dim=-1)
-            dense_emb = self.bottom_mlp(dense_x)
+        dense_emb = None
+        if self.dense_feats:        # numeric columns -> bottom MLP -> one more interaction "field" (DLRM.py:114-118)
+            dense_emb = self.bottom_mlp(torch.cat([X[name] for name in self.dense_feats], dim=-1))
             feat_emb = torch.cat([feat_emb, dense_emb.unsqueeze(1)], dim=1)
-        interact_out = self.interact(feat_emb)
-        if self.interaction_op == "dot" and self.dense_feats:
-            interact_out = torch.cat([interact_out, dense_emb], dim=-1)
-        return {"y_pred": self.top_mlp(interact_out)}
+        z = self.interact(feat_emb)
+        if dense_emb is not None and self.interaction_op == "dot":
+            z = torch.cat([z, dense_emb], dim=-1)
+        return {"y_pred": self.top_mlp(z)}
 
 
 class DIN(RankModel):
+    """model_zoo/DIN/src/DIN.py:50-149: one DIN_Attention per (target, sequence) field pair (tuples of
+    fields are concatenated), pooled sequences replace the raw ones, one DNN over all embeddings."""
+
     def __init__(self, feature_map, model_id="DIN", gpu=-1, dnn_hidden_units=[512, 128, 64],
                  dnn_activations="ReLU", attention_hidden_units=[64], attention_hidden_activations="Dice",
                  attention_output_activation=None, attention_dropout=0, learning_rate=1e-3,
@@ -449,70 +449,69 @@ class DIN(RankModel):
                  din_sequence_field=[("click_history", "cate_history")], din_use_softmax=False,
                  embedding_regularizer=None, net_regularizer=None, **kwargs):
         super(DIN, self).__init__(feature_map, model_id=model_id, gpu=gpu,
-                                  embedding_regularizer=embedding_regularizer,
-                                  net_regularizer=net_regularizer, **kwargs)
-        self.din_target_field = din_target_field if isinstance(din_target_field, list) else [din_target_field]
-        self.din_sequence_field = din_sequence_field if isinstance(din_sequence_field, list) \
-            else [din_sequence_field]
+                                  embedding_regularizer=embedding_regularizer, net_regularizer=net_regularizer,
+                                  **kwargs)
+        as_list = lambda v: v if isinstance(v, list) else [v]                   # noqa: E731
+        self.din_target_field, self.din_sequence_field = as_list(din_target_field), as_list(din_sequence_field)
         assert len(self.din_target_field) == len(self.din_sequence_field), \
             "len(din_target_field) != len(din_sequence_field)"
         if isinstance(dnn_activations, str) and dnn_activations.lower() == "dice":
-            dnn_activations = [Dice(units) for units in dnn_hidden_units]
+            dnn_activations = [Dice(width) for width in dnn_hidden_units]
         self.embedding_dim = embedding_dim
         self.embedding_layer = FeatureEmbeddingDict(feature_map, embedding_dim)
-        self.attention_layers = nn.ModuleList(
-            [DIN_Attention(embedding_dim * len(tf) if type(tf) == tuple else embedding_dim,
-                           attention_units=attention_hidden_units,
-                           hidden_activations=attention_hidden_activations,
-                           output_activation=attention_output_activation,
-                           dropout_rate=attention_dropout, use_softmax=din_use_softmax)
-             for tf in self.din_target_field])
-        self.dnn = MLP_Block(input_dim=feature_map.sum_emb_out_dim(), output_dim=1,
-                             hidden_units=dnn_hidden_units, hidden_activations=dnn_activations,
+        heads = []
+        for target in self.din_target_field:
+            parts = len(target) if type(target) == tuple else 1
+            heads.append(DIN_Attention(embedding_dim * parts, attention_units=attention_hidden_units,
+                                       hidden_activations=attention_hidden_activations,
+                                       output_activation=attention_output_activation,
+                                       dropout_rate=attention_dropout, use_softmax=din_use_softmax))
+        self.attention_layers = nn.ModuleList(heads)
+        self.dnn = MLP_Block(feature_map.sum_emb_out_dim(), hidden_units=dnn_hidden_units,
+                             hidden_activations=dnn_activations, output_dim=1,
                              output_activation=self.output_activation, dropout_rates=net_dropout,
                              batch_norm=batch_norm)
-        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
-        self.reset_parameters()
-        self.model_to_device()
+        self._finish(kwargs, learning_rate)
 
     def get_embedding(self, field, feature_emb_dict):
-        if type(field) == tuple:
-            return torch.cat([feature_emb_dict[f] for f in field], dim=-1)
-        return feature_emb_dict[field]
+        """A tuple of fields means their embeddings side by side (DIN.py:144-149)."""
+        names = field if type(field) == tuple else (field,)
+        parts = [feature_emb_dict[name] for name in names]
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
 
     def forward(self, inputs):
+        """DIN.py:109-142: attention-pool every sequence group against its target, write the pooled
+        vectors back under the sequence names, then one DNN over all embeddings in FeatureMap order."""
         X = self.get_inputs(inputs)
-        feature_emb_dict = self.embedding_layer(X)
-        for idx, (target_field, sequence_field) in enumerate(zip(self.din_target_field, self.din_sequence_field)):
-            target_emb = self.get_embedding(target_field, feature_emb_dict)
-            sequence_emb = self.get_embedding(sequence_field, feature_emb_dict)
-            seq_fields = list(_flatten([sequence_field]))
-            mask = X[seq_fields[0]].long() != 0  # padding_idx = 0 required
-            pooling_emb = self.attention_layers[idx](target_emb, sequence_emb, mask)
-            for field, field_emb in zip(seq_fields, pooling_emb.split(self.embedding_dim, dim=-1)):
-                feature_emb_dict[field] = field_emb
-        feature_emb = self.embedding_layer.dict2tensor(feature_emb_dict, flatten_emb=True)
-        return {"y_pred": self.dnn(feature_emb)}
+        emb = self.embedding_layer(X)
+        for head, target, sequence in zip(self.attention_layers, self.din_target_field, self.din_sequence_field):
+            seq_names = list(_flatten([sequence]))
+            valid = X[seq_names[0]].long() != 0            # padding id 0 marks the empty history slots
+            pooled = head(self.get_embedding(target, emb), self.get_embedding(sequence, emb), valid)
+            for name, piece in zip(seq_names, pooled.split(self.embedding_dim, dim=-1)):
+                emb[name] = piece
+        return {"y_pred": self.dnn(self.embedding_layer.dict2tensor(emb, flatten_emb=True))}
 
 
 class xDeepFM(RankModel):
+    """model_zoo/xDeepFM/src/xDeepFM.py:41-97: y = sigmoid(LR(X) + CIN(E) [+ DNN(flatten(E))])."""
+
     def __init__(self, feature_map, model_id="xDeepFM", gpu=-1, learning_rate=1e-3, embedding_dim=10,
                  dnn_hidden_units=[64, 64, 64], dnn_activations="ReLU", cin_hidden_units=[16, 16, 16],
                  net_dropout=0, batch_norm=False, embedding_regularizer=None, net_regularizer=None,
                  **kwargs):
         super(xDeepFM, self).__init__(feature_map, model_id=model_id, gpu=gpu,
-                                      embedding_regularizer=embedding_regularizer,
-                                      net_regularizer=net_regularizer, **kwargs)
+                                      embedding_regularizer=embedding_regularizer, net_regularizer=net_regularizer,
+                                      **kwargs)
         self.embedding_layer = FeatureEmbedding(feature_map, embedding_dim)
-        self.dnn = MLP_Block(input_dim=feature_map.sum_emb_out_dim(), output_dim=1,
-                             hidden_units=dnn_hidden_units, hidden_activations=dnn_activations,
-                             output_activation=None, dropout_rates=net_dropout, batch_norm=batch_norm) \
-            if dnn_hidden_units else None
+        self.dnn = None
+        if dnn_hidden_units:
+            self.dnn = MLP_Block(feature_map.sum_emb_out_dim(), hidden_units=dnn_hidden_units,
+                                 hidden_activations=dnn_activations, output_dim=1, output_activation=None,
+                                 dropout_rates=net_dropout, batch_norm=batch_norm)
         self.lr_layer = LogisticRegression(feature_map, use_bias=False)
         self.cin = CompressedInteractionNet(feature_map.num_fields, cin_hidden_units, output_dim=1)
-        self.compile(kwargs.get("optimizer", "adam"), kwargs.get("loss", "binary_crossentropy"), learning_rate)
-        self.reset_parameters()
-        self.model_to_device()
+        self._finish(kwargs, learning_rate)
 
     def forward_logits(self, inputs):
         X = self.get_inputs(inputs)

@@ -56,6 +56,7 @@ extern "C" {
 #define B2_ACT_NONE 0
 #define B2_ACT_RELU 1
 #define B2_ACT_SIGMOID 2
+#define B2_PREP_MUL 3 /* b2_prep_operand only: v = x * y (plain elementwise product, CrossNetV2 backward) */
 
 #define B2_MAX_FIELDS 128
 
@@ -370,7 +371,8 @@ B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, int64_t ldb, 
  * This covers the three contractions of nn.Linear (mlp_block.py:74, autograd of F.linear) on the
  * tensors as they lie in memory:  Y = X W^T (both K-major);  dX = dZ W (B = W MN-major);
  * dW = dZ^T X (A = dZ and B = X MN-major).
- * Epilogue, in this order:  v = acc + bias[n];  v = add + mul * v;  v = act(v);
+ * Epilogue, in this order:  v = acc + bias[n];  c_pre = v (optional: CrossNetV2 keeps W x_i + b for its
+ * backward);  v = add + mul * v;  v = act(v);
  *   v = act_bwd'(ybwd[m,n]) * v   (ybwd = the activation OUTPUT whose backward is fused: the dgrad
  *                                  GEMM of layer i+1 emits dZ_i directly; threshold_backward /
  *                                  sigmoid_backward of the reference's autograd);
@@ -386,6 +388,7 @@ typedef struct b2_gemm_desc {
   const float* b_small;
   float* c;
   float* c_small;
+  float* c_pre;
   const float* bias;
   const float* mul;
   const float* add;
@@ -407,7 +410,8 @@ B2_API int b2_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t
 
 /*
  * One-pass operand preparation for the K-major tensor-core GEMMs over x (R, C):
- *   v = act'(y) * x when y != NULL (y = activation OUTPUT; fuses the activation backward)
+ *   v = act'(y) * x when y != NULL (y = activation OUTPUT; fuses the activation backward);
+ *   act == B2_PREP_MUL: v = x * y
  *   out (R,C) = v, out_small = 3xTF32 small part, outT (C,R) = v^T, outT_small, colsum[c] = sum_r v[r,c]
  * Every output may be NULL.  Replaces b2_act_bwd + b2_transpose_f32 + b2_split_tf32 + b2_colsum.
  */

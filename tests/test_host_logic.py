@@ -127,3 +127,69 @@ def test_batch_views_alias_the_matrix_for_sequences_too():
     mat.mul_(-1)
     assert torch.equal(views["hist"], mat[:, 1:5]) and views["hist"].stride() == (7, 1)
     assert not torch.equal(copies["hist"], mat[:, 1:5])        # the collator-style entry is a copy
+
+
+# ---------------------------------------------------------------------------------------------
+# Mirror constructors vs the LIVE reference (baseline/_ref): same seed => bit-identical state_dict
+# (keys, shapes, registration order, RNG consumption order), over more configurations than the goldens.
+# ---------------------------------------------------------------------------------------------
+_SEQ_SPECS = [
+    ("user", {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 30}),
+    ("item_id", {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 50}),
+    ("cate_id", {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 12, "embedding_dim": 8}),
+    ("price", {"type": "numeric", "source": ""}),
+    ("click_history", {"type": "sequence", "source": "", "padding_idx": 0, "vocab_size": 50, "max_len": 6,
+                       "share_embedding": "item_id"}),
+    ("cate_history", {"type": "sequence", "source": "", "padding_idx": 0, "vocab_size": 12, "max_len": 6,
+                      "share_embedding": "cate_id", "embedding_dim": 8}),
+    ("tags", {"type": "sequence", "source": "", "padding_idx": 0, "vocab_size": 20, "max_len": 4,
+              "feature_encoder": "layers.MaskedAveragePooling()"}),
+]
+_CAT_SPECS = [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": 11 + 3 * i})
+              for i in range(5)]
+_MIRROR_CASES = [
+    ("DeepFM", _CAT_SPECS, dict(embedding_dim=4, hidden_units=[12, 8], hidden_activations="relu", net_dropout=0.1,
+                                batch_norm=True)),
+    ("DeepFM", _SEQ_SPECS[:3] + _SEQ_SPECS[6:], dict(embedding_dim=8, hidden_units=[6], hidden_activations=["PReLU"])),
+    ("DCNv2", _CAT_SPECS, dict(embedding_dim=4, model_structure="stacked_parallel", num_cross_layers=2,
+                               stacked_dnn_hidden_units=[10], parallel_dnn_hidden_units=[7, 5], dnn_activations="relu")),
+    ("DCNv2", _CAT_SPECS, dict(embedding_dim=4, model_structure="crossnet_only", num_cross_layers=1)),
+    ("DLRM", _CAT_SPECS, dict(embedding_dim=4, top_mlp_units=[9, 5], interaction_op="cat")),
+    ("DLRM", _CAT_SPECS + [("price", {"type": "numeric", "source": ""})],
+     dict(embedding_dim=4, top_mlp_units=[9], bottom_mlp_units=[6, 5], interaction_op="dot")),
+    ("xDeepFM", _CAT_SPECS, dict(embedding_dim=4, dnn_hidden_units=[], cin_hidden_units=[3])),
+    ("xDeepFM", _CAT_SPECS, dict(embedding_dim=4, dnn_hidden_units=[8, 4], cin_hidden_units=[4, 3, 2], batch_norm=True)),
+    ("DIN", _SEQ_SPECS[:3] + _SEQ_SPECS[4:6], dict(embedding_dim=8, dnn_hidden_units=[10, 6], dnn_activations="Dice",
+                                                   attention_hidden_units=[7, 5], attention_hidden_activations="Dice",
+                                                   din_use_softmax=True, attention_dropout=0.2)),
+    ("DIN", _SEQ_SPECS[:3] + _SEQ_SPECS[4:6], dict(embedding_dim=8, dnn_hidden_units=[10], dnn_activations="relu",
+                                                   attention_hidden_units=[7], attention_hidden_activations="ReLU",
+                                                   attention_output_activation="Sigmoid", batch_norm=True)),
+]
+
+
+@pytest.mark.parametrize("name,specs,kwargs", _MIRROR_CASES, ids=["%s-%d" % (c[0], i) for i, c in enumerate(_MIRROR_CASES)])
+def test_mirror_constructors_match_the_live_reference_seed_for_seed(name, specs, kwargs):
+    from baseline import refenv
+    if not refenv.available():
+        pytest.skip(refenv.why_unavailable())
+    refenv.import_reference()
+    ref_cls = refenv.load_model_class(name)
+    emb_dim = kwargs["embedding_dim"]
+    torch.manual_seed(4242)
+    ref = ref_cls(refenv.synthetic_feature_map(specs, embedding_dim=emb_dim), model_root="/tmp/b2_mirror/",
+                  metrics=["AUC"], verbose=0, gpu=-1, optimizer="adam", loss="binary_crossentropy", **kwargs)
+    torch.manual_seed(4242)
+    ours = getattr(zoo, name)(FeatureMap.from_specs(specs, embedding_dim=emb_dim), gpu=-1, **kwargs)
+    sd_ref, sd = ref.state_dict(), ours.state_dict()
+    assert list(sd.keys()) == list(sd_ref.keys())
+    for k, v in sd_ref.items():
+        assert sd[k].dtype == v.dtype and sd[k].shape == v.shape, k
+        assert torch.equal(sd[k], v), k
+    # module tree: same names, and the same torch module type wherever the reference uses a stock one
+    ref_mods = dict(ref.named_modules())
+    for mname, mod in ours.named_modules():
+        assert mname in ref_mods, mname
+        if type(ref_mods[mname]).__module__.startswith("torch."):
+            assert type(mod) is type(ref_mods[mname]), mname
+    assert set(ref_mods) == set(dict(ours.named_modules()))
