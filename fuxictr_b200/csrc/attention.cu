@@ -299,3 +299,85 @@ extern "C" B2_API int b2_din_wsum_bwd(const float* w, const unsigned char* mask,
   B2_CUDA_LAUNCH_CHECK("b2_din_wsum_bwd");
   return B2_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// DIN attention, use_softmax = True (target_attention.py:85-90):
+//   s = w * mask;  s = s + (-1e9) * (1 - mask);  p = softmax_L(s)
+// One warp per (sample) row of L scores: masked scale, row max, exp, row sum — in registers.
+// Backward: ds = p * (g - sum_l g p);  dw = ds * mask   (the additive fill has no gradient).
+// ---------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+din_softmax_fwd_kernel(const float* __restrict__ w, const unsigned char* __restrict__ mask, int64_t B, int L,
+                       float* __restrict__ p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < B; b += nwarps) {
+    float mx = -INFINITY;
+    for (int l = lane; l < L; l += 32) {
+      float s = __ldg(w + b * L + l);
+      if (mask != nullptr) {
+        const float m = (float) mask[b * L + l];
+        s = s * m + (-1.e9f) * (1.f - m);
+      }
+      mx = fmaxf(mx, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      float s = __ldg(w + b * L + l);
+      if (mask != nullptr) {
+        const float m = (float) mask[b * L + l];
+        s = s * m + (-1.e9f) * (1.f - m);
+      }
+      const float e = expf(s - mx);
+      p[b * L + l] = e;
+      sum += e;
+    }
+    sum = b2_warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int l = lane; l < L; l += 32) p[b * L + l] *= inv;   // each lane re-reads only its own writes
+  }
+}
+
+__global__ void __launch_bounds__(256)
+din_softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g,
+                       const unsigned char* __restrict__ mask, int64_t B, int L, float* __restrict__ gw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < B; b += nwarps) {
+    float dot = 0.f;
+    for (int l = lane; l < L; l += 32) dot = fmaf(__ldg(g + b * L + l), __ldg(p + b * L + l), dot);
+    dot = b2_warp_sum(dot);
+    for (int l = lane; l < L; l += 32) {
+      float ds = __ldg(p + b * L + l) * (__ldg(g + b * L + l) - dot);
+      if (mask != nullptr) ds *= (float) mask[b * L + l];
+      gw[b * L + l] = ds;
+    }
+  }
+}
+}  // namespace
+
+extern "C" B2_API int b2_din_softmax_fwd(const float* w, const unsigned char* mask, int64_t B, int L, float* p,
+                                         void* stream) {
+  B2_REQUIRE(w && p && L >= 1, "bad argument");
+  if (B <= 0) return B2_OK;
+  int64_t blocks = b2_ceil_div(B * 32, 256);
+  if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
+  din_softmax_fwd_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(w, mask, B, L, p);
+  B2_CUDA_LAUNCH_CHECK("b2_din_softmax_fwd");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_din_softmax_bwd(const float* p, const float* g, const unsigned char* mask, int64_t B,
+                                         int L, float* gw, void* stream) {
+  B2_REQUIRE(p && g && gw && L >= 1, "bad argument");
+  if (B <= 0) return B2_OK;
+  int64_t blocks = b2_ceil_div(B * 32, 256);
+  if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
+  din_softmax_bwd_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(p, g, mask, B, L, gw);
+  B2_CUDA_LAUNCH_CHECK("b2_din_softmax_bwd");
+  return B2_OK;
+}

@@ -988,9 +988,31 @@ class _DinWeightedSum(torch.autograd.Function):
         return gw, None, gh
 
 
+class _DinSoftmax(torch.autograd.Function):
+    """p = softmax_L(w * mask + (-1e9)(1 - mask))  (target_attention.py:85-90), one launch each way."""
+
+    @staticmethod
+    def forward(ctx, w, mask_u8):
+        w = _f32c(w)
+        B, L = w.shape
+        p = torch.empty_like(w)
+        _lib.call("b2_din_softmax_fwd", _ptr(w), _ptr(mask_u8), B, L, _ptr(p), _stream())
+        ctx.save_for_backward(p)
+        ctx.mask = mask_u8
+        return p
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        B, L = p.shape
+        gw = torch.empty_like(p)
+        _lib.call("b2_din_softmax_bwd", _ptr(p), _ptr(_f32c(g)), _ptr(ctx.mask), B, L, _ptr(gw), _stream())
+        return gw, None
+
+
 def din_attention(module, target_item, history_sequence, mask=None):
-    """DIN_Attention.forward (target_attention.py:79-92): input construction, mask and weighted sum
-    are single launches; the attention MLP runs on the b2 GEMM + Dice kernels."""
+    """DIN_Attention.forward (target_attention.py:79-92): input construction, mask (+ softmax) and
+    weighted sum are single launches; the attention MLP runs on the b2 GEMM + Dice kernels."""
     _require_cuda(target_item, history_sequence)
     B, L, d = history_sequence.shape
     att_in = _DinInput.apply(target_item, history_sequence)
@@ -998,13 +1020,8 @@ def din_attention(module, target_item, history_sequence, mask=None):
     mask_u8 = None
     if mask is not None:
         mask_u8 = mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
-    if module.use_softmax:
-        # softmax variant (:87-90): mask, additive -1e9 fill and softmax stay stock ops
-        if mask is not None:
-            mf = mask.float()
-            weight = weight * mf
-            weight = weight + -1.e9 * (1 - mf)
-        weight = weight.softmax(dim=-1)
+    if module.use_softmax:      # softmax variant (:87-90): mask, additive -1e9 fill and softmax in one kernel
+        weight = _DinSoftmax.apply(weight, mask_u8)
         mask_u8 = None
     return _DinWeightedSum.apply(weight, mask_u8, history_sequence)
 

@@ -324,6 +324,12 @@ B2_API int b2_din_wsum_fwd(const float* w, const unsigned char* mask, const floa
                            int d, float* out, void* stream);
 B2_API int b2_din_wsum_bwd(const float* w, const unsigned char* mask, const float* hist, const float* gout,
                            int64_t B, int L, int d, float* gw, float* ghist, void* stream);
+/* use_softmax = True branch of DIN_Attention (target_attention.py:85-90), one launch each way:
+ *   p = softmax_L( w * mask + (-1e9) * (1 - mask) )   (mask (B,L) uint8 or NULL)
+ *   bwd: gw = p * (g - sum_l g p) * mask */
+B2_API int b2_din_softmax_fwd(const float* w, const unsigned char* mask, int64_t B, int L, float* p, void* stream);
+B2_API int b2_din_softmax_bwd(const float* p, const float* g, const unsigned char* mask, int64_t B, int L,
+                              float* gw, void* stream);
 
 /*
  * Dense layer with fused epilogue; the GEMM behind MLP_Block
