@@ -35,7 +35,13 @@ NF, VOCAB, DIM, HIDDEN, BATCH = 39, 25641, 16, [300, 300, 300], 4096
 DLRM_VOCABS = [19_000_000] * 10 + [625_000] * 16
 DLRM_TOP, DLRM_GLOBAL_BATCH = [64, 64, 64], 65536
 METRICS = {"deepfm": "samples/sec DeepFM Criteo-shape train_step (fwd+bwd+clip+Adam)",
-           "dlrm": "samples/sec DLRM Criteo-1TB-shape train_step (fwd+bwd+clip+Adam), row-sharded tables"}
+           "dlrm": "samples/sec DLRM Criteo-1TB-shape train_step (fwd+bwd+clip+Adam), row-sharded tables",
+           "dcnv2": "samples/sec DCNv2 Criteo-shape train_step (fwd+bwd+clip+Adam)",
+           "din": "samples/sec DIN Taobao-shape train_step (fwd+bwd+clip+Adam)",
+           "xdeepfm": "samples/sec xDeepFM Criteo-shape train_step (fwd+bwd+clip+Adam)"}
+# per-GPU batch of each BASELINE config: C2, C5 (global 65,536), C3, C4, xDeepFM at the C2 shape
+DEFAULT_BATCH = {"deepfm": BATCH, "dcnv2": 8192, "din": 2048, "xdeepfm": 4096}
+DCN_HIDDEN, DIN_HIDDEN, XDFM_HIDDEN, XDFM_CIN, SEQ_LEN = [500, 500, 500], [500, 500, 500], [400, 400, 400], [16, 16, 16], 50
 
 
 def parse():
@@ -44,7 +50,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
-    ap.add_argument("--workload", default="deepfm", choices=["deepfm", "dlrm"])
+    ap.add_argument("--workload", default="deepfm", choices=["deepfm", "dlrm", "dcnv2", "din", "xdeepfm"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (deepfm: 4096; dlrm: 65536 / gpus)")
     ap.add_argument("--vocab-scale", type=float, default=1.0, help="dlrm: scale every cardinality (smoke runs)")
     ap.add_argument("--graph", type=int, default=1, help="capture the step in a CUDA graph")
@@ -60,56 +66,94 @@ def parse():
                     help="arithmetic of the dense GEMMs: fp32 FFMA, 3xTF32 (fp32-class) or 1xTF32 on tcgen05")
     a = ap.parse_args()
     if a.batch <= 0:
-        a.batch = BATCH if a.workload == "deepfm" else max(DLRM_GLOBAL_BATCH // max(a.gpus, 1), 1)
+        a.batch = DEFAULT_BATCH[a.workload] if a.workload != "dlrm" else max(DLRM_GLOBAL_BATCH // max(a.gpus, 1), 1)
+    if a.gpus > 1 and a.workload not in ("deepfm", "dlrm"):
+        raise SystemExit("--workload %s is a single-GPU line (row-sharding is implemented for deepfm and dlrm)" % a.workload)
     return a
 
 
 # ------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------
-def vocabs(args):
-    if args.workload == "deepfm":
-        return [VOCAB] * NF
-    return [max(int(v * args.vocab_scale), 16) for v in DLRM_VOCABS]
+def _cat(name, vocab):
+    return (name, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": vocab})
 
 
 def make_specs(args=None):
-    vs = [VOCAB] * NF if args is None else vocabs(args)
-    return [("C%d" % i, {"type": "categorical", "source": "", "padding_idx": 0, "vocab_size": v})
-            for i, v in enumerate(vs)]
+    """Synthetic FeatureMap of the workload."""
+    w = "deepfm" if args is None else args.workload
+    if w in ("deepfm", "dcnv2", "xdeepfm"):
+        return [_cat("C%d" % i, VOCAB) for i in range(NF)]
+    if w == "dlrm":
+        return [_cat("C%d" % i, max(int(v * args.vocab_scale), 16)) for i, v in enumerate(DLRM_VOCABS)]
+    # C4: Taobao-shape DIN: item / category targets, 23 profile fields, two histories sharing the target tables
+    specs = [_cat("item_id", 400000), _cat("cate_id", 10000)] + [_cat("f%d" % i, 20000) for i in range(23)]
+    for name, donor, vocab in (("click_history", "item_id", 400000), ("cate_history", "cate_id", 10000)):
+        specs.append((name, {"type": "sequence", "source": "", "padding_idx": 0, "vocab_size": vocab, "max_len": SEQ_LEN,
+                             "share_embedding": donor, "feature_encoder": None}))
+    return specs
+
+
+def vocabs(args):
+    return [sp["vocab_size"] for _, sp in make_specs(args)]
+
+
+def table_rows(args):
+    """Rows of parameter memory: shared tables count once."""
+    return sum(sp["vocab_size"] for _, sp in make_specs(args) if "share_embedding" not in sp)
 
 
 def workload_config(args, n_gpus):
-    vs = vocabs(args)
-    if args.workload == "deepfm":
+    specs = make_specs(args)
+    rows = table_rows(args)
+    w = args.workload
+    if w == "deepfm":
         name = ("DeepFM Criteo-shape: %d fields x %d rows, emb_dim %d, MLP %s, fp32 Adam" % (NF, VOCAB, DIM, HIDDEN))
-        par = ("single" if n_gpus == 1 else
-               ("dp%d (replicated tables, all-reduce of the gradient arena)" % n_gpus if args.dp_only else
-                "tables row-sharded over %d GPUs (P2P push/pull over NVLink) + dense dp all-reduce" % n_gpus))
-    else:
+    elif w == "dlrm":
         name = ("DLRM Criteo-1TB-shape: %d sparse fields, %.1f M rows total, emb_dim %d, dot interaction, top MLP %s, "
-                "dense fp32 Adam over every row" % (len(vs), sum(vs) / 1e6, DIM, DLRM_TOP))
-        par = ("single GPU holds all tables" if n_gpus == 1 else
-               "tables row-sharded over %d GPUs (P2P push/pull over NVLink) + dense dp all-reduce" % n_gpus)
-    arena_mb = sum(vs) * (DIM + (1 if args.workload == "deepfm" else 0)) * 4 / 1e6 / (1 if n_gpus == 1 or args.dp_only else n_gpus)
+                "dense fp32 Adam over every row" % (len(specs), rows / 1e6, DIM, DLRM_TOP))
+    elif w == "dcnv2":
+        name = ("DCNv2 Criteo-shape: %d fields x %d rows, emb_dim %d, 3 CrossNetV2 layers (624x624) parallel to DNN %s"
+                % (NF, VOCAB, DIM, DCN_HIDDEN))
+    elif w == "din":
+        name = ("DIN Taobao-shape: 27 fields (25 categorical + 2 histories of length %d sharing the target tables), "
+                "emb_dim %d, attention MLP [64] Dice, DNN %s" % (SEQ_LEN, DIM, DIN_HIDDEN))
+    else:
+        name = ("xDeepFM Criteo-shape: %d fields x %d rows, emb_dim %d, CIN %s, DNN %s" % (NF, VOCAB, DIM, XDFM_CIN, XDFM_HIDDEN))
+    if n_gpus == 1:
+        par = "single GPU holds all tables"
+    elif args.dp_only:
+        par = "dp%d (replicated tables, all-reduce of the gradient arena)" % n_gpus
+    else:
+        par = "tables row-sharded over %d GPUs (P2P push/pull over NVLink) + dense dp all-reduce" % n_gpus
+    width = DIM + (1 if w in ("deepfm", "xdeepfm") else 0)          # + the D=1 LogisticRegression tables
+    arena_mb = rows * width * 4 / 1e6 / (1 if n_gpus == 1 or args.dp_only else n_gpus)
     return {"workload": name, "global_batch": args.batch * n_gpus, "per_gpu_batch": args.batch, "parallelism": par,
             "cache": "working set (4 fp32 arenas x %.0f MB per GPU: params, grads, Adam m/v) exceeds the 126 MB L2; "
                      "%d distinct index batches are rotated" % (arena_mb, args.nbatches)}
 
 
-def make_batches(n, batch, seed=0, vs=None):
-    """uniform ids in [1, V), Bernoulli(0.25) labels, one (B, F+1) float64 matrix
-    per batch — exactly what the reference's BatchCollator hands to the model."""
+def make_batches(n, batch, seed=0, specs=None):
+    """uniform ids in [1, V), sequences post-padded with 0 to a random length in [1, L],
+    Bernoulli(0.25) labels, one (B, input_length + 1) float64 matrix per batch — exactly what the
+    reference's BatchCollator hands to the model."""
     import torch
-    vs = [VOCAB] * NF if vs is None else vs
+    specs = make_specs() if specs is None else specs
     gen = torch.Generator().manual_seed(seed)
-    hi = torch.tensor(vs, dtype=torch.float64)
     out = []
     for _ in range(n):
-        u = torch.rand(batch, len(vs), generator=gen, dtype=torch.float64)
-        ids = (1 + torch.floor(u * (hi - 1))).clamp_(max=hi - 1)          # uniform in [1, V_f)
-        label = (torch.rand(batch, 1, generator=gen) < 0.25).double()
-        out.append(torch.cat([ids, label], dim=1))
+        cols = []
+        for _, sp in specs:
+            v = float(sp["vocab_size"])
+            width = sp.get("max_len", 1) if sp["type"] == "sequence" else 1
+            u = torch.rand(batch, width, generator=gen, dtype=torch.float64)
+            ids = (1 + torch.floor(u * (v - 1))).clamp_(max=v - 1)          # uniform in [1, V)
+            if width > 1:
+                lens = torch.randint(1, width + 1, (batch, 1), generator=gen)
+                ids = ids * (torch.arange(width).view(1, -1) < lens)
+            cols.append(ids)
+        cols.append((torch.rand(batch, 1, generator=gen) < 0.25).double())
+        out.append(torch.cat(cols, dim=1))
     return out
 
 
@@ -190,15 +234,27 @@ def build_reference_model(args, gpu):
                   loss="binary_crossentropy", task="binary_classification", gpu=gpu, learning_rate=1e-3,
                   embedding_dim=DIM, embedding_regularizer=0, net_regularizer=0, net_dropout=0, batch_norm=False)
     R.torch_utils.seed_everything(seed=2019)
-    if args.workload == "deepfm":
-        cls = refenv.load_model_class("DeepFM")
-        model = cls(fm, model_id="DeepFM_bench", hidden_units=HIDDEN, hidden_activations="relu", **common)
-    else:
-        cls = refenv.load_model_class("DLRM")
+    w = args.workload
+    if w == "deepfm":
+        model = refenv.load_model_class("DeepFM")(fm, model_id="DeepFM_bench", hidden_units=HIDDEN,
+                                                  hidden_activations="relu", **common)
+    elif w == "dlrm":
         common.pop("net_dropout")
-        model = cls(fm, model_id="DLRM_bench", top_mlp_units=DLRM_TOP, bottom_mlp_units=[64, 64, 64],
-                    top_mlp_activations="ReLU", bottom_mlp_activations="ReLU", top_mlp_dropout=0,
-                    bottom_mlp_dropout=0, interaction_op="dot", **common)
+        model = refenv.load_model_class("DLRM")(fm, model_id="DLRM_bench", top_mlp_units=DLRM_TOP,
+                                                bottom_mlp_units=[64, 64, 64], top_mlp_activations="ReLU",
+                                                bottom_mlp_activations="ReLU", top_mlp_dropout=0, bottom_mlp_dropout=0,
+                                                interaction_op="dot", **common)
+    elif w == "dcnv2":
+        model = refenv.load_model_class("DCNv2")(fm, model_id="DCNv2_bench", model_structure="parallel",
+                                                 num_cross_layers=3, parallel_dnn_hidden_units=DCN_HIDDEN,
+                                                 dnn_activations="ReLU", **common)
+    elif w == "din":
+        model = refenv.load_model_class("DIN")(fm, model_id="DIN_bench", dnn_hidden_units=DIN_HIDDEN,
+                                               dnn_activations="ReLU", attention_hidden_units=[64],
+                                               attention_hidden_activations="Dice", attention_dropout=0, **common)
+    else:
+        model = refenv.load_model_class("xDeepFM")(fm, model_id="xDeepFM_bench", dnn_hidden_units=XDFM_HIDDEN,
+                                                   dnn_activations="ReLU", cin_hidden_units=XDFM_CIN, **common)
     model._max_gradient_norm = 10.0          # BaseModel.fit() sets it (rank_model.py:213); train_step reads it
     model.train()
     return model, fm, torch
@@ -207,7 +263,7 @@ def build_reference_model(args, gpu):
 def reference_batches(fm, mats):
     """What BatchCollator.__call__ yields (npz_dataloader.py:111-125): column views of one matrix."""
     cols = list(fm.features.keys()) + list(fm.labels)
-    return [{c: m[:, fm.get_column_index(c)] for c in cols} for m in mats]
+    return [{c: m[:, fm.get_column_index(c)] for c in cols} for m in mats]     # list index => (B, L) copy, as the collator
 
 
 def cpu_reference_run(args, steps, warmup, seconds=None, threads=None):
@@ -218,7 +274,7 @@ def cpu_reference_run(args, steps, warmup, seconds=None, threads=None):
     try:
         model, fm, torch = build_reference_model(args, -1)
         step = model.train_step
-        batches = reference_batches(fm, make_batches(4, batch, vs=vocabs(args)))
+        batches = reference_batches(fm, make_batches(4, batch, specs=make_specs(args)))
         kind = "reference"
     except ImportError:       # no baseline/_ref on this machine: the oracle restatement (same ATen ops)
         import torch
@@ -298,7 +354,7 @@ def reference_gpu_eager(args, steps=30, warmup=5):
     from fuxictr_b200 import patch
     patch.disable()
     model, fm, torch = build_reference_model(args, 0)
-    batches = reference_batches(fm, [m.pin_memory() for m in make_batches(8, args.batch, vs=vocabs(args))])
+    batches = reference_batches(fm, [m.pin_memory() for m in make_batches(8, args.batch, specs=make_specs(args))])
     out = {}
     for sync in (True, False):
         for i in range(warmup):
@@ -414,12 +470,14 @@ def kernel_rooflines(model, fm, dev_batch, peaks, args, with_gather=True):
     hbm = peaks["hbm_gbs"]
     X = OrderedDict((k, v) for k, v in fm.batch_dict(dev_batch).items() if k != "label")
     B = dev_batch.shape[0]
-    nf = len(X)
-    fed = model.embedding_layer.embedding_layer
+    nf = fm.num_fields
+    fed = model.embedding_layer
+    fed = getattr(fed, "embedding_layer", fed)          # DIN holds the FeatureEmbeddingDict directly
     if with_gather:
         with torch.no_grad():
-            ms = time_kernel(lambda: fed.forward_tensor(X), 50, None)
-        gbytes = B * (nf * 8 + 2 * nf * DIM * 4)   # F*8 (ids) + F*D*4 (rows) + F*D*4 (out) per sample
+            ms = time_kernel(lambda: fed.forward(X), 50, None)
+        slots = sum(sp.get("max_len", 1) if sp["type"] == "sequence" else 1 for sp in fm.features.values())
+        gbytes = B * (slots * 8 + 2 * slots * DIM * 4)   # per slot 8 (id) + D*4 (row) + D*4 (out)
         out["embed_gather_fwd"] = {"ms": ms, "algorithmic_bytes": gbytes, "GBps": gbytes / ms / 1e6,
                                    "frac_of_measured_hbm": gbytes / ms / 1e6 / hbm,
                                    "note": "B=%d, uniform ids; the launch is latency-bound at this size" % B}
@@ -447,10 +505,10 @@ def kernel_rooflines(model, fm, dev_batch, peaks, args, with_gather=True):
     if mode != "fp32":
         x3 = mode == "tf32x3"
         tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0       # dense TF32 = half the measured bf16 rate
-        widths = [nf * DIM] + (HIDDEN if args.workload == "deepfm" else DLRM_TOP)
-        if args.workload == "dlrm":
-            widths[0] = nf * (nf - 1) // 2
-        K_, N_ = widths[0], widths[1]
+        # the largest dense contraction of the workload: (in, out) widths of that Linear
+        K_, N_ = {"deepfm": (nf * DIM, HIDDEN[0]), "dlrm": (DLRM_TOP[0], DLRM_TOP[1]),
+                  "dcnv2": (nf * DIM, nf * DIM), "din": (fm.sum_emb_out_dim(), DIN_HIDDEN[0]),
+                  "xdeepfm": (nf * DIM, XDFM_HIDDEN[0])}[args.workload]
         x = torch.randn(B, K_, device="cuda"); w = torch.randn(N_, K_, device="cuda"); dz = torch.randn(B, N_, device="cuda")
         sm = (lambda t: F2.split_tf32(t) if x3 else None)
         xs, ws, dzs = sm(x), sm(w), sm(dz)
@@ -519,22 +577,30 @@ def build_model(args, local, world):
     from fuxictr_b200 import zoo
     from fuxictr_b200.schema import FeatureMap
     fm = FeatureMap.from_specs(make_specs(args), embedding_dim=DIM)
-    nf = len(fm.features)
 
     def construct():
         torch.manual_seed(2019)
         # parameters are created directly in HBM: a 200 M-row table set is 12.8 GB, too much to stage
         # through host memory once per rank
         with torch.device("cuda:%d" % local):
-            if args.workload == "deepfm":
+            w = args.workload
+            if w == "deepfm":
                 return zoo.DeepFM(fm, gpu=local, embedding_dim=DIM, hidden_units=HIDDEN)
-            return zoo.DLRM(fm, gpu=local, embedding_dim=DIM, top_mlp_units=DLRM_TOP, interaction_op="dot")
+            if w == "dlrm":
+                return zoo.DLRM(fm, gpu=local, embedding_dim=DIM, top_mlp_units=DLRM_TOP, interaction_op="dot")
+            if w == "dcnv2":
+                return zoo.DCNv2(fm, gpu=local, embedding_dim=DIM, model_structure="parallel", num_cross_layers=3,
+                                 parallel_dnn_hidden_units=DCN_HIDDEN)
+            if w == "din":
+                return zoo.DIN(fm, gpu=local, embedding_dim=DIM, dnn_hidden_units=DIN_HIDDEN, attention_hidden_units=[64],
+                               attention_hidden_activations="Dice")
+            return zoo.xDeepFM(fm, gpu=local, embedding_dim=DIM, dnn_hidden_units=XDFM_HIDDEN, cin_hidden_units=XDFM_CIN)
     model = construct()
     sharded = world > 1 and not args.dp_only
     if sharded:
         try:
             from fuxictr_b200.sharded import SymmPeerGroup
-            model.enable_sharding(SymmPeerGroup(), args.batch, nf + 1, torch.float64,
+            model.enable_sharding(SymmPeerGroup(), args.batch, fm.input_length + 1, torch.float64,
                                   want_fm=(args.workload == "deepfm"))
             torch.cuda.empty_cache()
         except Exception as exc:   # no peer-mapped memory on this box: replicated tables + arena all-reduce
@@ -576,14 +642,13 @@ def run_b200_arm(args):
             sys.stderr.flush()
 
     model, fm, sharded = build_model(args, local, world)
-    nf = len(fm.features)
-    vs = vocabs(args)
+    width = fm.input_length + 1
     note("model built")
-    host_batches = [m.pin_memory() for m in make_batches(args.nbatches, args.batch, seed=1000 + rank, vs=vs)]
+    host_batches = [m.pin_memory() for m in make_batches(args.nbatches, args.batch, seed=1000 + rank, specs=make_specs(args))]
     dev_batches = [m.cuda(non_blocking=True) for m in host_batches]
     # launches per step (our kernels only): counted by wrapping the C-ABI call around one eager step
     from fuxictr_b200.pipeline import TrainPipeline
-    pipe = TrainPipeline(model, args.batch, nf + 1, torch.float64, graph=False)
+    pipe = TrainPipeline(model, args.batch, width, torch.float64, graph=False)
     pipe.prime(dev_batches[0])
     counter = {"n": 0}
     orig_call = _lib.call
@@ -735,7 +800,7 @@ def run_b200_arm(args):
             line["reference_gpu_eager"] = reference_gpu_eager(args)
         except Exception as exc:
             line["reference_gpu_eager"] = {"unavailable": repr(exc)}
-    if world == 1 and not args.no_cpu_baseline and args.workload == "deepfm":
+    if world == 1 and not args.no_cpu_baseline and args.workload != "dlrm":
         r = cpu_reference_run(args, 0, 3, seconds=args.cpu_seconds)
         line["cpu_baseline"] = cpu_baseline_entry(r, args, "in %.0f s" % args.cpu_seconds)
     print(json.dumps(line))
