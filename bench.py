@@ -62,8 +62,9 @@ def parse():
     ap.add_argument("--lazy-adam", type=int, default=0,
                     help="1: evaluate the dense Adam semantics of the tables row-wise and lazily (bit-identical)")
     ap.add_argument("--steps-only", action="store_true", help="skip the per-kernel / stress / CPU legs (profiling)")
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
-                    help="arithmetic of the dense GEMMs: fp32 FFMA, 3xTF32 (fp32-class) or 1xTF32 on tcgen05")
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32", "bf16"],
+                    help="arithmetic of the dense GEMMs: fp32 FFMA, 3xTF32 (fp32-class, the parity mode), 1xTF32, or "
+                         "bf16 operands with fp32 accumulation (BASELINE configs[1]) on tcgen05")
     a = ap.parse_args()
     if a.batch <= 0:
         a.batch = DEFAULT_BATCH[a.workload] if a.workload != "dlrm" else max(DLRM_GLOBAL_BATCH // max(a.gpus, 1), 1)
@@ -504,14 +505,14 @@ def kernel_rooflines(model, fm, dev_batch, peaks, args, with_gather=True):
     mode = F2.get_matmul_precision()
     if mode != "fp32":
         x3 = mode == "tf32x3"
-        tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0       # dense TF32 = half the measured bf16 rate
+        # dense TF32 = half the measured bf16 rate; bf16 operands are measured against the bf16 rate itself
+        tf32_peak = peaks.get("bf16_tflops", 1590.0) / (1.0 if mode == "bf16" else 2.0)
         # the largest dense contraction of the workload: (in, out) widths of that Linear
         K_, N_ = {"deepfm": (nf * DIM, HIDDEN[0]), "dlrm": (DLRM_TOP[0], DLRM_TOP[1]),
                   "dcnv2": (nf * DIM, nf * DIM), "din": (fm.sum_emb_out_dim(), DIN_HIDDEN[0]),
                   "xdeepfm": (nf * DIM, XDFM_HIDDEN[0])}[args.workload]
         x = torch.randn(B, K_, device="cuda"); w = torch.randn(N_, K_, device="cuda"); dz = torch.randn(B, N_, device="cuda")
-        sm = (lambda t: F2.split_tf32(t) if x3 else None)
-        xs, ws, dzs = sm(x), sm(w), sm(dz)
+        xs, ws, dzs = F2.make_aux(x), F2.make_aux(w), F2.make_aux(dz)
         y, dx, dw = torch.empty(B, N_, device="cuda"), torch.empty(B, K_, device="cuda"), torch.empty(N_, K_, device="cuda")
         cases = {
             "gemm_fwd  Y=X.W^T": (lambda: F2.gemm_ex(x, w, y, a_small=xs, b_small=ws), (B, N_, K_)),
@@ -777,7 +778,8 @@ def run_b200_arm(args):
             "scaling": "weak" if args.workload == "deepfm" else "strong",
             "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core GEMMs, fp32 everything else)",
-                      "tf32": "tf32 GEMMs, f32 elsewhere"}[args.precision],
+                      "tf32": "tf32 GEMMs, f32 elsewhere",
+                      "bf16": "bf16 GEMM operands (fp32 accumulation in TMEM), f32 tables / optimizer"}[args.precision],
             "data": "synthetic", "config": dict(workload_config(args, world), matmul=args.precision,
                                              adam=("dense semantics, lazy row-wise evaluation" if args.lazy_adam and world == 1
                                                    else "dense pass over the arena")),

@@ -61,7 +61,7 @@ class b2_gemm_desc(ctypes.Structure):
         ("ybwd", c_void_p), ("colsum", c_void_p),
         ("lda", c_int64), ("ldb", c_int64), ("ldc", c_int64), ("M", c_int64), ("N", c_int64), ("K", c_int64),
         ("a_mn_major", c_int32), ("b_mn_major", c_int32), ("act", c_int32), ("act_bwd", c_int32),
-        ("beta_accumulate", c_int32), ("reserved_", c_int32),
+        ("beta_accumulate", c_int32), ("elem_dtype", c_int32), ("ld_aux", c_int64),
     ]
 
 # name -> (restype, argtypes); every symbol the header declares must appear here
@@ -123,6 +123,7 @@ SIGNATURES = {
     "b2_gemm_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                            c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_gemm_tc_ex": (c_int, [c_void_p, c_void_p]),
+    "b2_to_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "b2_split_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "b2_transpose_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "b2_prep_operand": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,

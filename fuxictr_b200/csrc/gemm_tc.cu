@@ -29,7 +29,7 @@
 
 namespace tc {
 constexpr int BM = 128;          // UMMA M (cta_group::1): TMEM lane == output row
-constexpr int BK = 32;           // fp32 elements per k-block == one 128-byte swizzle row
+constexpr int BK = 32;           // fp32 elements per k-block == one 128-byte swizzle row (bf16: 64)
 constexpr int UMMA_K_BYTES = 32; // kind::tf32: K = 8 elements of 4 bytes per instruction
 constexpr int MAX_STAGES = 4;  // 4 stages of (A,B) for one pass; 3 stages of (A,As,B,Bs) for 3xTF32
 constexpr int A_BYTES = BM * 128;
@@ -49,6 +49,8 @@ struct Params {
   float* colsum;          // optional (N): += column sums of C (bias gradient)
   int M, N, K, bn, nseg, act, act_bwd, beta, kb_per_split;
   int a_mn, b_mn;         // operand is MN-major (memory (K, rows))
+  int esz;                // operand element bytes: 4 = fp32 read as tf32 (kind::tf32), 2 = bf16 (kind::f16)
+  int64_t ld_aux;         // leading dimension of c_small (fp32 small part, or the bf16 copy of C when esz == 2)
   int nmain;      // TMEM accumulators for the main (big x big) product: its K range is cut in nmain chunks
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
 };
@@ -116,10 +118,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
 }
 // MN-major, 128-byte swizzle: the tile is a row of [32 MN-elements x BK k-rows] boxes (what one TMA
 // box writes: k-row r at r * 128 B, 8-row groups 1024 B apart = SBO), boxes BK * 128 B apart = LBO.
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t box_bytes) {
   uint64_t d = 0;
   d |= (uint64_t) ((addr & 0x3FFFFu) >> 4);      // start address  [0,14)
-  d |= (uint64_t) ((BK * 128) >> 4) << 16;       // leading byte offset [16,30): next 32-element MN block
+  d |= (uint64_t) (box_bytes >> 4) << 16;        // leading byte offset [16,30): next 128-byte-wide MN block
   d |= (uint64_t) (1024 >> 4) << 32;             // stride byte offset [32,46): next 8 k-rows
   d |= (uint64_t) 1 << 46;                       // descriptor version (sm_100)
   d |= (uint64_t) 2 << 61;                       // layout: SWIZZLE_128B
@@ -142,6 +144,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -183,7 +195,10 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.bn;
-  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int bke = 128 / p.esz;                      // k elements per k-block: one 128-byte swizzle row
+  const int mnb = 128 / p.esz;                      // MN elements per MN-major box (128 bytes wide)
+  const uint32_t box_bytes = (uint32_t) bke * 128u; // one MN-major box: bke k-rows x 128 B
+  const int num_kb_total = (p.K + bke - 1) / bke;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
   // a short last K split may hold fewer k-blocks than accumulation chains
@@ -229,14 +244,14 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         for (int s = 0; s < (x3 ? 2 : 1); ++s) {
           const uint32_t a_t = a_dst + (s ? off_as : 0u), b_t = a_dst + (s ? off_bs : off_b);
           if (!p.a_mn) {
-            tma_load_2d(a_t, &p.map_a[s], full, kb * BK, m0);
+            tma_load_2d(a_t, &p.map_a[s], full, kb * bke, m0);
           } else {
-            for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_t + j * (BK * 128), &p.map_a[s], full, m0 + 32 * j, kb * BK);
+            for (int j = 0; j < BM / mnb; ++j) tma_load_2d(a_t + j * box_bytes, &p.map_a[s], full, m0 + mnb * j, kb * bke);
           }
           if (!p.b_mn) {
-            tma_load_2d(b_t, &p.map_b[s], full, kb * BK, n0);
+            tma_load_2d(b_t, &p.map_b[s], full, kb * bke, n0);
           } else {
-            for (int j = 0; j < p.bn / 32; ++j) tma_load_2d(b_t + j * (BK * 128), &p.map_b[s], full, n0 + 32 * j, kb * BK);
+            for (int j = 0; j < p.bn / mnb; ++j) tma_load_2d(b_t + j * box_bytes, &p.map_b[s], full, n0 + mnb * j, kb * bke);
           }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -246,13 +261,15 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     // ---------------- MMA issuer (one thread) ----------------
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (p.a_mn ? 1 : 0) << 15) |
+      const uint32_t fmt = (p.esz == 2) ? 1u : 2u;   // operand format: kind::f16 1 = BF16; kind::tf32 2 = TF32
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.a_mn ? 1 : 0) << 15) |
                              ((uint32_t) (p.b_mn ? 1 : 0) << 16) | ((uint32_t) (p.bn >> 3) << 17) |
                              ((uint32_t) (BM >> 4) << 24);
-      // one instruction consumes 8 k-elements: 32 bytes along a K-major swizzle row (+2 in the
-      // (addr >> 4) field) or one 8-row group of an MN-major tile (+1024 B)
-      const uint64_t a_kstep = p.a_mn ? (uint64_t) (1024 >> 4) : (uint64_t) (UMMA_K_BYTES >> 4);
-      const uint64_t b_kstep = p.b_mn ? (uint64_t) (1024 >> 4) : (uint64_t) (UMMA_K_BYTES >> 4);
+      // one instruction consumes 32 bytes of K per row (8 tf32 / 16 bf16 elements): 32 bytes along a
+      // K-major swizzle row (+2 in the (addr >> 4) field), or 8 / 16 k-rows of an MN-major tile
+      const uint32_t mn_step = (p.esz == 2) ? 2048u : 1024u;
+      const uint64_t a_kstep = p.a_mn ? (uint64_t) (mn_step >> 4) : (uint64_t) (UMMA_K_BYTES >> 4);
+      const uint64_t b_kstep = p.b_mn ? (uint64_t) (mn_step >> 4) : (uint64_t) (UMMA_K_BYTES >> 4);
       // The tensor core adds each instruction's 8 products into the fp32 accumulator with
       // truncation, so rounding error grows with the length of one accumulation chain and with
       // the magnitude of the accumulator.  For 3xTF32 the K range of the main product is
@@ -269,10 +286,15 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         const uint32_t d_main = tmem_base + (uint32_t) (slot * p.bn);
         const uint32_t d_corr = tmem_base + (uint32_t) (nmain * p.bn);
         const uint32_t a_addr = smem_base + stage * stage_bytes;
-        const uint64_t adesc = p.a_mn ? make_smem_desc_mn(a_addr) : make_smem_desc(a_addr);
-        const uint64_t bdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_b) : make_smem_desc(a_addr + off_b);
-        const uint64_t asdesc = p.a_mn ? make_smem_desc_mn(a_addr + off_as) : make_smem_desc(a_addr + off_as);
-        const uint64_t bsdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_bs) : make_smem_desc(a_addr + off_bs);
+        const uint64_t adesc = p.a_mn ? make_smem_desc_mn(a_addr, box_bytes) : make_smem_desc(a_addr);
+        const uint64_t bdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_b, box_bytes) : make_smem_desc(a_addr + off_b);
+        const uint64_t asdesc = p.a_mn ? make_smem_desc_mn(a_addr + off_as, box_bytes) : make_smem_desc(a_addr + off_as);
+        const uint64_t bsdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_bs, box_bytes) : make_smem_desc(a_addr + off_bs);
+        if (p.esz == 2) {       // bf16 operands: one pass on kind::f16, fp32 accumulation in TMEM
+#pragma unroll
+          for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
+            umma_bf16(d_main, adesc + (uint64_t) k * a_kstep, bdesc + (uint64_t) k * b_kstep, idesc, (!first || k > 0) ? 1u : 0u);
+        } else {
 #pragma unroll
         for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
           const uint64_t ka = (uint64_t) k * a_kstep, kb_ = (uint64_t) k * b_kstep;
@@ -281,6 +303,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
             umma_tf32(d_corr, adesc + ka, bsdesc + kb_, idesc, (i > 0 || k > 0) ? 1u : 0u);   // A_big . B_small
             umma_tf32(d_corr, asdesc + ka, bdesc + kb_, idesc, 1u);                            // A_small . B_big
           }
+        }
         }
         umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -374,11 +397,16 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 #pragma unroll
           for (int r = 0; r < 32; ++r)
             if (mrow0 + r < p.M) cp[(int64_t) r * p.ldc] = t[r];   // 128 contiguous bytes per row
-          if (p.c_small != nullptr) {   // the consumer's 3xTF32 small part, produced where C is produced
-            float* sp = p.c_small + (int64_t) mrow0 * p.ldc + n;
+          if (p.c_small != nullptr && p.esz == 4) {   // the consumer's 3xTF32 small part, produced where C is produced
+            float* sp = p.c_small + (int64_t) mrow0 * p.ld_aux + n;
 #pragma unroll
             for (int r = 0; r < 32; ++r)
-              if (mrow0 + r < p.M) sp[(int64_t) r * p.ldc] = tf32_small(t[r]);
+              if (mrow0 + r < p.M) sp[(int64_t) r * p.ld_aux] = tf32_small(t[r]);
+          } else if (p.c_small != nullptr) {          // bf16 mode: the consumer's bf16 operand (round-to-nearest-even)
+            __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.c_small) + (int64_t) mrow0 * p.ld_aux + n;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (mrow0 + r < p.M) sp[(int64_t) r * p.ld_aux] = __float2bfloat16_rn(t[r]);
           }
           if (p.colsum != nullptr) {    // bias gradient: this lane owns column n of 32 rows
             float cs = 0.f;
@@ -605,31 +633,33 @@ static b2_encode_tiled_fn b2_get_encode() {
   return fn;
 }
 
-// K-major operand: memory (rows, K), K contiguous, leading dimension ld; box = 32 k (128 B) x box_rows.
-// MN-major operand: memory (K, rows), rows contiguous, leading dimension ld; box = 32 rows (128 B) x BK k.
-static int encode_operand(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld,
-                          int mn_major, int box_rows) {
+// K-major operand: memory (rows, K), K contiguous, leading dimension ld; box = 128 B of k x box_rows rows.
+// MN-major operand: memory (K, rows), rows contiguous, leading dimension ld; box = 128 B of rows x (128/esz) k.
+static int encode_operand(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld,
+                          int mn_major, int box_rows, int esz) {
   b2_encode_tiled_fn enc = b2_get_encode();
   if (enc == nullptr) return b2_fail(B2_E_CUDA, "cuTensorMapEncodeTiled is unavailable in this driver");
-  cuuint64_t dims[2], strides[1] = {(cuuint64_t) ld * 4};
+  const cuuint32_t per128 = (cuuint32_t) (128 / esz);
+  cuuint64_t dims[2], strides[1] = {(cuuint64_t) ld * (cuuint64_t) esz};
   cuuint32_t box[2], estr[2] = {1, 1};
   if (!mn_major) {
     dims[0] = (cuuint64_t) K; dims[1] = (cuuint64_t) rows;
-    box[0] = (cuuint32_t) tc::BK; box[1] = (cuuint32_t) box_rows;
+    box[0] = per128; box[1] = (cuuint32_t) box_rows;
   } else {
     dims[0] = (cuuint64_t) rows; dims[1] = (cuuint64_t) K;
-    box[0] = 32; box[1] = (cuuint32_t) tc::BK;
+    box[0] = per128; box[1] = per128;
   }
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return b2_fail(B2_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
   return B2_OK;
 }
 
-static bool tma_ok(const float* p, int64_t ld) {
-  return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0);
+static bool tma_ok_e(const void* p, int64_t ld, int esz) {
+  return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && ((ld * esz) % 16 == 0);
 }
+static bool tma_ok(const float* p, int64_t ld) { return tma_ok_e(p, ld, 4); }
 
 extern "C" B2_API int b2_gemm_tc_supported(const float* a, int64_t lda, const float* b, int64_t ldb,
                                            int64_t M, int64_t N, int64_t K) {
@@ -639,31 +669,39 @@ extern "C" B2_API int b2_gemm_tc_supported(const float* a, int64_t lda, const fl
 
 extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   B2_REQUIRE(d != nullptr, "NULL descriptor");
-  const float* a = d->a; const float* b = d->b; float* c = d->c;
+  const void* a = d->a; const void* b = d->b; float* c = d->c;
   const int64_t M = d->M, N = d->N, K = d->K, lda = d->lda, ldb = d->ldb, ldc = d->ldc;
   B2_REQUIRE(a && b && c, "NULL operand");
+  B2_REQUIRE(d->elem_dtype == B2_F32 || d->elem_dtype == B2_BF16, "operand dtype must be B2_F32 or B2_BF16");
+  const int esz = (d->elem_dtype == B2_BF16) ? 2 : 4;
   B2_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N, "bad shape");
+  B2_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "shape exceeds 31 bits");
   B2_REQUIRE(lda >= (d->a_mn_major ? M : K) && ldb >= (d->b_mn_major ? N : K), "leading dimension too small");
   B2_REQUIRE(d->act >= B2_ACT_NONE && d->act <= B2_ACT_SIGMOID, "bad activation code %d", d->act);
   B2_REQUIRE(d->act_bwd >= B2_ACT_NONE && d->act_bwd <= B2_ACT_SIGMOID, "bad act_bwd code %d", d->act_bwd);
   B2_REQUIRE(d->act_bwd == B2_ACT_NONE || d->ybwd != nullptr, "act_bwd needs ybwd");
   B2_REQUIRE((d->a_small == nullptr) == (d->b_small == nullptr), "3xTF32 needs both small operands");
-  if (!b2_gemm_tc_supported(a, lda, b, ldb, M, N, K) ||
+  B2_REQUIRE(esz == 4 || d->a_small == nullptr, "bf16 operands are single-pass (no small parts)");
+  const int64_t ld_aux = d->ld_aux > 0 ? d->ld_aux : ldc;
+  B2_REQUIRE(d->c_small == nullptr || ld_aux >= N, "ld_aux too small");
+  if (!tma_ok_e(a, lda, esz) || !tma_ok_e(b, ldb, esz) ||
       (d->a_small != nullptr && !(tma_ok(d->a_small, lda) && tma_ok(d->b_small, ldb))))
-    return b2_fail(B2_E_UNSUPPORTED, "operands are not TMA-addressable (16-byte base, ld %% 4 == 0)");
+    return b2_fail(B2_E_UNSUPPORTED, "operands are not TMA-addressable (16-byte base, 16-byte row pitch)");
   cudaStream_t st = (cudaStream_t) stream;
 
   // Tile-shape choice: BN in {32..256 step 32}; the kernel is bound by L2->SM operand traffic,
   // so minimise waves x per-CTA operand bytes, where one wave = 148 CTAs (one per SM).
+  const int bke = 128 / esz;
   const int64_t tiles_m = b2_ceil_div(M, tc::BM);
-  const int64_t num_kb = b2_ceil_div(K, tc::BK);
+  const int64_t num_kb = b2_ceil_div(K, bke);
   // split-K adds partial tiles with red.global: only for a plain linear epilogue
   const bool linear = (d->act == B2_ACT_NONE && d->mul == nullptr && d->add == nullptr && d->ybwd == nullptr &&
                        d->c_small == nullptr && d->c_pre == nullptr && d->colsum == nullptr);
-  int best_bn = 32, best_split = 1;
+  int best_bn = 0, best_split = 1;
   double best_cost = 1e300;
   const int bn_max = (d->a_small != nullptr) ? 128 : 256;  // 3xTF32 keeps >= 4 accumulator ranges in TMEM
-  for (int bn = 32; bn <= bn_max; bn += 32) {
+  const int bn_step = (d->b_mn_major && esz == 2) ? 64 : 32;   // an MN-major box is 128 bytes of rows
+  for (int bn = bn_step; bn <= bn_max; bn += bn_step) {
     const int64_t tiles_n = b2_ceil_div(N, bn);
     for (int split = 1; split <= 32; split *= 2) {
       if (split > 1 && (!linear || num_kb / split < 8)) break;
@@ -677,18 +715,19 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   }
   tc::Params p;
   const int nseg = (d->a_small != nullptr) ? 3 : 1;
-  const float* as[2] = {a, d->a_small};
-  const float* bs[2] = {b, d->b_small};
+  const void* as[2] = {a, d->a_small};
+  const void* bs[2] = {b, d->b_small};
   for (int s = 0; s < (nseg > 1 ? 2 : 1); ++s) {
-    int rc = encode_operand(&p.map_a[s], as[s], M, K, lda, d->a_mn_major, tc::BM);
+    int rc = encode_operand(&p.map_a[s], as[s], M, K, lda, d->a_mn_major, tc::BM, esz);
     if (rc != B2_OK) return rc;
-    rc = encode_operand(&p.map_b[s], bs[s], N, K, ldb, d->b_mn_major, best_bn);
+    rc = encode_operand(&p.map_b[s], bs[s], N, K, ldb, d->b_mn_major, best_bn, esz);
     if (rc != B2_OK) return rc;
   }
-  p.c = c; p.c_small = d->c_small; p.c_pre = d->c_pre; p.ldc = ldc; p.bias = d->bias; p.mul = d->mul; p.add = d->add;
+  p.c = c; p.c_small = reinterpret_cast<float*>(d->c_small); p.c_pre = d->c_pre; p.ldc = ldc; p.ld_aux = ld_aux;
+  p.bias = d->bias; p.mul = d->mul; p.add = d->add;
   p.ybwd = d->ybwd; p.colsum = d->colsum;
   p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.act = d->act;
-  p.act_bwd = d->act_bwd;
+  p.act_bwd = d->act_bwd; p.esz = esz;
   p.a_mn = d->a_mn_major ? 1 : 0; p.b_mn = d->b_mn_major ? 1 : 0;
   p.beta = d->beta_accumulate ? 1 : 0;
   p.kb_per_split = (int) b2_ceil_div(num_kb, best_split);
@@ -724,6 +763,32 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   B2_REQUIRE(grid.y <= 65535, "N too large for this launch geometry");
   tc::gemm_tf32_kernel<<<grid, tc::NTHREADS, smem, st>>>(p);
   B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
+  return B2_OK;
+}
+
+// fp32 (rows, cols; ld_in) -> bf16 (rows, cols; ld_out), round-to-nearest-even: the bf16-mode operand of a
+// tensor whose producer is not one of our epilogues (weights once per step, the first layer's input).
+namespace tc {
+__global__ void __launch_bounds__(256)
+to_bf16_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
+               __nv_bfloat16* __restrict__ out, int64_t ld_out) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    out[r * ld_out + c] = __float2bfloat16_rn(__ldg(x + r * ld_in + c));
+  }
+}
+}  // namespace tc
+
+extern "C" B2_API int b2_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_in, void* out,
+                                 int64_t ld_out, void* stream) {
+  B2_REQUIRE(x && out && rows >= 0 && cols >= 0 && ld_in >= cols && ld_out >= cols, "bad argument");
+  if (rows == 0 || cols == 0) return B2_OK;
+  int64_t blocks = b2_ceil_div(rows * cols, 256);
+  if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
+  tc::to_bf16_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(x, rows, cols, ld_in,
+                                                                       reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  B2_CUDA_LAUNCH_CHECK("b2_to_bf16");
   return B2_OK;
 }
 

@@ -10,7 +10,7 @@ import weakref
 import torch
 
 from . import _lib
-from ._lib import (B2_F32, B2_F64, B2_I32, B2_I64, B2_POOL_NONE, B2_POOL_SUM, B2_POOL_MEAN,
+from ._lib import (B2_F32, B2_BF16, B2_F64, B2_I32, B2_I64, B2_POOL_NONE, B2_POOL_SUM, B2_POOL_MEAN,
                    B2_ACT_NONE, B2_ACT_RELU, B2_ACT_SIGMOID, B2_PREP_MUL, b2_field)
 
 _IDX_CODE = {torch.float64: B2_F64, torch.int64: B2_I64, torch.int32: B2_I32}
@@ -364,12 +364,14 @@ def gemm_f32(a, b, out, a_t=False, b_t=False, bias=None, act=B2_ACT_NONE, mul=No
 #   "fp32"   FFMA SIMT kernel (b2_gemm_f32)                       — bit-for-bit the reference's class
 #   "tf32x3" tcgen05 tensor cores, error-compensated 3xTF32       — fp32-class accuracy (1e-5 parity)
 #   "tf32"   tcgen05 tensor cores, single TF32 pass (10-bit mantissa, >= the bf16 of BASELINE configs[1])
+#   "bf16"   tcgen05 kind::f16 on bf16 copies of the operands, fp32 accumulation (BASELINE configs[1] "bf16");
+#            activations / weights / gradients stay fp32 in HBM, every producer also emits the bf16 operand
 _MATMUL = {"mode": "fp32"}
 
 
 def set_matmul_precision(mode):
-    if mode not in ("fp32", "tf32x3", "tf32"):
-        raise ValueError("matmul precision must be 'fp32', 'tf32x3' or 'tf32'")
+    if mode not in ("fp32", "tf32x3", "tf32", "bf16"):
+        raise ValueError("matmul precision must be 'fp32', 'tf32x3', 'tf32' or 'bf16'")
     _MATMUL["mode"] = mode
 
 
@@ -410,9 +412,15 @@ def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=
     K2, N = (b.shape if b_mn else b.shape[::-1])
     if K != K2 or tuple(out.shape) != (M, N) or out.stride(1) != 1 or a.stride(1) != 1 or b.stride(1) != 1:
         raise ValueError("gemm_ex shape mismatch: a%s b%s out%s" % (tuple(a.shape), tuple(b.shape), tuple(out.shape)))
-    for t in (mul, add, ybwd, out_small, out_pre):
+    for t in (mul, add, ybwd, out_pre) + ((out_small,) if (out_small is not None and out_small.dtype == torch.float32) else ()):
         if t is not None and (tuple(t.shape) != (M, N) or t.stride(0) != out.stride(0) or t.stride(1) != 1):
             raise ValueError("gemm_ex: epilogue tensors must share out's shape and leading dimension")
+    bf16 = a_small is not None and a_small.dtype == torch.bfloat16
+    if bf16:        # the auxiliary tensors ARE the operands (bf16 copies, row pitch padded to 16 bytes)
+        if b_small is None or b_small.dtype != torch.bfloat16 or a_small.shape != a.shape or b_small.shape != b.shape:
+            raise ValueError("gemm_ex: bf16 mode needs bf16 copies of both operands")
+        a, b, a_small, b_small = a_small, b_small, None, None
+        d.elem_dtype = B2_BF16
     for t, ref in ((a_small, a), (b_small, b)):
         if t is not None and (t.shape != ref.shape or t.stride() != ref.stride()):
             raise ValueError("gemm_ex: small parts must share their operand's layout")
@@ -421,6 +429,10 @@ def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=
     d.b_small = b_small.data_ptr() if b_small is not None else None
     d.c = out.data_ptr()
     d.c_small = out_small.data_ptr() if out_small is not None else None
+    if out_small is not None:
+        if (out_small.dtype == torch.bfloat16) != bf16:
+            raise ValueError("gemm_ex: out_small dtype does not match the operand mode")
+        d.ld_aux = out_small.stride(0)
     d.c_pre = out_pre.data_ptr() if out_pre is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
     d.mul = mul.data_ptr() if mul is not None else None
@@ -444,15 +456,11 @@ def gemm_nt(a, b, out, bias=None, act=B2_ACT_NONE, mul=None, add=None, accumulat
     use_tc = (mode != "fp32" and N >= 16 and _tc_operand_ok(a) and _tc_operand_ok(b) and out.stride(1) == 1)
     if not use_tc:
         return gemm_f32(a, b, out, b_t=True, bias=bias, act=act, mul=mul, add=add, accumulate=accumulate)
-    if mode == "tf32x3":
+    if mode in ("tf32x3", "bf16"):
         if a_small is None:
-            if not a.is_contiguous():
-                a = a.contiguous()
-            a_small = split_tf32(a)
+            a_small = make_aux(a)
         if b_small is None:
-            if not b.is_contiguous():
-                b = b.contiguous()
-            b_small = split_tf32(b)
+            b_small = make_aux(b)
     else:
         a_small = b_small = None
     return gemm_ex(a, b, out, a_small=a_small, b_small=b_small, bias=bias, act=act, mul=mul, add=add,
@@ -471,16 +479,48 @@ def bump_weight_epoch():
     _WEIGHT_EPOCH[0] += 1
 
 
-def weight_small(w):
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def empty_aux(rows, cols, device):
+    """Uninitialised auxiliary operand of a (rows, cols) fp32 tensor for the current precision: its 3xTF32
+    small part (fp32, same layout), or its bf16 copy (row pitch padded to 16 bytes for TMA); None otherwise."""
+    mode = _MATMUL["mode"]
+    if mode == "tf32x3":
+        return torch.empty((rows, cols), dtype=torch.float32, device=device)
+    if mode == "bf16":
+        return torch.empty((rows, _pad8(cols)), dtype=torch.bfloat16, device=device)[:, :cols]
+    return None
+
+
+def make_aux(t):
+    """The auxiliary operand of a contiguous-row fp32 matrix `t` (see empty_aux), computed in one launch."""
+    mode = _MATMUL["mode"]
+    if mode == "tf32x3":
+        return split_tf32(t if t.is_contiguous() else t.contiguous())
+    if mode == "bf16":
+        rows, cols = t.shape
+        out = empty_aux(rows, cols, t.device)
+        _lib.call("b2_to_bf16", _ptr(t), rows, cols, t.stride(0), _ptr(out), out.stride(0), _stream())
+        return out
+    return None
+
+
+def weight_aux(w):
+    """Auxiliary operand of a WEIGHT, cached until the weight changes (see bump_weight_epoch)."""
+    mode = _MATMUL["mode"]
+    if mode not in ("tf32x3", "bf16"):
+        return None
     if not w.is_contiguous():
         raise RuntimeError("tensor-core GEMM weights must be contiguous")
-    key = (w.data_ptr(), w._version, _WEIGHT_EPOCH[0], tuple(w.shape))
+    key = (mode, w.data_ptr(), w._version, _WEIGHT_EPOCH[0], tuple(w.shape))
     ent = _SMALL_CACHE.get(w)
     if ent is not None and ent[0] == key:
         return ent[1]
-    small = split_tf32(w.detach())
-    _SMALL_CACHE[w] = (key, small)
-    return small
+    aux = make_aux(w.detach())
+    _SMALL_CACHE[w] = (key, aux)
+    return aux
 
 
 def prep_operand(x, y=None, act=B2_ACT_NONE, want_out=False, want_small=False, want_t=False,
@@ -528,9 +568,8 @@ class _LinearAct(torch.autograd.Function):
             return y
         if _tc_layer_ok(weight) and x.data_ptr() % 16 == 0:
             ctx.kind = "tc"
-            x3 = mode == "tf32x3"
-            x_small = split_tf32(x) if x3 else None
-            gemm_ex(x, weight, y, a_small=x_small, b_small=weight_small(weight) if x3 else None, bias=bias, act=act)
+            x_small = make_aux(x)
+            gemm_ex(x, weight, y, a_small=x_small, b_small=weight_aux(weight), bias=bias, act=act)
             ctx.x_small = x_small
             ctx.save_for_backward(x, weight, y if act != B2_ACT_NONE else None)
             return y
@@ -558,15 +597,16 @@ class _LinearAct(torch.autograd.Function):
         gb = _grad_buffer(ctx.bias, zero=False) if need_b else None
         fused = act != B2_ACT_NONE
         if ctx.kind == "tc":
-            x3 = ctx.x_small is not None
+            x3 = _MATMUL["mode"] == "tf32x3"
             # dZ = act'(Y) * dY, its 3xTF32 small part and the bias gradient: one pass over dY
             gz, gz_small, _, _ = prep_operand(gy, y if fused else None, act, want_out=fused, want_small=x3, colsum=gb)
             if not fused:
                 gz = gy
+            if not x3:
+                gz_small = make_aux(gz)          # bf16 mode: the bf16 operand of dZ (None for single-pass TF32)
             if need_x:
                 gx = torch.empty((M, K), dtype=torch.float32, device=x.device)
-                gemm_ex(gz, weight, gx, b_mn=True, a_small=gz_small,
-                        b_small=weight_small(weight) if x3 else None)                        # dX = dZ W
+                gemm_ex(gz, weight, gx, b_mn=True, a_small=gz_small, b_small=weight_aux(weight))   # dX = dZ W
             if need_w:
                 gw = _grad_buffer(weight, zero=False)
                 gemm_ex(gz, x, gw, a_mn=True, b_mn=True, a_small=gz_small, b_small=ctx.x_small)    # dW = dZ^T X
@@ -609,25 +649,24 @@ class _MLPChain(torch.autograd.Function):
             else:
                 kinds.append("simt")
         hs = [x]
-        smalls = [split_tf32(x) if (x3 and kinds[0] == "tc") else None]
+        smalls = [make_aux(x) if kinds[0] == "tc" else None]
         for i in range(L):
             W, b, act = Ws[i], bs[i], acts[i]
             N, K = W.shape
             h = hs[-1]
             y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-            want_small = x3 and i + 1 < L and kinds[i + 1] == "tc"
+            want_small = i + 1 < L and kinds[i + 1] == "tc"
             y_small = None
             if kinds[i] == "head":
                 _lib.call("b2_head_fwd", _ptr(h), _ptr(W), _ptr(b), M, K, act, _ptr(y), _stream())
             elif kinds[i] == "tc" and h.data_ptr() % 16 == 0:
-                y_small = torch.empty_like(y) if want_small else None
-                gemm_ex(h, W, y, a_small=smalls[-1], b_small=weight_small(W) if x3 else None, bias=b, act=act,
-                        out_small=y_small)
+                y_small = empty_aux(M, N, x.device) if want_small else None
+                gemm_ex(h, W, y, a_small=smalls[-1], b_small=weight_aux(W), bias=b, act=act, out_small=y_small)
             else:
                 kinds[i] = "simt"
                 gemm_f32(h, W, y, b_t=True, bias=b, act=act)
             if want_small and y_small is None:
-                y_small = split_tf32(y)
+                y_small = make_aux(y)
             hs.append(y)
             smalls.append(y_small)
         ctx.acts, ctx.kinds, ctx.smalls, ctx.params = acts, kinds, smalls, params
@@ -655,17 +694,20 @@ class _MLPChain(torch.autograd.Function):
             N, K = W.shape
             need_gx = i > 0 or ctx.needs_input_grad[0]
             fuse_prev = i > 0                       # fold layer i-1's activation backward / bias grad into this dgrad
-            prev_small = fuse_prev and x3 and kinds[i - 1] == "tc"
+            prev_small = fuse_prev and kinds[i - 1] == "tc"
             gx = torch.empty((M, K), dtype=torch.float32, device=dev) if need_gx else None
-            gx_small = torch.empty_like(gx) if (prev_small and gx is not None) else None
+            gx_small = empty_aux(M, K, dev) if (prev_small and gx is not None) else None
             gb_prev = None
             if kinds[i] == "head":
                 gw = _grad_buffer(W, zero=False)
                 gb = None if g_is_dz else bias_buf(i)          # g already dZ_i: activation backward and db_i are done
                 gb_prev = bias_buf(i - 1) if fuse_prev else None
+                fp32_small = gx_small if (gx_small is not None and gx_small.dtype == torch.float32) else None
                 _lib.call("b2_head_bwd_ex", _ptr(h), _ptr(W), None if g_is_dz else _ptr(y), _ptr(g), M, K,
                           B2_ACT_NONE if g_is_dz else act, _ptr(gx), _ptr(gw), _ptr(gb),
-                          acts[i - 1] if fuse_prev else B2_ACT_NONE, _ptr(gx_small), _ptr(gb_prev), _stream())
+                          acts[i - 1] if fuse_prev else B2_ACT_NONE, _ptr(fp32_small), _ptr(gb_prev), _stream())
+                if gx_small is not None and fp32_small is None:     # bf16 mode: the head kernel emits fp32 only
+                    gx_small = make_aux(gx)
                 grads[2 * i] = gw
                 if not g_is_dz:
                     grads[2 * i + 1] = gb
@@ -679,6 +721,8 @@ class _MLPChain(torch.autograd.Function):
                 out, sm, _, _ = prep_operand(g, y if fused else None, act, want_out=fused,
                                              want_small=x3 and kinds[i] == "tc", colsum=gb)
                 gz, gz_small = (out if fused else g), sm
+                if gz_small is None and kinds[i] == "tc":
+                    gz_small = make_aux(gz)          # bf16 mode (None for single-pass TF32)
                 grads[2 * i + 1] = gb
             else:
                 gz, gz_small = g, g_small
@@ -686,7 +730,7 @@ class _MLPChain(torch.autograd.Function):
                 if gx is not None:
                     prev_act = acts[i - 1] if fuse_prev else B2_ACT_NONE
                     gb_prev = bias_buf(i - 1) if fuse_prev else None
-                    gemm_ex(gz, W, gx, b_mn=True, a_small=gz_small, b_small=weight_small(W) if x3 else None,
+                    gemm_ex(gz, W, gx, b_mn=True, a_small=gz_small, b_small=weight_aux(W),
                             ybwd=hs[i] if (fuse_prev and prev_act != B2_ACT_NONE) else None, act_bwd=prev_act,
                             out_small=gx_small, colsum=gb_prev)                                   # dX (= dZ_{i-1})
                 if W.requires_grad:
@@ -724,9 +768,8 @@ class _CrossV2Layer(torch.autograd.Function):
                   and xi.data_ptr() % 16 == 0 and x0.data_ptr() % 16 == 0)
         ctx.xi_small = None
         if ctx.tc:
-            x3 = _MATMUL["mode"] == "tf32x3"
-            ctx.xi_small = split_tf32(xi) if x3 else None
-            gemm_ex(xi, weight, out, a_small=ctx.xi_small, b_small=weight_small(weight) if x3 else None, bias=bias,
+            ctx.xi_small = make_aux(xi)
+            gemm_ex(xi, weight, out, a_small=ctx.xi_small, b_small=weight_aux(weight), bias=bias,
                     mul=x0, add=xi, out_pre=lin)
         else:
             gemm_f32(xi, weight, lin, b_t=True, bias=bias)
@@ -741,12 +784,14 @@ class _CrossV2Layer(torch.autograd.Function):
         g = _f32c(g)
         bias = ctx.bias
         gb = _grad_buffer(bias, zero=False) if (bias is not None and bias.requires_grad) else None
-        x3 = ctx.xi_small is not None
+        x3 = _MATMUL["mode"] == "tf32x3"
         dlin, dlin_small, _, _ = prep_operand(g, x0, B2_PREP_MUL, want_out=True, want_small=x3 and ctx.tc, colsum=gb)
+        if ctx.tc and dlin_small is None:
+            dlin_small = make_aux(dlin)          # bf16 mode (None for single-pass TF32)
         gxi = torch.empty_like(xi)
         gw = _grad_buffer(weight, zero=False) if weight.requires_grad else None
         if ctx.tc:
-            gemm_ex(dlin, weight, gxi, b_mn=True, a_small=dlin_small, b_small=weight_small(weight) if x3 else None,
+            gemm_ex(dlin, weight, gxi, b_mn=True, a_small=dlin_small, b_small=weight_aux(weight),
                     add=g)                                                                   # dx_i = g + dlin W
             if gw is not None:
                 gemm_ex(dlin, xi, gw, a_mn=True, b_mn=True, a_small=dlin_small, b_small=ctx.xi_small)

@@ -386,14 +386,18 @@ B2_API int b2_gemm_tc(const float* a, int64_t lda, const float* b, int64_t ldb, 
  *   colsum[n] = sum_m v  (bias gradient; the call zeroes colsum first).
  * mul, add, ybwd, c_small share C's leading dimension.  a_small/b_small: 3xTF32 small parts of the
  * operands (same layout as the operands) or both NULL for single-pass TF32.
+ * elem_dtype == B2_BF16 (BASELINE configs[1] "bf16"): a and b hold bf16 (row pitch a multiple of 16
+ * bytes, i.e. leading dimensions % 8 == 0), one pass of tcgen05.mma kind::f16 with fp32 accumulation;
+ * C stays fp32 and c_small, if given, receives C rounded to bf16 (leading dimension ld_aux) — the
+ * next contraction's operand.  b2_to_bf16 makes that operand for tensors no epilogue produced.
  */
 typedef struct b2_gemm_desc {
-  const float* a;
-  const float* b;
+  const void* a;          /* fp32, or bf16 when elem_dtype == B2_BF16 */
+  const void* b;
   const float* a_small;
   const float* b_small;
   float* c;
-  float* c_small;
+  void* c_small;          /* fp32 small part of C; bf16 copy of C when elem_dtype == B2_BF16 */
   float* c_pre;
   const float* bias;
   const float* mul;
@@ -404,9 +408,13 @@ typedef struct b2_gemm_desc {
   int64_t M, N, K;
   int32_t a_mn_major, b_mn_major;
   int32_t act, act_bwd;
-  int32_t beta_accumulate, reserved_;
+  int32_t beta_accumulate;
+  int32_t elem_dtype;     /* B2_F32 (kind::tf32 on raw fp32) or B2_BF16 (kind::f16, fp32 accumulation) */
+  int64_t ld_aux;         /* leading dimension of c_small (0 = ldc) */
 } b2_gemm_desc;
 B2_API int b2_gemm_tc_ex(const b2_gemm_desc* desc, void* stream);
+B2_API int b2_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                      void* stream);
 /* small[i] = x[i] - (x[i] with the 13 low mantissa bits cleared). */
 B2_API int b2_split_tf32(const float* x, float* small, int64_t n, void* stream);
 /* out (cols, rows; ld_out) = in (rows, cols; ld_in)^T; if out_small != NULL it also receives the

@@ -561,8 +561,8 @@ MN_SHAPES = [(128, 32, 32), (300, 624, 4096), (4096, 624, 300), (624, 300, 8192)
 
 
 @pytest.mark.parametrize("M,N,K", MN_SHAPES)
-@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3", "bf16"])
 def test_gemm_tc_mn_major_operands_vs_fp64(M, N, K, a_mn, b_mn, mode):
     """The contraction reads operands as they lie in memory: A stored (K, M) and/or B stored (K, N)
     (the dgrad / wgrad layouts of nn.Linear) through MN-major matrix descriptors — no transpose."""
@@ -574,13 +574,22 @@ def test_gemm_tc_mn_major_operands_vs_fp64(M, N, K, a_mn, b_mn, mode):
     a_dev = (a.t().contiguous() if a_mn else a).cuda()
     b_dev = (b.t().contiguous() if b_mn else b).cuda()
     out = torch.full((M, N), float("nan"), device="cuda")
-    x3 = mode == "tf32x3"
-    F2.gemm_ex(a_dev, b_dev, out, a_mn=a_mn, b_mn=b_mn, a_small=F2.split_tf32(a_dev) if x3 else None,
-               b_small=F2.split_tf32(b_dev) if x3 else None)
+    F2.set_matmul_precision(mode)
+    try:
+        out_aux = F2.empty_aux(M, N, "cuda") if mode == "bf16" else None
+        F2.gemm_ex(a_dev, b_dev, out, a_mn=a_mn, b_mn=b_mn, a_small=F2.make_aux(a_dev), b_small=F2.make_aux(b_dev),
+                   out_small=out_aux)
+    finally:
+        F2.set_matmul_precision("fp32")
     torch.cuda.synchronize()
     assert not torch.isnan(out).any()
-    err = rel_err(out, ref)
-    assert err <= (3e-3 if mode == "tf32" else 2e-6), err
+    if mode == "bf16":      # checker: the same contraction of the bf16-rounded operands, in float64
+        ref = a.bfloat16().double() @ b.bfloat16().double().t()
+        assert rel_err(out, ref) <= 2e-6
+        assert torch.equal(out_aux, out.bfloat16())          # the epilogue's bf16 copy is RN(out)
+    else:
+        err = rel_err(out, ref)
+        assert err <= (3e-3 if mode == "tf32" else 2e-6), err
 
 
 @pytest.mark.parametrize("act_bwd", ["none", "relu", "sigmoid"])
@@ -611,7 +620,7 @@ def test_gemm_tc_fused_backward_epilogue(act_bwd):
     assert close(colsum, want.sum(dim=0), RTOL, atol=1e-5 * float(want.abs().sum(dim=0).max()))
 
 
-@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32", "bf16"])
 @pytest.mark.parametrize("dims,acts,B", [((624, 300, 300, 300, 1), ("relu", "relu", "relu", None), 4096),
                                          ((325, 64, 64, 64, 1), ("relu", "relu", "relu", "sigmoid"), 1000),
                                          ((128, 64, 1), ("sigmoid", None), 777),
@@ -646,7 +655,7 @@ def test_mlp_chain_matches_torch_autograd(mode, dims, acts, B):
         yg.backward(gout.cuda())
     finally:
         F2.set_matmul_precision("fp32")
-    tol = RTOL if mode == "tf32x3" else 5e-3
+    tol = {"tf32x3": RTOL, "tf32": 5e-3, "bf16": 3e-2}[mode]
     assert close(yg, yr, tol)
     assert close(xg.grad, xr.grad, tol, atol=tol * float(xr.grad.abs().max()))
     for (k, pg), (_, pr) in zip(mlp.named_parameters(), ref.named_parameters()):
