@@ -16,6 +16,7 @@ B2_F32, B2_BF16, B2_F64, B2_I64, B2_I32 = 0, 1, 2, 3, 4
 B2_POOL_NONE, B2_POOL_SUM, B2_POOL_MEAN = 0, 1, 2
 B2_ACT_NONE, B2_ACT_RELU, B2_ACT_SIGMOID = 0, 1, 2
 B2_PREP_MUL = 3
+B2_GEMM_C_IS_ZERO, B2_GEMM_COLSUM_IS_ZERO = 1, 2
 B2_MAX_FIELDS = 128
 FM_PRODUCT_SUM, FM_BI_INTERACTION, FM_INNER_PRODUCT = 0, 1, 2
 
@@ -62,6 +63,7 @@ class b2_gemm_desc(ctypes.Structure):
         ("lda", c_int64), ("ldb", c_int64), ("ldc", c_int64), ("M", c_int64), ("N", c_int64), ("K", c_int64),
         ("a_mn_major", c_int32), ("b_mn_major", c_int32), ("act", c_int32), ("act_bwd", c_int32),
         ("beta_accumulate", c_int32), ("elem_dtype", c_int32), ("ld_aux", c_int64),
+        ("flags", c_int64),
     ]
 
 # name -> (restype, argtypes); every symbol the header declares must appear here
@@ -132,7 +134,7 @@ SIGNATURES = {
     "b2_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p]),
     "b2_head_bwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
-                               c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+                               c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "b2_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b2_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "b2_logit_bce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,

@@ -64,6 +64,7 @@ class ParamArena(object):
         # squares there so that ONE all-reduce carries the dense gradients and the norm term
         self._G_ext = torch.zeros(off + 4, dtype=torch.float32, device=dev)
         self.G = self._G_ext[:off]
+        self._G_ext._b2_arena = self          # lets a kernel wrapper recognise a slice of this (zeroed) arena
         self.params = uniq
         self.step_id = 0
         self.grads_are_zero = True

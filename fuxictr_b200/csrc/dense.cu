@@ -435,7 +435,8 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
     b2_adam_apply(pp.z, __fmul_rn(gg.z, clip), mm.z, vv.z, c, step_size, ibc2);
     b2_adam_apply(pp.w, __fmul_rn(gg.w, clip), mm.w, vv.w, c, step_size, ibc2);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
-    if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // zero_grad fused in; rows no sample touched are already zero (most of a table): skip their 16-byte store
+    if (zero_grad && (gg.x != 0.f || gg.y != 0.f || gg.z != 0.f || gg.w != 0.f)) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;

@@ -745,11 +745,11 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     p.tmem_cols = cols;
   }
   const int splits = (int) b2_ceil_div(num_kb, p.kb_per_split);
-  if (splits > 1 && !p.beta) {
+  if (splits > 1 && !p.beta && !(d->flags & B2_GEMM_C_IS_ZERO)) {
     cudaError_t e = cudaMemset2DAsync(c, (size_t) ldc * 4, 0, (size_t) N * 4, (size_t) M, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
-  if (d->colsum != nullptr) {
+  if (d->colsum != nullptr && !(d->flags & B2_GEMM_COLSUM_IS_ZERO)) {
     cudaError_t e = cudaMemsetAsync(d->colsum, 0, sizeof(float) * (size_t) N, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
@@ -860,12 +860,12 @@ extern "C" B2_API int b2_head_fwd(const float* x, const float* w, const float* b
 
 extern "C" B2_API int b2_head_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M,
                                   int K, int act, float* gx, float* gw, float* gb, void* stream) {
-  return b2_head_bwd_ex(x, w, y, gy, M, K, act, gx, gw, gb, B2_ACT_NONE, nullptr, nullptr, stream);
+  return b2_head_bwd_ex(x, w, y, gy, M, K, act, gx, gw, gb, B2_ACT_NONE, nullptr, nullptr, 0, stream);
 }
 
 extern "C" B2_API int b2_head_bwd_ex(const float* x, const float* w, const float* y, const float* gy, int64_t M,
                                      int K, int act, float* gx, float* gw, float* gb, int prev_act,
-                                     float* gx_small, float* gb_prev, void* stream) {
+                                     float* gx_small, float* gb_prev, int grads_zeroed, void* stream) {
   B2_REQUIRE(x && w && gy && gw, "NULL pointer");
   B2_REQUIRE(K >= 1 && K <= 6144 && act >= B2_ACT_NONE && act <= B2_ACT_SIGMOID, "bad K/act");
   B2_REQUIRE(prev_act >= B2_ACT_NONE && prev_act <= B2_ACT_SIGMOID, "bad prev_act");
@@ -873,9 +873,12 @@ extern "C" B2_API int b2_head_bwd_ex(const float* x, const float* w, const float
   B2_REQUIRE(gx != nullptr || (gx_small == nullptr && gb_prev == nullptr && prev_act == B2_ACT_NONE),
              "prev_act / gx_small / gb_prev need gx");
   cudaStream_t st = (cudaStream_t) stream;
-  cudaError_t e = cudaMemsetAsync(gw, 0, sizeof(float) * (size_t) K, st);
-  if (e == cudaSuccess && gb_prev != nullptr) e = cudaMemsetAsync(gb_prev, 0, sizeof(float) * (size_t) K, st);
-  if (e == cudaSuccess && gb != nullptr) e = cudaMemsetAsync(gb, 0, sizeof(float), st);
+  cudaError_t e = cudaSuccess;
+  if (!grads_zeroed) {    // the caller vouches that gw / gb / gb_prev are all-zero (a gradient arena cleared by Adam)
+    e = cudaMemsetAsync(gw, 0, sizeof(float) * (size_t) K, st);
+    if (e == cudaSuccess && gb_prev != nullptr) e = cudaMemsetAsync(gb_prev, 0, sizeof(float) * (size_t) K, st);
+    if (e == cudaSuccess && gb != nullptr) e = cudaMemsetAsync(gb, 0, sizeof(float), st);
+  }
   if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_head_bwd: memset: %s", cudaGetErrorString(e));
   if (M <= 0) return B2_OK;
   int64_t ctas = 2 * B2_NUM_SMS;

@@ -59,6 +59,14 @@ def _grad_buffer(param, zero):
     return torch.zeros_like(param) if zero else torch.empty_like(param)
 
 
+def _is_zeroed(buf):
+    """True when `buf` is a gradient-arena slice that the optimizer pass left all-zero (so a kernel that
+    accumulates into it needs no memset node of its own)."""
+    base = buf._base if buf is not None else None
+    arena = getattr(base, "_b2_arena", None) if base is not None else None
+    return arena is not None and arena.grads_are_zero
+
+
 # --------------------------------------------------------------------------------------
 # Fused multi-field embedding gather
 # --------------------------------------------------------------------------------------
@@ -402,7 +410,7 @@ def transpose_f32(t, want_small):
 
 def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=None, act=B2_ACT_NONE,
             mul=None, add=None, ybwd=None, act_bwd=B2_ACT_NONE, out_small=None, colsum=None, accumulate=False,
-            out_pre=None):
+            out_pre=None, out_is_zero=False):
     """out (M,N) = epi(sum_k A(m,k) B(n,k)) on the tcgen05 kernel (b2_gemm_tc_ex).  a is (M,K), or (K,M) when
     a_mn (MN-major: the tensor is consumed as it lies, no transpose); b is (N,K), or (K,N) when b_mn.
     a_small / b_small: the operands' 3xTF32 small parts (both or neither).  Epilogue extras: ybwd/act_bwd
@@ -444,6 +452,7 @@ def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=
     d.a_mn_major, d.b_mn_major = int(bool(a_mn)), int(bool(b_mn))
     d.act, d.act_bwd = act, (act_bwd if ybwd is not None else B2_ACT_NONE)
     d.beta_accumulate = 1 if accumulate else 0
+    d.flags = (_lib.B2_GEMM_C_IS_ZERO if out_is_zero else 0) | (_lib.B2_GEMM_COLSUM_IS_ZERO if _is_zeroed(colsum) else 0)
     _lib.call("b2_gemm_tc_ex", ctypes.byref(d), _stream())
     return out
 
@@ -609,7 +618,8 @@ class _LinearAct(torch.autograd.Function):
                 gemm_ex(gz, weight, gx, b_mn=True, a_small=gz_small, b_small=weight_aux(weight))   # dX = dZ W
             if need_w:
                 gw = _grad_buffer(weight, zero=False)
-                gemm_ex(gz, x, gw, a_mn=True, b_mn=True, a_small=gz_small, b_small=ctx.x_small)    # dW = dZ^T X
+                gemm_ex(gz, x, gw, a_mn=True, b_mn=True, a_small=gz_small, b_small=ctx.x_small,
+                        out_is_zero=_is_zeroed(gw))                                                # dW = dZ^T X
             return gx, gw, gb, None
         # fp32 SIMT path
         gz = gy
@@ -705,7 +715,9 @@ class _MLPChain(torch.autograd.Function):
                 fp32_small = gx_small if (gx_small is not None and gx_small.dtype == torch.float32) else None
                 _lib.call("b2_head_bwd_ex", _ptr(h), _ptr(W), None if g_is_dz else _ptr(y), _ptr(g), M, K,
                           B2_ACT_NONE if g_is_dz else act, _ptr(gx), _ptr(gw), _ptr(gb),
-                          acts[i - 1] if fuse_prev else B2_ACT_NONE, _ptr(fp32_small), _ptr(gb_prev), _stream())
+                          acts[i - 1] if fuse_prev else B2_ACT_NONE, _ptr(fp32_small), _ptr(gb_prev),
+                          1 if (_is_zeroed(gw) and (gb is None or _is_zeroed(gb))
+                                and (gb_prev is None or _is_zeroed(gb_prev))) else 0, _stream())
                 if gx_small is not None and fp32_small is None:     # bf16 mode: the head kernel emits fp32 only
                     gx_small = make_aux(gx)
                 grads[2 * i] = gw
@@ -735,7 +747,8 @@ class _MLPChain(torch.autograd.Function):
                             out_small=gx_small, colsum=gb_prev)                                   # dX (= dZ_{i-1})
                 if W.requires_grad:
                     gw = _grad_buffer(W, zero=False)
-                    gemm_ex(gz, h, gw, a_mn=True, b_mn=True, a_small=gz_small, b_small=smalls[i])     # dW = dZ^T X
+                    gemm_ex(gz, h, gw, a_mn=True, b_mn=True, a_small=gz_small, b_small=smalls[i],
+                            out_is_zero=_is_zeroed(gw))                                              # dW = dZ^T X
                     grads[2 * i] = gw
                 g, g_small, g_is_dz = gx, gx_small, fuse_prev
             else:               # fp32 SIMT layer inside a chain (odd shapes)
@@ -794,7 +807,7 @@ class _CrossV2Layer(torch.autograd.Function):
             gemm_ex(dlin, weight, gxi, b_mn=True, a_small=dlin_small, b_small=weight_aux(weight),
                     add=g)                                                                   # dx_i = g + dlin W
             if gw is not None:
-                gemm_ex(dlin, xi, gw, a_mn=True, b_mn=True, a_small=dlin_small, b_small=ctx.xi_small)
+                gemm_ex(dlin, xi, gw, a_mn=True, b_mn=True, a_small=dlin_small, b_small=ctx.xi_small, out_is_zero=_is_zeroed(gw))
         else:
             gemm_f32(dlin, weight, gxi, add=g)
             if gw is not None:

@@ -411,7 +411,10 @@ typedef struct b2_gemm_desc {
   int32_t beta_accumulate;
   int32_t elem_dtype;     /* B2_F32 (kind::tf32 on raw fp32) or B2_BF16 (kind::f16, fp32 accumulation) */
   int64_t ld_aux;         /* leading dimension of c_small (0 = ldc) */
+  int64_t flags;          /* B2_GEMM_*: the caller vouches an output is already all-zero (skips its memset) */
 } b2_gemm_desc;
+#define B2_GEMM_C_IS_ZERO 1      /* split-K accumulates into C with red.global: C needs no clearing */
+#define B2_GEMM_COLSUM_IS_ZERO 2
 B2_API int b2_gemm_tc_ex(const b2_gemm_desc* desc, void* stream);
 B2_API int b2_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                       void* stream);
@@ -442,10 +445,11 @@ B2_API int b2_head_bwd(const float* x, const float* w, const float* y, const flo
                        int act, float* gx, float* gw, float* gb, void* stream);
 /* Same, fused with the activation backward of the layer that PRODUCED x (x is that layer's
  * activation output, mlp_block.py:78-80): gx <- prev_act'(x) * gx, gx_small = its 3xTF32 small part
- * (or NULL), gb_prev (K) = sum_m gx[m,:] = that layer's bias gradient (or NULL). */
+ * (or NULL), gb_prev (K) = sum_m gx[m,:] = that layer's bias gradient (or NULL).  grads_zeroed != 0: the
+ * caller vouches gw, gb and gb_prev are already all-zero (a gradient arena cleared by the optimizer pass). */
 B2_API int b2_head_bwd_ex(const float* x, const float* w, const float* y, const float* gy, int64_t M, int K,
                           int act, float* gx, float* gw, float* gb, int prev_act, float* gx_small,
-                          float* gb_prev, void* stream);
+                          float* gb_prev, int grads_zeroed, void* stream);
 /* Elementwise helpers used by the dense backward.
  * b2_act_bwd: gx = gy * act'(y) where y is the activation OUTPUT (relu, sigmoid). */
 B2_API int b2_act_bwd(const float* y, const float* gy, float* gx, int64_t n, int act, void* stream);
