@@ -181,6 +181,7 @@ class FusedAdam(object):
         self.host_steps = 0          # optimizer steps issued (eager calls + graph replays), see count_step()
         self.grad_allreduce = False  # data-parallel replicas: average G across ranks before the step
         self.sharded = False         # row-sharded tables in G[:tail_offset], replicated dense params after
+        self.dense_prescaled = False # sharded: gradients were born divided by the world size (no mul_ after the all-reduce)
 
     def enable_lazy(self, tables):
         """Evaluate the dense Adam semantics of `tables` (the arena's leading parameters) lazily."""
@@ -239,7 +240,7 @@ class FusedAdam(object):
             # ONE collective: dense gradients (to be averaged) + the shard norm term (to be summed)
             dist.all_reduce(a._G_ext[a.tail_offset:a.numel + 1], op=dist.ReduceOp.SUM)
             dense = a.G[a.tail_offset:]
-            if dense.numel() > 0:
+            if dense.numel() > 0 and not self.dense_prescaled:
                 dense.mul_(1.0 / world)                          # mean over the global batch
             if self.max_norm is not None:
                 # global norm^2 = sum over ranks of the shard parts + the (replicated) dense part once

@@ -248,9 +248,12 @@ front_reduce_kernel(const float* __restrict__ emb, const float* __restrict__ lrw
 __global__ void __launch_bounds__(256)
 front_gprep_kernel(const float* __restrict__ gx, const float* __restrict__ emb,
                    const float* __restrict__ sums, const float* __restrict__ glogit, int64_t batch,
-                   int F, int dim, int want_fm, float* __restrict__ gemb) {
+                   int F, int dim, int want_fm, float* __restrict__ gemb, float* __restrict__ glogit_out) {
   const int64_t n4 = batch * (int64_t) F * dim / 4;
   const int d4 = dim / 4;
+  if (glogit_out != nullptr)      // publish the logit gradient where the row owners can read it (LR tables)
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < batch; i += (int64_t) gridDim.x * blockDim.x)
+      glogit_out[i] = __ldg(glogit + i);
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t) gridDim.x * blockDim.x) {
     const int64_t bf = i / d4;
@@ -404,14 +407,16 @@ extern "C" B2_API int b2_front_reduce(const float* emb, const float* lrw, const 
 
 extern "C" B2_API int b2_front_gprep(const float* gx, const float* emb, const float* sums, const float* glogit,
                                      int64_t batch, int nfields, int dim, int want_fm, float* gemb,
-                                     void* stream) {
+                                     float* glogit_out, void* stream) {
   B2_REQUIRE(gemb != nullptr, "NULL output");
+  B2_REQUIRE(glogit_out == nullptr || glogit != nullptr, "glogit_out needs glogit");
   B2_REQUIRE(dim >= 4 && dim % 4 == 0 && nfields >= 1, "bad dim/nfields");
   B2_REQUIRE(!want_fm || (emb && sums && glogit), "want_fm needs emb, sums, glogit");
   if (batch <= 0) return B2_OK;
   const int64_t n4 = batch * (int64_t) nfields * dim / 4;
   const int grid = grid_for(n4, 256);
-  front_gprep_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(gx, emb, sums, glogit, batch, nfields, dim, want_fm, gemb);
+  front_gprep_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(gx, emb, sums, glogit, batch, nfields, dim, want_fm, gemb,
+                                                             glogit_out);
   B2_CUDA_LAUNCH_CHECK("b2_front_gprep");
   return B2_OK;
 }

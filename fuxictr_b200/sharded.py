@@ -152,6 +152,9 @@ class ShardedFront(object):
         self.gemb, self.gemb_ptrs, _ = g.alloc("gemb", (batch_local, self.F * dim), torch.float32)
         self.glogit, self.glogit_ptrs, _ = g.alloc("glogit", (batch_local,), torch.float32)
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        # mean over the GLOBAL batch (rank_model.py:130): either the pull scales every gradient row by
+        # 1/world (default), or the caller seeds backward() with 1/world and sets pull_scale = 1
+        self.pull_scale = 1.0 / g.world
 
     # -- descriptors --------------------------------------------------------------------------
     def _descs(self, tables, dim):
@@ -196,15 +199,14 @@ class ShardedFront(object):
     # -- backward phases ------------------------------------------------------------------------
     def phase_gprep(self, gx, emb, sums, glogit):
         _lib.call("b2_front_gprep", F2._ptr(gx), F2._ptr(emb), F2._ptr(sums), F2._ptr(glogit), self.B, self.F,
-                  self.dim, 1 if self.want_fm else 0, F2._ptr(self.gemb), F2._stream())
-        self.glogit.copy_(glogit)
+                  self.dim, 1 if self.want_fm else 0, F2._ptr(self.gemb), F2._ptr(self.glogit), F2._stream())
 
     def phase_pull(self, emb_grads, lr_grads):
         g = self.group
         lr = self._descs(lr_grads, 1) if lr_grads else None
         _lib.call("b2_shard_pull", self._descs(emb_grads, self.dim), lr, self.F, self.B, g.world, g.rank,
                   _ptr_array(self.gemb_ptrs), _ptr_array(self.glogit_ptrs) if lr is not None else None,
-                  1.0 / g.world, F2._ptr(self.owned), F2._ptr(self.owned_count), self.owned_cap, F2._stream())
+                  self.pull_scale, F2._ptr(self.owned), F2._ptr(self.owned_count), self.owned_cap, F2._stream())
 
 
 class _ShardedFrontFn(torch.autograd.Function):

@@ -192,6 +192,10 @@ class RankModel(nn.Module):
                                               bias=(lr_layer.bias if lr_layer is not None else None),
                                               want_fm=want_fm)
         self._sharded_params = etabs + ltabs
+        # fused_train_step seeds backward() with 1/world, so every gradient (dense and rows) is born
+        # divided by the world size: the pull and the dense all-reduce then need no scaling pass
+        self._sharded_front.pull_scale = 1.0
+        self._loss_grad = torch.full((), 1.0 / group.world, dtype=torch.float32, device=self.device)
         return self._sharded_front
 
     def _batch_matrix(self, inputs):
@@ -241,6 +245,7 @@ class RankModel(nn.Module):
         self._arena = ParamArena(self, first=getattr(self, "_sharded_params", ()))
         self._fused_optimizer = FusedAdam(self._arena, lr=self._lr, max_norm=self._max_gradient_norm)
         self._fused_optimizer.sharded = bool(getattr(self, "_sharded_params", None))
+        self._fused_optimizer.dense_prescaled = getattr(self, "_loss_grad", None) is not None
         self.optimizer = None
         return self._fused_optimizer
 
@@ -263,7 +268,11 @@ class RankModel(nn.Module):
             loss, _ = F2.logit_bce(y_true, *self.forward_logits(batch_data))
         else:
             loss = self.compute_loss(self.forward(batch_data), y_true)
-        loss.backward()
+        seed = getattr(self, "_loss_grad", None)      # 1/world for row-sharded runs (see enable_sharding)
+        if seed is not None:
+            loss.backward(seed)
+        else:
+            loss.backward()
         opt.step()
         return loss
 

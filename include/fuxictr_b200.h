@@ -253,9 +253,11 @@ B2_API int b2_peer_bcast(const void* src, int64_t nbytes, void* const* peer_dst,
  * sums[b,:] = sum_f emb[b,f,:] (saved for the backward). */
 B2_API int b2_front_reduce(const float* emb, const float* lrw, const float* bias, int64_t batch,
                            int nfields, int dim, int want_fm, float* logit, float* sums, void* stream);
-/* Before the pull: gemb[b,f,:] = gx[b,f,:] + glogit[b] * (sums[b,:] - emb[b,f,:]) (2nd term if want_fm). */
+/* Before the pull: gemb[b,f,:] = gx[b,f,:] + glogit[b] * (sums[b,:] - emb[b,f,:]) (2nd term if want_fm);
+ * glogit_out (optional, peer-visible) receives a copy of glogit for the owners of the LR rows. */
 B2_API int b2_front_gprep(const float* gx, const float* emb, const float* sums, const float* glogit,
-                          int64_t batch, int nfields, int dim, int want_fm, float* gemb, void* stream);
+                          int64_t batch, int nfields, int dim, int want_fm, float* gemb, float* glogit_out,
+                          void* stream);
 
 /*
  * InnerProductInteraction (layers/interactions/inner_product.py:55-70).
