@@ -1,0 +1,50 @@
+#!/bin/bash
+# One GPU-box session that measures as much as possible (GPU slots are scarce): every stage logs to
+# gpurun_out/<tag>_*.{log,json,csv} and never aborts the following stages.
+#   tools/gpu_session.sh <tag> [stages...]      stages: tests bench bf16 workloads ncu sanitize
+tag=${1:-s}; shift
+stages=${@:-tests bench}
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
+for st in $stages; do
+  case $st in
+    tests)
+      timeout 900 python -m pytest tests/test_reference_boundary.py -q -m gpu > gpurun_out/${tag}_boundary.log 2>&1
+      tail -5 gpurun_out/${tag}_boundary.log
+      timeout 1500 python -m pytest tests -q -m gpu --durations=12 -p no:cacheprovider > gpurun_out/${tag}_gputests.log 2>&1
+      tail -25 gpurun_out/${tag}_gputests.log ;;
+    quicktests)
+      timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "gemm_tc or mlp_chain or trajectory_tf32x3 or criteo_shape" -p no:cacheprovider > gpurun_out/${tag}_quick.log 2>&1
+      tail -25 gpurun_out/${tag}_quick.log ;;
+    bench)
+      timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+      tail -c 1500 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err ;;
+    bf16)
+      for prec in bf16 tf32 fp32; do
+        timeout 300 python bench.py --precision $prec --steps-only > gpurun_out/${tag}_bench_$prec.json 2> gpurun_out/${tag}_bench_$prec.err
+        cat gpurun_out/${tag}_bench_$prec.json; tail -2 gpurun_out/${tag}_bench_$prec.err
+      done ;;
+    workloads)
+      for w in dcnv2 din xdeepfm; do
+        timeout 400 python bench.py --workload $w --steps 100 --cpu-seconds 6 > gpurun_out/${tag}_bench_$w.json 2> gpurun_out/${tag}_bench_$w.err
+        head -c 600 gpurun_out/${tag}_bench_$w.json; echo; tail -2 gpurun_out/${tag}_bench_$w.err
+      done ;;
+    dlrm1)
+      timeout 600 python bench.py --workload dlrm --steps 20 --warmup 5 --nbatches 8 > gpurun_out/${tag}_bench_dlrm_n1.json 2> gpurun_out/${tag}_bench_dlrm_n1.err
+      head -c 800 gpurun_out/${tag}_bench_dlrm_n1.json; echo; tail -3 gpurun_out/${tag}_bench_dlrm_n1.err ;;
+    ncu)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
+        python bench.py --steps 2 --warmup 3 --graph 0 --steps-only --nbatches 4 > gpurun_out/${tag}_ncu_launch.log 2>&1
+      tail -3 gpurun_out/${tag}_ncu_launch.log
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 12 -c 9 -o gpurun_out/${tag}_gemm \
+        python bench.py --steps 1 --warmup 3 --graph 0 --steps-only --nbatches 4 > gpurun_out/${tag}_ncu_gemm.log 2>&1
+      tail -3 gpurun_out/${tag}_ncu_gemm.log ;;
+    sanitize)
+      timeout 1500 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -m gpu -x -p no:cacheprovider \
+        -k "gemm_tc_mn_major and (128-32-32 or 77-44-36 or 129-260) or fused_backward or mlp_chain and 40 or lazy_adam_optimizer or cin_fused" \
+        > gpurun_out/${tag}_memcheck.log 2>&1
+      tail -8 gpurun_out/${tag}_memcheck.log ;;
+  esac
+done
+echo "[gpu_session $tag] done"
