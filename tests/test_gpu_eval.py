@@ -222,7 +222,7 @@ def test_loader_feeds_pipeline_from_pinned_ring(tmp_path):
     path = str(tmp_path / "train.npz")
     np.savez(path, **cols)
     loader = DL.NpzDataLoader(fm, path, batch_size=B, shuffle=True)
-    assert loader.matrix.is_pinned() and len(loader) == 33
+    assert not loader.matrix.is_pinned() and len(loader) == 33     # shuffled: batches leave through the pinned ring slots
     torch.manual_seed(5)
     kept = [m.clone() for m in loader.matrices()]          # the epoch's batches, in order
     ref.use_fused_optimizer()
