@@ -189,6 +189,10 @@ class ShardedFront(object):
         # The landed rows are consumed in place: the next overwrite of this peer buffer is the NEXT
         # step's push, which is ordered after this step's backward (and its closing barrier).
         emb = self.emb
+        if not self.lr_tables and not self.want_fm:     # embeddings only (DLRM): nothing to reduce
+            if getattr(self, "_zero_logit", None) is None:
+                self._zero_logit = torch.zeros((self.B, 1), dtype=torch.float32, device="cuda")
+            return emb, self._zero_logit, None
         logit = torch.empty((self.B, 1), dtype=torch.float32, device="cuda")
         sums = torch.empty((self.B, self.dim), dtype=torch.float32, device="cuda") if self.want_fm else None
         _lib.call("b2_front_reduce", F2._ptr(emb), F2._ptr(self.lrw) if self.lr_tables else None,
@@ -199,7 +203,8 @@ class ShardedFront(object):
     # -- backward phases ------------------------------------------------------------------------
     def phase_gprep(self, gx, emb, sums, glogit):
         _lib.call("b2_front_gprep", F2._ptr(gx), F2._ptr(emb), F2._ptr(sums), F2._ptr(glogit), self.B, self.F,
-                  self.dim, 1 if self.want_fm else 0, F2._ptr(self.gemb), F2._ptr(self.glogit), F2._stream())
+                  self.dim, 1 if self.want_fm else 0, F2._ptr(self.gemb),
+                  F2._ptr(self.glogit) if glogit is not None else None, F2._stream())
 
     def phase_pull(self, emb_grads, lr_grads):
         g = self.group
@@ -235,7 +240,10 @@ class _ShardedFrontFn(torch.autograd.Function):
         emb, sums = ctx.saved_tensors
         g = front.group
         gx = None if gemb is None else F2._f32c(gemb).view(front.B, -1)
-        gl = (torch.zeros(front.B, device="cuda") if glogit is None else F2._f32c(glogit).view(-1))
+        needs_logit = bool(front.lr_tables) or front.want_fm
+        gl = None
+        if needs_logit:
+            gl = (torch.zeros(front.B, device="cuda") if glogit is None else F2._f32c(glogit).view(-1))
         front.phase_gprep(gx, emb, sums, gl)
         g.barrier()                      # every rank's gradient rows are ready to be pulled
         n = front.F
