@@ -550,11 +550,14 @@ def gather_points(peaks, rows, vs_label):
                 mat = torch.cat([zipf_ids(B, [rows] * F_, 1.05, seed=B, device="cuda"),
                                  torch.zeros(B, 1, device="cuda", dtype=torch.float64)], dim=1)
             idx = [mat[:, i] for i in range(F_)]
-            with torch.no_grad():
-                ms = time_kernel(lambda: F2.embed_gather(plan, idx, tables), 20, None)
             nbytes = B * (F_ * 8 + 2 * F_ * D * 4)
-            res.append({"ids": dist_name, "batch": B, "ms": ms, "GBps": nbytes / ms / 1e6,
-                        "frac_of_measured_hbm": nbytes / ms / 1e6 / peaks["hbm_gbs"]})
+            for hot_rows in ((0,) if dist_name == "uniform" else (0, 16)):
+                plan.hot_rows = hot_rows
+                with torch.no_grad():
+                    ms = time_kernel(lambda: F2.embed_gather(plan, idx, tables), 20, None)
+                res.append({"ids": dist_name, "batch": B, "hot_rows_in_smem": hot_rows, "ms": ms, "GBps": nbytes / ms / 1e6,
+                            "frac_of_measured_hbm": nbytes / ms / 1e6 / peaks["hbm_gbs"]})
+            plan.hot_rows = 0
             del mat, idx
     del tables
     torch.cuda.empty_cache()

@@ -46,14 +46,33 @@ __device__ __forceinline__ void b2_st_row<4>(float4* p, const float4& v, int mod
   if (mode == 1) b2_stg_stream(p, v); else *p = v;
 }
 
-template <typename IdxT, int VEC, int UNROLL>
+// HOT > 0: the first `hot_rows` rows of every table (FuxiCTR's tokenizer numbers ids by descending
+// frequency, so small ids are the hot ones; Zipf-like data sends 20-40 % of the lookups there) are staged
+// once per CTA in shared memory and served from it instead of L2.
+template <typename IdxT, int VEC, int UNROLL, bool HOT>
 __global__ void __launch_bounds__(256)
 gather_fast_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int lpr_log2,
-                   int32_t* __restrict__ status, int stream) {
+                   int32_t* __restrict__ status, int stream, int hot_rows, int hot_dim) {
   using V = typename VecT<VEC>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemFields sf = b2_stage_fields(pack, smem_raw);
   const int nslots = pack.nslots, nfields = pack.nfields;
+  float* hot = nullptr;
+  if (HOT) {   // [field][row][hot_dim] fp32, rows beyond a table's vocabulary are never addressed
+    hot = reinterpret_cast<float*>(smem_raw + ((pack_smem_bytes(pack.nfields) + 15) & ~(size_t) 15));
+    const int per_row = hot_dim / VEC;
+    const int total = nfields * hot_rows * per_row;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int fi = i / (hot_rows * per_row);
+      const int rem = i - fi * (hot_rows * per_row);
+      const int r = rem / per_row, c = (rem - r * per_row) * VEC;
+      V v = b2_vzero<VEC>();
+      if (r < sf.f[fi].vocab)
+        v = __ldg(reinterpret_cast<const V*>(reinterpret_cast<const float*>(sf.f[fi].table) + (int64_t) r * hot_dim + c));
+      *reinterpret_cast<V*>(hot + ((int64_t) fi * hot_rows + r) * hot_dim + c) = v;
+    }
+    __syncthreads();
+  }
   const bool all_len1 = pack.all_len1 != 0;
   const int sub = threadIdx.x & ((1 << lpr_log2) - 1);
   const int e = sub * VEC;  // first element this lane moves
@@ -66,11 +85,13 @@ gather_fast_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int 
     const V* src[UNROLL];
     V* dst[UNROLL];
     bool live[UNROLL];
+    bool in_smem[UNROLL];
     // Phase 1: all index loads in flight together.
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const int64_t item = base + (int64_t) u * ngroups;
       live[u] = false;
+      in_smem[u] = false;
       src[u] = nullptr;
       dst[u] = nullptr;
       if (item < nitems) {
@@ -93,7 +114,10 @@ gather_fast_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int 
         if (lane_on) {
           dst[u] = reinterpret_cast<V*>(reinterpret_cast<float*>(fd.out) + b * fd.out_stride +
                                         (int64_t) l * fd.dim + e);
-          if (row >= 0 && row < fd.vocab) {
+          if (HOT && row >= 0 && row < hot_rows && row < fd.vocab) {
+            src[u] = reinterpret_cast<const V*>(hot + ((int64_t) fi * hot_rows + row) * hot_dim + e);
+            live[u] = in_smem[u] = true;
+          } else if (row >= 0 && row < fd.vocab) {
             src[u] = reinterpret_cast<const V*>(reinterpret_cast<const float*>(fd.table) +
                                                 row * fd.dim + e);
             live[u] = true;
@@ -108,7 +132,7 @@ gather_fast_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch, int 
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       val[u] = b2_vzero<VEC>();
-      if (live[u]) val[u] = b2_ld_row<VEC>(src[u], stream);
+      if (live[u]) val[u] = (HOT && in_smem[u]) ? *src[u] : b2_ld_row<VEC>(src[u], stream);
     }
     // Phase 3: coalesced stores of the stacked/concatenated tensor.
 #pragma unroll
@@ -351,9 +375,9 @@ lr_bwd_kernel(const __grid_constant__ B2FieldPack pack, int64_t batch,
 // ---------------------------------------------------------------------------------
 template <typename IdxT>
 static int launch_gather(const B2FieldPack& pack, int64_t batch, int vec, int max_dim,
-                         bool any_pooled, float* mean_count, int32_t* status, cudaStream_t st) {
+                         bool any_pooled, float* mean_count, int32_t* status, int hot_rows, cudaStream_t st) {
   const int block = 256;
-  const size_t smem = pack_smem_bytes(pack.nfields);
+  size_t smem = pack_smem_bytes(pack.nfields);
   int lpr_log2 = next_pow2_log2((max_dim + vec - 1) / vec);
   if (lpr_log2 > 5) lpr_log2 = 5;
   const bool one_pass = ((1 << lpr_log2) * vec) >= max_dim;
@@ -366,16 +390,27 @@ static int launch_gather(const B2FieldPack& pack, int64_t batch, int vec, int ma
     const bool big = nitems >= (int64_t) 1 << 20;
     const int unroll = env_unroll ? env_unroll : (big ? 8 : 4);
     const int stream = env_stream > 0 ? env_stream : 0;  // load flavour (b2_ld_row); measured (10 GB tables, B=524288): 3.77 TB/s plain vs 3.65 TB/s streaming
+    // hot-row staging: one common dim, every field one slot, a staging area of at most 44 KB per CTA
+    bool same_dim = pack.all_len1 != 0;
+    for (int i = 0; i < pack.nfields && same_dim; ++i) same_dim = pack.f[i].dim == max_dim;
+    const size_t hot_bytes = (size_t) pack.nfields * hot_rows * max_dim * sizeof(float);
+    if (hot_rows > 0 && same_dim && vec == 4 && unroll == 8 && (max_dim % 4) == 0 && hot_bytes <= 44 * 1024) {
+      const size_t hsmem = ((smem + 15) & ~(size_t) 15) + hot_bytes;
+      const int grid = grid_for(b2_ceil_div(nitems, 8) << lpr_log2, block);
+      gather_fast_kernel<IdxT, 4, 8, true><<<grid, block, hsmem, st>>>(pack, batch, lpr_log2, status, stream, hot_rows, max_dim);
+      B2_CUDA_LAUNCH_CHECK("b2_embed_gather_fwd");
+      return B2_OK;
+    }
     if (unroll == 8) {
       const int grid = grid_for(b2_ceil_div(nitems, 8) << lpr_log2, block);
-      if (vec == 4) gather_fast_kernel<IdxT, 4, 8><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
-      else if (vec == 2) gather_fast_kernel<IdxT, 2, 8><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
-      else gather_fast_kernel<IdxT, 1, 8><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
+      if (vec == 4) gather_fast_kernel<IdxT, 4, 8, false><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream, 0, 0);
+      else if (vec == 2) gather_fast_kernel<IdxT, 2, 8, false><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream, 0, 0);
+      else gather_fast_kernel<IdxT, 1, 8, false><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream, 0, 0);
     } else {
       const int grid = grid_for(b2_ceil_div(nitems, 4) << lpr_log2, block);
-      if (vec == 4) gather_fast_kernel<IdxT, 4, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
-      else if (vec == 2) gather_fast_kernel<IdxT, 2, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
-      else gather_fast_kernel<IdxT, 1, 4><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream);
+      if (vec == 4) gather_fast_kernel<IdxT, 4, 4, false><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream, 0, 0);
+      else if (vec == 2) gather_fast_kernel<IdxT, 2, 4, false><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream, 0, 0);
+      else gather_fast_kernel<IdxT, 1, 4, false><<<grid, block, smem, st>>>(pack, batch, lpr_log2, status, stream, 0, 0);
     }
   } else {
     const int grid = grid_for(nitems << lpr_log2, block);
@@ -406,6 +441,13 @@ static int launch_scatter(const B2FieldPack& pack, int64_t batch, int vec, int m
 extern "C" B2_API int b2_embed_gather_fwd(const b2_field* fields, int nfields, int64_t batch,
                                    int idx_dtype, int elem_dtype, float* mean_count,
                                    int32_t* status, void* stream) {
+  return b2_embed_gather_hot_fwd(fields, nfields, batch, idx_dtype, elem_dtype, mean_count, status, 0, stream);
+}
+
+extern "C" B2_API int b2_embed_gather_hot_fwd(const b2_field* fields, int nfields, int64_t batch,
+                                       int idx_dtype, int elem_dtype, float* mean_count,
+                                       int32_t* status, int hot_rows, void* stream) {
+  B2_REQUIRE(hot_rows >= 0, "negative hot_rows");
   B2_REQUIRE(elem_dtype == B2_F32, "elem_dtype %d unsupported (only B2_F32)", elem_dtype);
   B2_REQUIRE(batch >= 0, "negative batch");
   if (batch == 0) return B2_OK;
@@ -419,9 +461,9 @@ extern "C" B2_API int b2_embed_gather_fwd(const b2_field* fields, int nfields, i
       B2_REQUIRE(mean_count != nullptr, "field %d: POOL_MEAN needs mean_count", i);
   cudaStream_t st = (cudaStream_t) stream;
   switch (idx_dtype) {
-    case B2_F64: return launch_gather<double>(pack, batch, vec, max_dim, any_pooled, mean_count, status, st);
-    case B2_I64: return launch_gather<int64_t>(pack, batch, vec, max_dim, any_pooled, mean_count, status, st);
-    case B2_I32: return launch_gather<int32_t>(pack, batch, vec, max_dim, any_pooled, mean_count, status, st);
+    case B2_F64: return launch_gather<double>(pack, batch, vec, max_dim, any_pooled, mean_count, status, hot_rows, st);
+    case B2_I64: return launch_gather<int64_t>(pack, batch, vec, max_dim, any_pooled, mean_count, status, hot_rows, st);
+    case B2_I32: return launch_gather<int32_t>(pack, batch, vec, max_dim, any_pooled, mean_count, status, hot_rows, st);
     default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
   }
 }

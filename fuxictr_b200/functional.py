@@ -101,6 +101,7 @@ class GatherPlan(object):
             f.out_offset = off
             off += f.out_width
         self.width = off
+        self.hot_rows = 0       # > 0: stage that many leading (most frequent) rows of every table in shared memory
         self.needs_count = any(f.seq_len > 1 and f.pool == B2_POOL_MEAN for f in self.fields)
         self.widths = [f.out_width for f in self.fields]
         self._descs = (b2_field * len(self.fields))()
@@ -161,8 +162,8 @@ class _EmbedGather(torch.autograd.Function):
         count = (torch.empty((len(plan.fields), max(batch, 1)), dtype=torch.float32, device=dev)
                  if plan.needs_count else None)
         descs = plan.fill(tables, idx_list, arena, batch)
-        _lib.call("b2_embed_gather_fwd", descs, len(plan.fields), batch, ctx_code(idx_list),
-                  B2_F32, _ptr(count), _ptr(status), _stream())
+        _lib.call("b2_embed_gather_hot_fwd", descs, len(plan.fields), batch, ctx_code(idx_list),
+                  B2_F32, _ptr(count), _ptr(status), int(plan.hot_rows), _stream())
         ctx.plan, ctx.idx_list, ctx.count, ctx.tables = plan, idx_list, count, tables
         return arena
 

@@ -114,6 +114,14 @@ typedef struct b2_field {
  */
 B2_API int b2_embed_gather_fwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype,
                         int elem_dtype, float* mean_count, int32_t* status, void* stream);
+/* Same, with the first `hot_rows` rows of every table staged once per CTA in shared memory and served
+ * from there (north_star "shared-memory staging of hot rows"): FuxiCTR's tokenizer numbers ids by
+ * descending frequency, so the small ids are the hot ones.  Applies when every field is one slot of one
+ * common dim (% 4) and the staging area fits 44 KB per CTA; otherwise identical to b2_embed_gather_fwd.
+ * The result is bit-identical either way. */
+B2_API int b2_embed_gather_hot_fwd(const b2_field* fields, int nfields, int64_t batch, int idx_dtype,
+                                   int elem_dtype, float* mean_count, int32_t* status, int hot_rows,
+                                   void* stream);
 
 /*
  * Backward of the fused gather: dense-gradient scatter-add with warp-level

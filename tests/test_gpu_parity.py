@@ -506,6 +506,28 @@ def test_scatter_linearity_and_idempotent_gather():
     assert close(lhs, rhs, RTOL)
 
 
+def test_gather_hot_row_staging_is_bit_identical():
+    """Shared-memory staging of the leading (most frequent) rows: same bytes out, Zipf-skewed ids that
+    mix staged rows, cold rows, the padding row and a table shorter than the staging depth."""
+    from fuxictr_b200 import functional as F2
+    sys.path.insert(0, ROOT)
+    import bench
+    D, B = 16, 32768
+    vocabs = [4000] * 20 + [9] + [250000] * 18            # one table with fewer rows than hot_rows
+    tables = [torch.randn(v, D, device="cuda") for v in vocabs]
+    ids = bench.zipf_ids(B, vocabs, 1.05, seed=3, device="cuda")
+    ids[::97, 0] = 0                                       # padding rows
+    idx = [ids[:, i] for i in range(len(vocabs))]
+    plan = F2.GatherPlan([F2.GatherField("C%d" % i, i, D, padding_idx=0) for i in range(len(vocabs))])
+    with torch.no_grad():
+        base = F2.embed_gather(plan, idx, tables).clone()
+        plan.hot_rows = 16
+        hot = F2.embed_gather(plan, idx, tables)
+    assert torch.equal(base, hot)
+    want = torch.cat([t[ids[:, i].long()] for i, t in enumerate(tables)], dim=1)
+    assert torch.equal(hot, want)
+
+
 # ------------------------------------------------------------------ tcgen05 tensor-core GEMM
 TC_SHAPES = [(128, 32, 32), (128, 96, 64), (256, 160, 128), (4096, 300, 624), (4096, 624, 300),
              (300, 624, 4096), (1000, 500, 432), (77, 45, 36), (129, 257, 1000), (8192, 624, 624)]
