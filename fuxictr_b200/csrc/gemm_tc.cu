@@ -116,15 +116,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   d |= (uint64_t) 2 << 61;                   // layout: SWIZZLE_128B
   return d;
 }
-// MN-major, 128-byte swizzle: the tile is a row of [32 MN-elements x BK k-rows] boxes (what one TMA
-// box writes: k-row r at r * 128 B, 8-row groups 1024 B apart = SBO), boxes BK * 128 B apart = LBO.
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t box_bytes) {
+// MN-major: the tile is a row of [128 bytes of MN-elements x bke k-rows] boxes (what one TMA box writes:
+// k-row r at r * 128 B), boxes box_bytes apart = LBO.
+//   16-bit operands: SWIZZLE_128B, swizzle atom = 8 k-rows (1024 B) = SBO.
+//   32-bit operands (tf32): the ONLY MN-major layout the tensor core accepts is SWIZZLE_128B_BASE32B
+//   (32-byte swizzle granules, atom = 4 k-rows = 512 B = SBO); its TMA twin is SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t box_bytes, int esz) {
   uint64_t d = 0;
   d |= (uint64_t) ((addr & 0x3FFFFu) >> 4);      // start address  [0,14)
   d |= (uint64_t) (box_bytes >> 4) << 16;        // leading byte offset [16,30): next 128-byte-wide MN block
-  d |= (uint64_t) (1024 >> 4) << 32;             // stride byte offset [32,46): next 8 k-rows
+  d |= (uint64_t) ((esz == 4 ? 512 : 1024) >> 4) << 32;   // stride byte offset [32,46): next swizzle atom along K
   d |= (uint64_t) 1 << 46;                       // descriptor version (sm_100)
-  d |= (uint64_t) 2 << 61;                       // layout: SWIZZLE_128B
+  d |= (uint64_t) (esz == 4 ? 1 : 2) << 61;      // layout: SWIZZLE_128B_BASE32B (1) / SWIZZLE_128B (2)
   return d;
 }
 // small(x) = rna_tf32(x - big(x)), big(x) = x with the 13 low mantissa bits cleared (what
@@ -286,10 +289,10 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         const uint32_t d_main = tmem_base + (uint32_t) (slot * p.bn);
         const uint32_t d_corr = tmem_base + (uint32_t) (nmain * p.bn);
         const uint32_t a_addr = smem_base + stage * stage_bytes;
-        const uint64_t adesc = p.a_mn ? make_smem_desc_mn(a_addr, box_bytes) : make_smem_desc(a_addr);
-        const uint64_t bdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_b, box_bytes) : make_smem_desc(a_addr + off_b);
-        const uint64_t asdesc = p.a_mn ? make_smem_desc_mn(a_addr + off_as, box_bytes) : make_smem_desc(a_addr + off_as);
-        const uint64_t bsdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_bs, box_bytes) : make_smem_desc(a_addr + off_bs);
+        const uint64_t adesc = p.a_mn ? make_smem_desc_mn(a_addr, box_bytes, p.esz) : make_smem_desc(a_addr);
+        const uint64_t bdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_b, box_bytes, p.esz) : make_smem_desc(a_addr + off_b);
+        const uint64_t asdesc = p.a_mn ? make_smem_desc_mn(a_addr + off_as, box_bytes, p.esz) : make_smem_desc(a_addr + off_as);
+        const uint64_t bsdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_bs, box_bytes, p.esz) : make_smem_desc(a_addr + off_bs);
         if (p.esz == 2) {       // bf16 operands: one pass on kind::f16, fp32 accumulation in TMEM
 #pragma unroll
           for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
@@ -651,7 +654,8 @@ static int encode_operand(CUtensorMap* map, const void* base, int64_t rows, int6
   }
   CUresult r = enc(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   (mn_major && esz == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return b2_fail(B2_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
   return B2_OK;
 }

@@ -482,7 +482,7 @@ def gemm_nt(a, b, out, bias=None, act=B2_ACT_NONE, mul=None, add=None, accumulat
 # torch bumps `_version` for in-place ops; updates through raw pointers (the fused arena optimizer,
 # CUDA-graph replays of it) are announced with bump_weight_epoch().
 _WEIGHT_EPOCH = [0]
-_SMALL_CACHE = weakref.WeakKeyDictionary()
+_SMALL_CACHE = {}      # id(weight) -> (key, aux, weakref to the weight)
 
 
 def bump_weight_epoch():
@@ -525,11 +525,12 @@ def weight_aux(w):
     if not w.is_contiguous():
         raise RuntimeError("tensor-core GEMM weights must be contiguous")
     key = (mode, w.data_ptr(), w._version, _WEIGHT_EPOCH[0], tuple(w.shape))
-    ent = _SMALL_CACHE.get(w)
-    if ent is not None and ent[0] == key:
+    ent = _SMALL_CACHE.get(id(w))
+    if ent is not None and ent[0] == key and ent[2]() is w:
         return ent[1]
     aux = make_aux(w.detach())
-    _SMALL_CACHE[w] = (key, aux)
+    wid = id(w)
+    _SMALL_CACHE[wid] = (key, aux, weakref.ref(w, lambda _r, wid=wid: _SMALL_CACHE.pop(wid, None)))
     return aux
 
 

@@ -607,7 +607,7 @@ def test_gemm_tc_mn_major_operands_vs_fp64(M, N, K, a_mn, b_mn, mode):
     assert not torch.isnan(out).any()
     if mode == "bf16":      # checker: the same contraction of the bf16-rounded operands, in float64
         ref = a.bfloat16().double() @ b.bfloat16().double().t()
-        assert rel_err(out, ref) <= 2e-6
+        assert rel_err(out, ref) <= 1e-5          # fp32 (truncating) accumulation of up to 8192 exact products
         assert torch.equal(out_aux, out.bfloat16())          # the epilogue's bf16 copy is RN(out)
     else:
         err = rel_err(out, ref)

@@ -115,16 +115,31 @@ def test_unmodified_model_zoo_runs_on_the_kernels(name, expid, dataset):
             for layer in EXPECT_CALLS[name]:
                 assert after.get(layer, 0) > before.get(layer, 0), "%s did not take the kernel path" % layer
             cpu_model.train(), gpu_model.train()
-            for b in batches:
+            w0 = {k: v.detach().clone() for k, v in cpu_model.state_dict().items()}
+            for step, b in enumerate(batches):
                 l_ref = cpu_model.train_step(b)         # the reference's own train_step, both sides
                 l_gpu = gpu_model.train_step(b)
                 assert abs(float(l_gpu) - float(l_ref)) <= 1e-5 * abs(float(l_ref)) + 1e-7
+                if step == 0:       # identical weights going in: every parameter gradient within 1e-5 (north_star)
+                    g_ref = {k: p.grad for k, p in cpu_model.named_parameters() if p.grad is not None}
+                    g_gpu = {k: p.grad for k, p in gpu_model.named_parameters() if p.grad is not None}
+                    assert set(g_ref) == set(g_gpu)
+                    scale = max(float(g.abs().max()) for g in g_ref.values())
+                    for k in g_ref:
+                        err = float((g_gpu[k].cpu() - g_ref[k]).abs().max())
+                        assert err <= 1e-5 * max(float(g_ref[k].abs().max()), 1e-3 * scale), "grad %s: %g" % (k, err)
             sd_ref, sd_gpu = cpu_model.state_dict(), gpu_model.state_dict()
             for k in keys:
                 if not sd_ref[k].dtype.is_floating_point:
                     assert torch.equal(sd_gpu[k].cpu(), sd_ref[k]), k
                     continue
-                assert rel_err(sd_gpu[k], sd_ref[k]) <= 1e-5, "%s after 3 train_steps" % k
+                # Adam divides by sqrt(v): a gradient component that nearly cancels over the batch turns a
+                # 1e-7 summation-order difference into a visible one, so the weights are held to 0.1 % of the
+                # distance the optimizer moved them (3 steps of lr), not to 1e-5 of their magnitude
+                moved = 3 * params["learning_rate"]
+                err = float((sd_gpu[k].cpu() - sd_ref[k]).abs().max())
+                assert err <= 1e-3 * moved + 1e-5 * float((sd_ref[k] - w0[k]).abs().max()), \
+                    "%s after 3 train_steps: %g" % (k, err)
         finally:
             patch.disable()
             logging.disable(logging.NOTSET)
