@@ -248,12 +248,24 @@ front_reduce_kernel(const float* __restrict__ emb, const float* __restrict__ lrw
 __global__ void __launch_bounds__(256)
 front_gprep_kernel(const float* __restrict__ gx, const float* __restrict__ emb,
                    const float* __restrict__ sums, const float* __restrict__ glogit, int64_t batch,
-                   int F, int dim, int want_fm, float* __restrict__ gemb, float* __restrict__ glogit_out) {
+                   int F, int dim, int want_fm, float* __restrict__ gemb, float* __restrict__ glogit_out,
+                   float* __restrict__ gbias) {
+  __shared__ float red[32];
   const int64_t n4 = batch * (int64_t) F * dim / 4;
   const int d4 = dim / 4;
-  if (glogit_out != nullptr)      // publish the logit gradient where the row owners can read it (LR tables)
-    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < batch; i += (int64_t) gridDim.x * blockDim.x)
-      glogit_out[i] = __ldg(glogit + i);
+  if (glogit_out != nullptr || gbias != nullptr) {
+    // publish the logit gradient where the row owners can read it (LR tables); its sum is the LR bias gradient
+    float acc = 0.f;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < batch; i += (int64_t) gridDim.x * blockDim.x) {
+      const float g = __ldg(glogit + i);
+      if (glogit_out != nullptr) glogit_out[i] = g;
+      acc += g;
+    }
+    if (gbias != nullptr) {
+      const float t = b2_block_sum(acc, red);
+      if (threadIdx.x == 0 && t != 0.f) b2_red_add(gbias, t);
+    }
+  }
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t) gridDim.x * blockDim.x) {
     const int64_t bf = i / d4;
@@ -407,16 +419,20 @@ extern "C" B2_API int b2_front_reduce(const float* emb, const float* lrw, const 
 
 extern "C" B2_API int b2_front_gprep(const float* gx, const float* emb, const float* sums, const float* glogit,
                                      int64_t batch, int nfields, int dim, int want_fm, float* gemb,
-                                     float* glogit_out, void* stream) {
+                                     float* glogit_out, float* gbias, int gbias_is_zero, void* stream) {
   B2_REQUIRE(gemb != nullptr, "NULL output");
-  B2_REQUIRE(glogit_out == nullptr || glogit != nullptr, "glogit_out needs glogit");
+  B2_REQUIRE((glogit_out == nullptr && gbias == nullptr) || glogit != nullptr, "glogit_out / gbias need glogit");
+  if (gbias != nullptr && !gbias_is_zero) {
+    cudaError_t e = cudaMemsetAsync(gbias, 0, sizeof(float), (cudaStream_t) stream);
+    if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_front_gprep: memset: %s", cudaGetErrorString(e));
+  }
   B2_REQUIRE(dim >= 4 && dim % 4 == 0 && nfields >= 1, "bad dim/nfields");
   B2_REQUIRE(!want_fm || (emb && sums && glogit), "want_fm needs emb, sums, glogit");
   if (batch <= 0) return B2_OK;
   const int64_t n4 = batch * (int64_t) nfields * dim / 4;
   const int grid = grid_for(n4, 256);
   front_gprep_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(gx, emb, sums, glogit, batch, nfields, dim, want_fm, gemb,
-                                                             glogit_out);
+                                                             glogit_out, gbias);
   B2_CUDA_LAUNCH_CHECK("b2_front_gprep");
   return B2_OK;
 }

@@ -201,10 +201,11 @@ class ShardedFront(object):
         return emb, logit, sums
 
     # -- backward phases ------------------------------------------------------------------------
-    def phase_gprep(self, gx, emb, sums, glogit):
+    def phase_gprep(self, gx, emb, sums, glogit, gbias=None):
         _lib.call("b2_front_gprep", F2._ptr(gx), F2._ptr(emb), F2._ptr(sums), F2._ptr(glogit), self.B, self.F,
                   self.dim, 1 if self.want_fm else 0, F2._ptr(self.gemb),
-                  F2._ptr(self.glogit) if glogit is not None else None, F2._stream())
+                  F2._ptr(self.glogit) if glogit is not None else None, F2._ptr(gbias),
+                  1 if (gbias is not None and F2._is_zeroed(gbias)) else 0, F2._stream())
 
     def phase_pull(self, emb_grads, lr_grads):
         g = self.group
@@ -244,16 +245,15 @@ class _ShardedFrontFn(torch.autograd.Function):
         gl = None
         if needs_logit:
             gl = (torch.zeros(front.B, device="cuda") if glogit is None else F2._f32c(glogit).view(-1))
-        front.phase_gprep(gx, emb, sums, gl)
+        gbias = None
+        if bias is not None and bias.requires_grad:
+            gbias = F2._grad_buffer(bias, zero=False)
+        front.phase_gprep(gx, emb, sums, gl, gbias)      # also: LR bias gradient = sum_b glogit[b]
         g.barrier()                      # every rank's gradient rows are ready to be pulled
         n = front.F
         egrads = [(F2._grad_buffer(t, zero=True) if t.requires_grad else None) for t in tables[:n]]
         lgrads = [(F2._grad_buffer(t, zero=True) if t.requires_grad else None) for t in tables[n:]]
         front.phase_pull(egrads, lgrads if front.lr_tables else None)
-        gbias = None
-        if bias is not None and bias.requires_grad:
-            gbias = F2._grad_buffer(bias, zero=False)
-            gbias.copy_(gl.sum().view(1))
         return (None, None, gbias) + tuple(egrads) + tuple(lgrads)
 
 

@@ -262,10 +262,12 @@ B2_API int b2_peer_bcast(const void* src, int64_t nbytes, void* const* peer_dst,
 B2_API int b2_front_reduce(const float* emb, const float* lrw, const float* bias, int64_t batch,
                            int nfields, int dim, int want_fm, float* logit, float* sums, void* stream);
 /* Before the pull: gemb[b,f,:] = gx[b,f,:] + glogit[b] * (sums[b,:] - emb[b,f,:]) (2nd term if want_fm);
- * glogit_out (optional, peer-visible) receives a copy of glogit for the owners of the LR rows. */
+ * glogit_out (optional, peer-visible) receives a copy of glogit for the owners of the LR rows;
+ * gbias (optional, 1 float) receives sum_b glogit[b], the LogisticRegression bias gradient (cleared by the
+ * call unless gbias_is_zero). */
 B2_API int b2_front_gprep(const float* gx, const float* emb, const float* sums, const float* glogit,
                           int64_t batch, int nfields, int dim, int want_fm, float* gemb, float* glogit_out,
-                          void* stream);
+                          float* gbias, int gbias_is_zero, void* stream);
 
 /*
  * InnerProductInteraction (layers/interactions/inner_product.py:55-70).
