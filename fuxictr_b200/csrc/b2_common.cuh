@@ -28,7 +28,36 @@ int b2_fail(int code, const char* fmt, ...);
 
 static inline int64_t b2_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (opt-in: B2_PDL=1) --------------------------------------------
+// The step is a chain of ~45 short kernels; with PDL a kernel's CTAs are scheduled while its predecessor
+// drains and sit at griddepcontrol.wait (which returns only when the predecessor has COMPLETED and its
+// writes are visible), so the launch latency — and, for the GEMM, the barrier/TMEM/tensormap prologue —
+// overlaps the predecessor's tail.  Captured into CUDA graphs as programmatic dependency edges.
+#include <stdlib.h>
+static inline bool b2_pdl_on() {
+  static const bool on = [] { const char* e = getenv("B2_PDL"); return e != nullptr && atoi(e) != 0; }();
+  return on;
+}
+#define B2_LAUNCH(kernel, grid, block, smem, st, ...)                                             \
+  do {                                                                                              \
+    if (b2_pdl_on()) {                                                                              \
+      cudaLaunchConfig_t cfg__ = {};                                                                \
+      cfg__.gridDim = dim3(grid); cfg__.blockDim = dim3(block);                                     \
+      cfg__.dynamicSmemBytes = (size_t) (smem); cfg__.stream = (st);                                \
+      cudaLaunchAttribute at__[1];                                                                  \
+      at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+      at__[0].val.programmaticStreamSerializationAllowed = 1;                                       \
+      cfg__.attrs = at__; cfg__.numAttrs = 1;                                                       \
+      cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                                              \
+    } else {                                                                                        \
+      kernel<<<grid, block, smem, st>>>(__VA_ARGS__);                                               \
+    }                                                                                               \
+  } while (0)
+
 // ---- device helpers ----------------------------------------------------------
+// No-ops for a kernel launched without the PDL attribute.
+__device__ __forceinline__ void b2_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void b2_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float b2_warp_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   v += __shfl_xor_sync(0xffffffffu, v, 8);

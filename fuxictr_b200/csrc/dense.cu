@@ -298,6 +298,8 @@ logit_bce_kernel(const float* __restrict__ t0, const float* __restrict__ t1,
                  const float* __restrict__ t2, const float* __restrict__ t3,
                  const float* __restrict__ label, int64_t batch, float* __restrict__ y_pred,
                  float* __restrict__ loss, float* __restrict__ glogit) {
+  b2_pdl_wait();
+  b2_pdl_trigger();
   __shared__ float red[32];
   const float inv_b = 1.f / (float) batch;
   float part = 0.f;
@@ -338,7 +340,7 @@ extern "C" B2_API int b2_logit_bce_fwd(const float* t0, const float* t1, const f
   }
   int64_t blocks = b2_ceil_div(batch, 256);
   if (blocks > B2_NUM_SMS * 4) blocks = B2_NUM_SMS * 4;
-  logit_bce_kernel<<<(int) blocks, 256, 0, st>>>(t0, t1, t2, t3, label, batch, y_pred, loss, glogit);
+  B2_LAUNCH(logit_bce_kernel, (int) blocks, 256, 0, st, t0, t1, t2, t3, label, batch, y_pred, loss, glogit);
   B2_CUDA_LAUNCH_CHECK("b2_logit_bce_fwd");
   return B2_OK;
 }
@@ -349,6 +351,8 @@ extern "C" B2_API int b2_logit_bce_fwd(const float* t0, const float* t1, const f
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+  b2_pdl_wait();
+  b2_pdl_trigger();
   __shared__ float red[32];
   float acc = 0.f;
   const int64_t n4 = n >> 2;
@@ -373,7 +377,7 @@ extern "C" B2_API int b2_sumsq(const float* g, int64_t n, float* out, void* stre
   int64_t blocks = b2_ceil_div(n >> 2, 256 * 4);
   if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(g, n, out);
+  B2_LAUNCH(sumsq_kernel, (int) blocks, 256, 0, (cudaStream_t) stream, g, n, out);
   B2_CUDA_LAUNCH_CHECK("b2_sumsq");
   return B2_OK;
 }
@@ -394,6 +398,8 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, const float* __restrict__ sumsq, float max_norm,
             float lr, float beta1, float beta2, float eps, const int64_t* __restrict__ step_dev,
             int zero_grad, const B2AdamSched* __restrict__ sched) {
+  b2_pdl_wait();
+  b2_pdl_trigger();
   __shared__ B2AdamConst sc;
   __shared__ float s_clip, s_step, s_ibc2;
   if (threadIdx.x == 0) {
@@ -458,9 +464,9 @@ extern "C" B2_API int b2_adam_step(float* p, float* g, float* m, float* v, int64
   int64_t blocks = b2_ceil_div(n >> 2, 256 * 2);
   if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(p, g, m, v, n, sumsq, max_norm, lr,
-                                                              beta1, beta2, eps, step_dev,
-                                                              zero_grad, nullptr);
+  const B2AdamSched* no_sched = nullptr;
+  B2_LAUNCH(adam_kernel, (int) blocks, 256, 0, (cudaStream_t) stream, p, g, m, v, n, sumsq, max_norm, lr, beta1, beta2,
+            eps, step_dev, zero_grad, no_sched);
   B2_CUDA_LAUNCH_CHECK("b2_adam_step");
   return B2_OK;
 }
@@ -485,9 +491,9 @@ extern "C" B2_API int b2_adam_step_sched(float* p, float* g, float* m, float* v,
   int64_t blocks = b2_ceil_div(n >> 2, 256 * 2);
   if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(p, g, m, v, n, sumsq, max_norm, 0.f, beta1, beta2,
-                                                              eps, step_dev, zero_grad,
-                                                              reinterpret_cast<const B2AdamSched*>(sched));
+  const B2AdamSched* sched_tab = reinterpret_cast<const B2AdamSched*>(sched);
+  B2_LAUNCH(adam_kernel, (int) blocks, 256, 0, (cudaStream_t) stream, p, g, m, v, n, sumsq, max_norm, 0.f, beta1, beta2,
+            eps, step_dev, zero_grad, sched_tab);
   B2_CUDA_LAUNCH_CHECK("b2_adam_step_sched");
   return B2_OK;
 }

@@ -31,11 +31,13 @@ front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
                  const float* __restrict__ bias, float* __restrict__ logit_out,
                  float* __restrict__ sum_out, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SmemFields sf = b2_stage_fields(emb, smem_raw);
+  const SmemFields sf = b2_stage_fields(emb, smem_raw);     // kernel parameters -> shared memory only
   SmemFields lf;
   lf.f = nullptr;
   lf.slot_start = nullptr;
   if (has_lr) lf = b2_stage_fields(lr, smem_raw + ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15));
+  b2_pdl_trigger();
+  b2_pdl_wait();
   const int F = emb.nfields;
   const int LPR = 1 << lpr_log2;
   const int rows_per_pass = 32 >> lpr_log2;
@@ -181,6 +183,8 @@ front_bwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
   lf.f = nullptr;
   lf.slot_start = nullptr;
   if (has_lr) lf = b2_stage_fields(lr, smem_raw + ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15));
+  b2_pdl_trigger();
+  b2_pdl_wait();
   const int F = emb.nfields;
   const int LPR = 1 << lpr_log2;
   const int lane = threadIdx.x & 31;
@@ -293,12 +297,10 @@ int launch_front_fwd(const B2FieldPack& emb, const B2FieldPack& lr, const b2_laz
   const size_t smem = ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15) + pack_smem_bytes(emb.nfields) + 16;
   const int grid = grid_for(batch * 32, 256);
   const int passes = (emb.nfields + (32 >> lpr_log2) - 1) / (32 >> lpr_log2);
-  if (passes <= 2)
-    front_fwd_kernel<IdxT, 2><<<grid, 256, smem, st>>>(emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
-  else if (passes <= 5)
-    front_fwd_kernel<IdxT, 5><<<grid, 256, smem, st>>>(emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
-  else
-    front_fwd_kernel<IdxT, 8><<<grid, 256, smem, st>>>(emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
+  auto kfn = front_fwd_kernel<IdxT, 8>;
+  if (passes <= 2) kfn = front_fwd_kernel<IdxT, 2>;
+  else if (passes <= 5) kfn = front_fwd_kernel<IdxT, 5>;
+  B2_LAUNCH(kfn, grid, 256, smem, st, emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
   B2_CUDA_LAUNCH_CHECK("b2_front_fwd");
   return B2_OK;
 }
@@ -311,8 +313,8 @@ int launch_front_bwd(const B2FieldPack& emb, const B2FieldPack& lr, const b2_laz
   int lpr_log2 = next_pow2_log2((dim + 3) / 4);
   const size_t smem = ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15) + pack_smem_bytes(emb.nfields) + 16;
   const int grid = grid_for((batch * (int64_t) emb.nfields) << lpr_log2, 256);
-  front_bwd_kernel<IdxT><<<grid, 256, smem, st>>>(emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, emb_saved,
-                                                 gx, sums, glogit, gbias);
+  auto kfn = front_bwd_kernel<IdxT>;
+  B2_LAUNCH(kfn, grid, 256, smem, st, emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, emb_saved, gx, sums, glogit, gbias);
   B2_CUDA_LAUNCH_CHECK("b2_front_bwd");
   return B2_OK;
 }

@@ -230,6 +230,10 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above touched only shared memory, TMEM and the kernel parameters; from here on the
+  // predecessor's outputs are read.  Let the successor begin ITS prologue once every CTA got this far.
+  b2_pdl_trigger();
+  b2_pdl_wait();
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -434,6 +438,8 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, float* __restrict__ small, int64_t n) {
+  b2_pdl_wait();
+  b2_pdl_trigger();
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t) gridDim.x * blockDim.x) {
     small[i] = tf32_small(x[i]);
@@ -478,6 +484,8 @@ __global__ void __launch_bounds__(256)
 prep_operand_kernel(const float* __restrict__ x, const float* __restrict__ y, int act, int64_t R,
                     int64_t C, int64_t ld_in, float* __restrict__ out, float* __restrict__ out_small,
                     float* __restrict__ outT, float* __restrict__ outT_small, float* __restrict__ colsum) {
+  b2_pdl_wait();
+  b2_pdl_trigger();
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int64_t c0 = (int64_t) blockIdx.x * 32, r0 = (int64_t) blockIdx.y * 32;
@@ -533,6 +541,8 @@ prep_operand_kernel(const float* __restrict__ x, const float* __restrict__ y, in
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                 int64_t M, int K, int act, float* __restrict__ y) {
+  b2_pdl_wait();
+  b2_pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
@@ -556,6 +566,8 @@ head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
                 const float* __restrict__ gy, int64_t M, int K, int act, int64_t rows_per_cta,
                 float* __restrict__ gx, float* __restrict__ gw, float* __restrict__ gb, int prev_act,
                 float* __restrict__ gx_small, float* __restrict__ gb_prev) {
+  b2_pdl_wait();
+  b2_pdl_trigger();
   extern __shared__ float sgw[];  // K partial sums of gw, then K partial sums of gb_prev
   __shared__ float red[32];
   float* sgp = sgw + K;
@@ -765,7 +777,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   if (attr_rc != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(attr_rc));
   dim3 grid((unsigned) tiles_m, (unsigned) b2_ceil_div(N, best_bn), (unsigned) splits);
   B2_REQUIRE(grid.y <= 65535, "N too large for this launch geometry");
-  tc::gemm_tf32_kernel<<<grid, tc::NTHREADS, smem, st>>>(p);
+  B2_LAUNCH(tc::gemm_tf32_kernel, grid, tc::NTHREADS, smem, st, p);
   B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
   return B2_OK;
 }
@@ -814,7 +826,7 @@ extern "C" B2_API int b2_split_tf32(const float* x, float* small, int64_t n, voi
   if (n <= 0) return B2_OK;
   int64_t blocks = b2_ceil_div(n, 256);
   if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
-  tc::split_tf32_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(x, small, n);
+  B2_LAUNCH(tc::split_tf32_kernel, (int) blocks, 256, 0, (cudaStream_t) stream, x, small, n);
   B2_CUDA_LAUNCH_CHECK("b2_split_tf32");
   return B2_OK;
 }
@@ -845,7 +857,7 @@ extern "C" B2_API int b2_prep_operand(const float* x, const float* y, int act, i
   if (R == 0 || C == 0) return B2_OK;
   dim3 grid((unsigned) b2_ceil_div(C, 32), (unsigned) b2_ceil_div(R, 32));
   B2_REQUIRE(grid.y <= 65535, "too many rows for this launch geometry");
-  tc::prep_operand_kernel<<<grid, 256, 0, st>>>(x, y, act, R, C, C, out, out_small, outT, outT_small, colsum);
+  B2_LAUNCH(tc::prep_operand_kernel, grid, 256, 0, st, x, y, act, R, C, C, out, out_small, outT, outT_small, colsum);
   B2_CUDA_LAUNCH_CHECK("b2_prep_operand");
   return B2_OK;
 }
@@ -857,7 +869,7 @@ extern "C" B2_API int b2_head_fwd(const float* x, const float* w, const float* b
   if (M <= 0) return B2_OK;
   int64_t blocks = b2_ceil_div(M * 32, 256);
   if (blocks > (int64_t) B2_NUM_SMS * 8) blocks = (int64_t) B2_NUM_SMS * 8;
-  tc::head_fwd_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(x, w, b, M, K, act, y);
+  B2_LAUNCH(tc::head_fwd_kernel, (int) blocks, 256, 0, (cudaStream_t) stream, x, w, b, M, K, act, y);
   B2_CUDA_LAUNCH_CHECK("b2_head_fwd");
   return B2_OK;
 }
@@ -889,8 +901,9 @@ extern "C" B2_API int b2_head_bwd_ex(const float* x, const float* w, const float
   if (ctas > b2_ceil_div(M, 8)) ctas = b2_ceil_div(M, 8);
   const int64_t rows_per_cta = b2_ceil_div(M, ctas);
   ctas = b2_ceil_div(M, rows_per_cta);
-  tc::head_bwd_kernel<<<(int) ctas, 256, 2 * sizeof(float) * (size_t) K, st>>>(
-      x, w, (act == B2_ACT_NONE) ? nullptr : y, gy, M, K, act, rows_per_cta, gx, gw, gb, prev_act, gx_small, gb_prev);
+  const float* y_arg = (act == B2_ACT_NONE) ? nullptr : y;
+  B2_LAUNCH(tc::head_bwd_kernel, (int) ctas, 256, 2 * sizeof(float) * (size_t) K, st,
+            x, w, y_arg, gy, M, K, act, rows_per_cta, gx, gw, gb, prev_act, gx_small, gb_prev);
   B2_CUDA_LAUNCH_CHECK("b2_head_bwd");
   return B2_OK;
 }
