@@ -100,6 +100,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// One elected lane of a fully converged warp (elect.sync): unlike `lane == 0`, the compiler knows the
+// enclosing control flow is warp-uniform, so descriptors / coordinates stay in uniform registers and
+// every UTCHMMA / UTMALDG is a single instruction instead of a per-instruction election loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -236,14 +250,15 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   b2_pdl_wait();
 
   if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    // ---------------- TMA producer (the warp loops converged; one elected lane issues) ----------------
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(empty0 + 8 * stage, phase ^ 1, 0);
         const uint32_t a_dst = smem_base + stage * stage_bytes;
         const uint32_t full = full0 + 8 * stage;
+        if (elect_one()) {
         mbar_expect_tx(full, stage_bytes);
         // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products.
         // K-major operand: one box (BK k-columns x rows).  MN-major operand: one box per 32 rows
@@ -261,12 +276,14 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
             for (int j = 0; j < p.bn / mnb; ++j) tma_load_2d(b_t + j * box_bytes, &p.map_b[s], full, n0 + mnb * j, kb * bke);
           }
         }
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer (one thread) ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (the warp loops converged; one elected lane issues) ----------------
+    {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N = bn, M = 128
       const uint32_t fmt = (p.esz == 2) ? 1u : 2u;   // operand format: kind::f16 1 = BF16; kind::tf32 2 = TF32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.a_mn ? 1 : 0) << 15) |
@@ -282,40 +299,63 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       // the magnitude of the accumulator.  For 3xTF32 the K range of the main product is
       // therefore cut into `nmain` chains held in separate TMEM column ranges, and the two small
       // correction products get a range of their own; the epilogue adds the ranges in fp32 RN.
-      int stage = 0;
-      uint32_t phase = 0;
+      //
+      // This ONE thread is the instruction stream behind every MMA of the CTA, so its scalar work per
+      // k-block is on the critical path: descriptors are built once (stage 0) and advanced by 32-bit
+      // adds on their low word (the 14-bit start-address field never carries), the chain boundaries
+      // are precomputed, and the bf16 / TF32 / 3xTF32 loops are separate.
       const int nkb = kb_end - kb_begin;
+      // chain c covers k-blocks [ceil(c nkb / nmain), ceil((c+1) nkb / nmain)): divisions only at the <= 4 boundaries
+      int this_start = 0, next_start = (nkb + nmain - 1) / nmain;
+      const uint64_t a0 = p.a_mn ? make_smem_desc_mn(smem_base, box_bytes, p.esz) : make_smem_desc(smem_base);
+      const uint64_t b0 = p.b_mn ? make_smem_desc_mn(smem_base + off_b, box_bytes, p.esz) : make_smem_desc(smem_base + off_b);
+      const uint64_t as0 = p.a_mn ? make_smem_desc_mn(smem_base + off_as, box_bytes, p.esz) : make_smem_desc(smem_base + off_as);
+      const uint64_t bs0 = p.b_mn ? make_smem_desc_mn(smem_base + off_bs, box_bytes, p.esz) : make_smem_desc(smem_base + off_bs);
+      const uint32_t a_hi = (uint32_t) (a0 >> 32), b_hi = (uint32_t) (b0 >> 32);
+      const uint32_t as_hi = (uint32_t) (as0 >> 32), bs_hi = (uint32_t) (bs0 >> 32);
+      const uint32_t ak = (uint32_t) a_kstep, bk = (uint32_t) b_kstep, stage_units = stage_bytes >> 4;
+      const uint32_t d_corr = tmem_base + (uint32_t) (nmain * p.bn);
+#define B2_DESC(hi, lo) ((((uint64_t) (hi)) << 32) | (uint64_t) (uint32_t) (lo))
+      int stage = 0, slot = 0;
+      uint32_t phase = 0, so = 0;      // so: this stage's offset in descriptor units
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(full0 + 8 * stage, phase, 1);
         tc_fence_after();
-        const int slot = (int) (((long long) i * nmain) / nkb);
-        const bool first = (i == (int) (((long long) slot * nkb + nmain - 1) / nmain));
+        if (i == next_start) {
+          ++slot;
+          this_start = next_start;
+          next_start = ((slot + 1) * nkb + nmain - 1) / nmain;
+        }
+        const uint32_t keep = (i == this_start) ? 0u : 1u;      // first k-block of a chain overwrites
         const uint32_t d_main = tmem_base + (uint32_t) (slot * p.bn);
-        const uint32_t d_corr = tmem_base + (uint32_t) (nmain * p.bn);
-        const uint32_t a_addr = smem_base + stage * stage_bytes;
-        const uint64_t adesc = p.a_mn ? make_smem_desc_mn(a_addr, box_bytes, p.esz) : make_smem_desc(a_addr);
-        const uint64_t bdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_b, box_bytes, p.esz) : make_smem_desc(a_addr + off_b);
-        const uint64_t asdesc = p.a_mn ? make_smem_desc_mn(a_addr + off_as, box_bytes, p.esz) : make_smem_desc(a_addr + off_as);
-        const uint64_t bsdesc = p.b_mn ? make_smem_desc_mn(a_addr + off_bs, box_bytes, p.esz) : make_smem_desc(a_addr + off_bs);
+        const uint32_t al = (uint32_t) a0 + so, bl = (uint32_t) b0 + so;
+        if (elect_one()) {
         if (p.esz == 2) {       // bf16 operands: one pass on kind::f16, fp32 accumulation in TMEM
 #pragma unroll
           for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
-            umma_bf16(d_main, adesc + (uint64_t) k * a_kstep, bdesc + (uint64_t) k * b_kstep, idesc, (!first || k > 0) ? 1u : 0u);
-        } else {
+            umma_bf16(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep);
+        } else if (!x3) {
 #pragma unroll
-        for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
-          const uint64_t ka = (uint64_t) k * a_kstep, kb_ = (uint64_t) k * b_kstep;
-          umma_tf32(d_main, adesc + ka, bdesc + kb_, idesc, (!first || k > 0) ? 1u : 0u);      // A_big . B_big
-          if (x3) {
-            umma_tf32(d_corr, adesc + ka, bsdesc + kb_, idesc, (i > 0 || k > 0) ? 1u : 0u);   // A_big . B_small
-            umma_tf32(d_corr, asdesc + ka, bdesc + kb_, idesc, 1u);                            // A_small . B_big
+          for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
+            umma_tf32(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep);
+        } else {
+          const uint32_t asl = (uint32_t) as0 + so, bsl = (uint32_t) bs0 + so;
+#pragma unroll
+          for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
+            const uint64_t ad = B2_DESC(a_hi, al + k * ak), bd = B2_DESC(b_hi, bl + k * bk);
+            umma_tf32(d_main, ad, bd, idesc, (k > 0) ? 1u : keep);                                       // A_big . B_big
+            umma_tf32(d_corr, ad, B2_DESC(bs_hi, bsl + k * bk), idesc, (i > 0 || k > 0) ? 1u : 0u);     // A_big . B_small
+            umma_tf32(d_corr, B2_DESC(as_hi, asl + k * ak), bd, idesc, 1u);                              // A_small . B_big
           }
         }
-        }
         umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (i == nkb - 1) umma_commit(tmem_full);  // ... and the last one: accumulator complete
+        }
+        __syncwarp();
+        so += stage_units;
+        if (++stage == STAGES) { stage = 0; phase ^= 1; so = 0; }
       }
-      umma_commit(tmem_full);  // accumulator complete
+#undef B2_DESC
     }
   } else {
     // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----------------
