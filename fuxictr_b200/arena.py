@@ -66,6 +66,7 @@ class ParamArena(object):
         self.G = self._G_ext[:off]
         self._G_ext._b2_arena = self          # lets a kernel wrapper recognise a slice of this (zeroed) arena
         self.params = uniq
+        self.tail_params = uniq[n_first:]      # the dense (non-`first`) parameters, contiguous from tail_offset
         self.step_id = 0
         self.grads_are_zero = True
         with torch.no_grad():

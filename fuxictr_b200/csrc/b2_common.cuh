@@ -111,6 +111,17 @@ __device__ __forceinline__ void b2_red_add(float* p, float x) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(x) : "memory");
 }
 
+// 3xTF32 split: small(x) = rna_tf32(x - big(x)), big(x) = x with the 13 low mantissa bits cleared (what
+// kind::tf32 reads from a raw fp32 operand).  x - big(x) is exact; rounding it to a tf32-representable
+// value HERE (round-to-nearest) makes the hardware truncation of the small operand a no-op, so the
+// residual of the split is unbiased instead of always toward zero.
+__device__ __forceinline__ float b2_tf32_small(float v) {
+  const float big = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - big));
+  return __uint_as_float(r);
+}
+
 // Index fetch with the reference's `.long()` semantics (feature_embedding.py:284):
 // float64 ids are truncated toward zero.
 template <typename IdxT>

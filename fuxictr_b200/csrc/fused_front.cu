@@ -29,7 +29,7 @@ front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
                  const __grid_constant__ b2_lazy_ctx lz, int lazy,
                  int64_t batch, int dim, int lpr_log2, int has_lr, int want_fm,
                  const float* __restrict__ bias, float* __restrict__ logit_out,
-                 float* __restrict__ sum_out, int32_t* __restrict__ status) {
+                 float* __restrict__ sum_out, int32_t* __restrict__ status, int64_t small_delta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemFields sf = b2_stage_fields(emb, smem_raw);     // kernel parameters -> shared memory only
   SmemFields lf;
@@ -137,7 +137,11 @@ front_fwd_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant_
         if (f < F) {
           if (lane_on) {
             const b2_field& fd = sf.f[f];
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(fd.out) + b * fd.out_stride + e) = v[u];
+            float* op = reinterpret_cast<float*>(fd.out) + b * fd.out_stride + e;
+            *reinterpret_cast<float4*>(op) = v[u];
+            if (small_delta != 0)    // the 3xTF32 small part of the first GEMM's A operand, born with the rows
+              *reinterpret_cast<float4*>(op + small_delta) = make_float4(b2_tf32_small(v[u].x), b2_tf32_small(v[u].y),
+                                                                        b2_tf32_small(v[u].z), b2_tf32_small(v[u].w));
           }
           s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
           q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y);
@@ -292,7 +296,7 @@ template <typename IdxT>
 int launch_front_fwd(const B2FieldPack& emb, const B2FieldPack& lr, const b2_lazy_ctx& lz, int lazy,
                      int64_t batch, int dim, int has_lr,
                      int want_fm, const float* bias, float* logit_out, float* sum_out, int32_t* status,
-                     cudaStream_t st) {
+                     int64_t small_delta, cudaStream_t st) {
   int lpr_log2 = next_pow2_log2((dim + 3) / 4);
   const size_t smem = ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15) + pack_smem_bytes(emb.nfields) + 16;
   const int grid = grid_for(batch * 32, 256);
@@ -300,7 +304,7 @@ int launch_front_fwd(const B2FieldPack& emb, const B2FieldPack& lr, const b2_laz
   auto kfn = front_fwd_kernel<IdxT, 8>;
   if (passes <= 2) kfn = front_fwd_kernel<IdxT, 2>;
   else if (passes <= 5) kfn = front_fwd_kernel<IdxT, 5>;
-  B2_LAUNCH(kfn, grid, 256, smem, st, emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status);
+  B2_LAUNCH(kfn, grid, 256, smem, st, emb, lr, lz, lazy, batch, dim, lpr_log2, has_lr, want_fm, bias, logit_out, sum_out, status, small_delta);
   B2_CUDA_LAUNCH_CHECK("b2_front_fwd");
   return B2_OK;
 }
@@ -357,9 +361,16 @@ void fill_pack(B2FieldPack& pack, const b2_field* fields, int nfields) {
 extern "C" B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* lr_fields, int nfields,
                                    int64_t batch, int idx_dtype, int want_fm, const float* bias,
                                    float* logit_out, float* sum_out, int32_t* status,
-                                   const b2_lazy_ctx* lazy, void* stream) {
+                                   const b2_lazy_ctx* lazy, float* emb_small, void* stream) {
   int rc = check_front(emb_fields, lr_fields, nfields, false);
   if (rc != B2_OK) return rc;
+  // emb_small mirrors the output arena: field i's rows land at emb_small + (emb_fields[i].out - emb_fields[0].out)
+  int64_t small_delta = 0;
+  if (emb_small != nullptr) {
+    B2_REQUIRE(((uintptr_t) emb_small % 16) == 0, "emb_small must be 16-byte aligned");
+    small_delta = emb_small - reinterpret_cast<float*>(emb_fields[0].out);
+    B2_REQUIRE(small_delta != 0, "emb_small must not alias the output");
+  }
   B2_REQUIRE(batch >= 0, "negative batch");
   B2_REQUIRE(!want_fm || sum_out != nullptr, "want_fm needs sum_out (saved for the backward)");
   if (batch == 0) return B2_OK;
@@ -373,9 +384,9 @@ extern "C" B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* l
   const b2_lazy_ctx& lz = lazy ? *lazy : lz_none;
   const int lzf = lazy ? 1 : 0;
   switch (idx_dtype) {
-    case B2_F64: return launch_front_fwd<double>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
-    case B2_I64: return launch_front_fwd<int64_t>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
-    case B2_I32: return launch_front_fwd<int32_t>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, st);
+    case B2_F64: return launch_front_fwd<double>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, small_delta, st);
+    case B2_I64: return launch_front_fwd<int64_t>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, small_delta, st);
+    case B2_I32: return launch_front_fwd<int32_t>(epack, lpack, lz, lzf, batch, dim, has_lr, want_fm, bias, logit_out, sum_out, status, small_delta, st);
     default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
   }
 }

@@ -144,16 +144,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t bo
   d |= (uint64_t) (esz == 4 ? 1 : 2) << 61;      // layout: SWIZZLE_128B_BASE32B (1) / SWIZZLE_128B (2)
   return d;
 }
-// small(x) = rna_tf32(x - big(x)), big(x) = x with the 13 low mantissa bits cleared (what
-// kind::tf32 reads from a raw fp32 operand).  x - big(x) is exact; rounding it to a
-// tf32-representable value HERE (round-to-nearest) makes the hardware truncation of the small
-// operand a no-op, so the residual of the split is unbiased instead of always toward zero.
-__device__ __forceinline__ float tf32_small(float v) {
-  const float big = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - big));
-  return __uint_as_float(r);
-}
+__device__ __forceinline__ float tf32_small(float v) { return b2_tf32_small(v); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(

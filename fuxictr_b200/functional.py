@@ -507,6 +507,11 @@ def empty_aux(rows, cols, device):
 def make_aux(t):
     """The auxiliary operand of a contiguous-row fp32 matrix `t` (see empty_aux), computed in one launch."""
     mode = _MATMUL["mode"]
+    base = t._base if t._base is not None else t
+    hint = getattr(base, "_b2_aux", None)       # the producer already emitted it (fused front -> first MLP layer)
+    if hint is not None and hint[0] == mode and hint[2] == base._version and t.is_contiguous() \
+            and t.data_ptr() == base.data_ptr() and hint[1].numel() == t.numel():
+        return hint[1].view(t.shape)
     if mode == "tf32x3":
         return split_tf32(t if t.is_contiguous() else t.contiguous())
     if mode == "bf16":
@@ -524,6 +529,18 @@ def weight_aux(w):
         return None
     if not w.is_contiguous():
         raise RuntimeError("tensor-core GEMM weights must be contiguous")
+    slot = getattr(w, "_b2_slot", None)
+    if mode == "tf32x3" and slot is not None and slot.offset >= slot.arena.tail_offset > 0:
+        # the dense parameters of an arena are one contiguous slice: ONE split launch per optimizer step
+        # serves every Linear of the model (the small part has the operand's own layout)
+        arena = slot.arena
+        key = (_WEIGHT_EPOCH[0], arena.P.data_ptr(), tuple(p._version for p in arena.tail_params))
+        ent = getattr(arena, "_tail_small", None)
+        if ent is None or ent[0] != key:
+            ent = (key, split_tf32(arena.P[arena.tail_offset:arena.numel]))
+            arena._tail_small = ent
+        off = slot.offset - arena.tail_offset
+        return ent[1][off:off + slot.numel].view(slot.shape)
     key = (mode, w.data_ptr(), w._version, _WEIGHT_EPOCH[0], tuple(w.shape))
     ent = _SMALL_CACHE.get(id(w))
     if ent is not None and ent[0] == key and ent[2]() is w:
@@ -1116,9 +1133,14 @@ class _Front(torch.autograd.Function):
                 d.out, d.out_stride = 0, 0
         lazy = getattr(emb_tables[0], "_b2_lazy", None)       # set by arena.LazyTables on its parameters
         lz = lazy.ctx_for(plan, lr_plan, emb_tables, lr_tables) if lazy is not None else None
+        # 3xTF32: the rows' small parts are written by the same kernel (no split pass over the arena);
+        # the MLP finds them through the arena tensor (make_aux looks at `_b2_aux` of its input's base)
+        small = torch.empty_like(arena) if (_MATMUL["mode"] == "tf32x3" and batch > 0) else None
         _lib.call("b2_front_fwd", descs, lr_descs, len(plan.fields), batch, ctx_code(idx_list),
                   1 if want_fm else 0, _ptr(bias), _ptr(logit), _ptr(sums), _ptr(status),
-                  ctypes.byref(lz) if lz is not None else None, _stream())
+                  ctypes.byref(lz) if lz is not None else None, _ptr(small), _stream())
+        if small is not None:
+            arena._b2_aux = ("tf32x3", small, arena._version)
         ctx.lazy_ctx = lz
         ctx.plan, ctx.lr_plan, ctx.idx_list, ctx.want_fm = plan, lr_plan, idx_list, want_fm
         ctx.emb_tables, ctx.lr_tables, ctx.bias = emb_tables, lr_tables, bias

@@ -242,7 +242,16 @@ class RankModel(nn.Module):
             self._lazy = self._fused_optimizer.enable_lazy(first)
             self.optimizer = None
             return self._fused_optimizer
-        self._arena = ParamArena(self, first=getattr(self, "_sharded_params", ()))
+        # tables first (the row shards of a sharded run, else every nn.Embedding weight): the dense
+        # parameters then form one contiguous tail (one all-reduce, one 3xTF32 split launch per step)
+        first = getattr(self, "_sharded_params", None)
+        if not first:
+            first, seen = [], set()
+            for m in self.modules():
+                if type(m) == nn.Embedding and id(m.weight) not in seen and m.weight.requires_grad:
+                    seen.add(id(m.weight))
+                    first.append(m.weight)
+        self._arena = ParamArena(self, first=first)
         self._fused_optimizer = FusedAdam(self._arena, lr=self._lr, max_norm=self._max_gradient_norm)
         self._fused_optimizer.sharded = bool(getattr(self, "_sharded_params", None))
         self._fused_optimizer.dense_prescaled = getattr(self, "_loss_grad", None) is not None

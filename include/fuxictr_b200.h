@@ -189,6 +189,8 @@ typedef struct b2_lazy_ctx {
 B2_API int b2_front_fwd(const b2_field* emb_fields, const b2_field* lr_fields, int nfields, int64_t batch,
                         int idx_dtype, int want_fm, const float* bias, float* logit_out, float* sum_out,
                         int32_t* status, const b2_lazy_ctx* lazy /* NULL = tables are up to date */,
+                        float* emb_small /* NULL, or a second arena of the output's layout that receives the
+                                            3xTF32 small part of every row (the first GEMM's A operand) */,
                         void* stream);
 /*
  * Backward of b2_front_fwd.  In emb_fields, `table` is the (vocab, dim) gradient buffer (NULL =
