@@ -678,8 +678,9 @@ def test_mlp_chain_matches_torch_autograd(mode, dims, acts, B):
         yg.backward(gout.cuda())
     finally:
         F2.set_matmul_precision("fp32")
-    # single-pass modes truncate (TF32) / round (bf16) every operand of a 4-layer network: percent-level
-    tol = {"tf32x3": RTOL, "tf32": 2e-2, "bf16": 6e-2}[mode]
+    # single-pass modes truncate (TF32: ~3e-3 per contraction, see test_gemm_tc_vs_fp64) / round (bf16) every
+    # operand of up to 8 chained contractions (forward + backward of 4 layers): percent-level, non-parity modes
+    tol = {"tf32x3": RTOL, "tf32": 5e-2, "bf16": 1e-1}[mode]
     assert close(yg, yr, tol)
     assert close(xg.grad, xr.grad, tol, atol=tol * float(xr.grad.abs().max()))
     for (k, pg), (_, pr) in zip(mlp.named_parameters(), ref.named_parameters()):
