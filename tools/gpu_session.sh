@@ -34,8 +34,8 @@ for st in $stages; do
       timeout 600 python bench.py --workload dlrm --steps 20 --warmup 5 --nbatches 8 > gpurun_out/${tag}_bench_dlrm_n1.json 2> gpurun_out/${tag}_bench_dlrm_n1.err
       head -c 800 gpurun_out/${tag}_bench_dlrm_n1.json; echo; tail -3 gpurun_out/${tag}_bench_dlrm_n1.err ;;
     ncu)
-      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
-        python bench.py --steps 2 --warmup 3 --graph 0 --steps-only --nbatches 4 > gpurun_out/${tag}_ncu_launch.log 2>&1
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 520 -c 300 --csv --log-file gpurun_out/${tag}_launches.csv \
+        python bench.py --steps 4 --warmup 3 --graph 0 --steps-only --nbatches 4 > gpurun_out/${tag}_ncu_launch.log 2>&1
       tail -3 gpurun_out/${tag}_ncu_launch.log
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 12 -c 9 -o gpurun_out/${tag}_gemm \
         python bench.py --steps 1 --warmup 3 --graph 0 --steps-only --nbatches 4 > gpurun_out/${tag}_ncu_gemm.log 2>&1
