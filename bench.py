@@ -689,7 +689,9 @@ def run_b200_arm(args):
         try:
             pipe.capture(3)     # the constructor does this for graph=True; done late here to count launches first
         except Exception as exc:   # report an eager number rather than none (the JSON line says cuda_graph: false)
-            sys.stderr.write("[bench r%d] CUDA-graph capture failed (%r); timing the eager step\n" % (rank, exc))
+            import traceback
+            sys.stderr.write("[bench r%d] CUDA-graph capture failed (%r); timing the eager step\n%s\n"
+                             % (rank, exc, traceback.format_exc()))
             pipe.graph, pipe.loss_dev = None, None
             torch.cuda.synchronize()
     note("graph captured")

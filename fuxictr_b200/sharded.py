@@ -190,9 +190,7 @@ class ShardedFront(object):
         # step's push, which is ordered after this step's backward (and its closing barrier).
         emb = self.emb
         if not self.lr_tables and not self.want_fm:     # embeddings only (DLRM): nothing to reduce
-            if getattr(self, "_zero_logit", None) is None:
-                self._zero_logit = torch.zeros((self.B, 1), dtype=torch.float32, device="cuda")
-            return emb, self._zero_logit, None
+            return emb, torch.zeros((self.B, 1), dtype=torch.float32, device="cuda"), None
         logit = torch.empty((self.B, 1), dtype=torch.float32, device="cuda")
         sums = torch.empty((self.B, self.dim), dtype=torch.float32, device="cuda") if self.want_fm else None
         _lib.call("b2_front_reduce", F2._ptr(emb), F2._ptr(self.lrw) if self.lr_tables else None,

@@ -30,6 +30,9 @@ for st in $stages; do
         timeout 400 python bench.py --workload $w --steps 100 --cpu-seconds 6 > gpurun_out/${tag}_bench_$w.json 2> gpurun_out/${tag}_bench_$w.err
         head -c 600 gpurun_out/${tag}_bench_$w.json; echo; tail -2 gpurun_out/${tag}_bench_$w.err
       done ;;
+    dlrm_small)
+      timeout 300 python bench.py --workload dlrm --vocab-scale 0.01 --steps 30 --warmup 5 --nbatches 8 --steps-only > gpurun_out/${tag}_bench_dlrmsmall_n1.json 2> gpurun_out/${tag}_bench_dlrmsmall_n1.err
+      cat gpurun_out/${tag}_bench_dlrmsmall_n1.json; tail -30 gpurun_out/${tag}_bench_dlrmsmall_n1.err ;;
     dlrm1)
       timeout 600 python bench.py --workload dlrm --steps 20 --warmup 5 --nbatches 8 > gpurun_out/${tag}_bench_dlrm_n1.json 2> gpurun_out/${tag}_bench_dlrm_n1.err
       head -c 800 gpurun_out/${tag}_bench_dlrm_n1.json; echo; tail -3 gpurun_out/${tag}_bench_dlrm_n1.err ;;
