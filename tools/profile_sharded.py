@@ -41,20 +41,32 @@ REPS = 50
 
 
 def timed(fn, reps=REPS):
-    """mean microseconds of fn() per repetition, max over ranks; ranks aligned before each rep."""
-    for _ in range(3):
-        fn()
-    total = 0.0
-    for _ in range(reps):
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        torch.cuda.synchronize()
-        total += e0.elapsed_time(e1)
-    t = torch.tensor([total / reps * 1e3], device="cuda")
+    """mean microseconds of fn() per repetition, max over ranks.  `reps` calls are captured into one CUDA
+    graph (an eager ctypes call costs more host time than these kernels run), every rank replays it at
+    the same moment (host barrier first), CUDA events bracket the replay."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    dist.barrier()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    g.replay()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
@@ -82,9 +94,25 @@ out["dense_allreduce"] = timed(lambda: dist.all_reduce(tail))
 out["optimizer_step"] = timed(opt.step)
 pipe = TrainPipeline(model, B, bench.NF + 1, torch.float64, graph=False)
 pipe.prime(mats[0])
-out["eager_step"] = timed(lambda: pipe.step_device(mats[1]), reps=20)
 pipe.capture(3)
-out["graph_step"] = timed(lambda: pipe.step_device(mats[2]), reps=50)
+
+
+def replay_steps(n=50):
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        pipe.step_device(mats[i % len(mats)])
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n * 1e3], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+replay_steps(10)
+out["graph_step"] = replay_steps(50)
 if rank == 0:
     print(json.dumps(out), flush=True)
 dist.barrier()
