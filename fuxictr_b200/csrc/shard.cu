@@ -34,6 +34,8 @@ struct PeerPtrs {
   const float* glogit[16];
 };
 
+struct BcastDst { void* p[16]; };
+
 // flags packed next to the field index in an owned-list entry
 #define B2_OWN_EMB (1 << 17)
 #define B2_OWN_LR (1 << 16)
@@ -181,7 +183,6 @@ shard_pull_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant
 }
 
 // One launch: this rank's buffer -> the same slot on every peer (P2P stores, 16 B per thread-iteration).
-struct BcastDst { void* p[16]; };
 __global__ void __launch_bounds__(256)
 shard_bcast_kernel(const void* __restrict__ src, int64_t nbytes, const __grid_constant__ BcastDst dst, int world) {
   const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t) gridDim.x * blockDim.x;
@@ -195,6 +196,28 @@ shard_bcast_kernel(const void* __restrict__ src, int64_t nbytes, const __grid_co
   for (int64_t i = tail0 + tid * 4; i + 4 <= nbytes; i += nth * 4) {
     const int32_t v = *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(src) + i);
     for (int p = 0; p < world; ++p) *reinterpret_cast<int32_t*>(reinterpret_cast<char*>(dst.p[p]) + i) = v;
+  }
+}
+
+// The id exchange, compressed: the batch matrix arrives as float64 (the reference's collator), the owners
+// only need the row numbers — one launch truncates like `.long()`, narrows to int32 (vocabularies < 2^31)
+// and stores the result into this rank's slot on every peer: 4 bytes per id over NVLink instead of 8.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+shard_bcast_ids_kernel(const void* __restrict__ src, int64_t n, const __grid_constant__ BcastDst dst, int world) {
+  const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t) gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = tid; i < n4; i += nth) {
+    int4 v;
+    v.x = (int) b2_load_index<IdxT>(src, 4 * i + 0);
+    v.y = (int) b2_load_index<IdxT>(src, 4 * i + 1);
+    v.z = (int) b2_load_index<IdxT>(src, 4 * i + 2);
+    v.w = (int) b2_load_index<IdxT>(src, 4 * i + 3);
+    for (int p = 0; p < world; ++p) reinterpret_cast<int4*>(dst.p[p])[i] = v;
+  }
+  for (int64_t i = (n4 << 2) + tid; i < n; i += nth) {
+    const int v = (int) b2_load_index<IdxT>(src, i);
+    for (int p = 0; p < world; ++p) reinterpret_cast<int32_t*>(dst.p[p])[i] = v;
   }
 }
 
@@ -383,6 +406,28 @@ extern "C" B2_API int b2_shard_pull(const b2_field* emb_fields, const b2_field* 
                                                                reinterpret_cast<const int4*>(owned), owned_count,
                                                                owned_capacity);
   B2_CUDA_LAUNCH_CHECK("b2_shard_pull");
+  return B2_OK;
+}
+
+extern "C" B2_API int b2_peer_bcast_ids(const void* src, int idx_dtype, int64_t count, int32_t* const* peer_dst,
+                                        int world, void* stream) {
+  B2_REQUIRE(src && peer_dst && world >= 1 && world <= 16 && count >= 0, "bad argument");
+  if (count == 0) return B2_OK;
+  BcastDst d;
+  for (int i = 0; i < 16; ++i) d.p[i] = nullptr;
+  for (int i = 0; i < world; ++i) {
+    B2_REQUIRE(peer_dst[i] != nullptr && ((uintptr_t) peer_dst[i] % 16) == 0, "peer_dst[%d] NULL or misaligned", i);
+    d.p[i] = peer_dst[i];
+  }
+  const int grid = grid_for(count >> 2, 256);
+  cudaStream_t st = (cudaStream_t) stream;
+  switch (idx_dtype) {
+    case B2_F64: shard_bcast_ids_kernel<double><<<grid, 256, 0, st>>>(src, count, d, world); break;
+    case B2_I64: shard_bcast_ids_kernel<int64_t><<<grid, 256, 0, st>>>(src, count, d, world); break;
+    case B2_I32: shard_bcast_ids_kernel<int32_t><<<grid, 256, 0, st>>>(src, count, d, world); break;
+    default: return b2_fail(B2_E_INVALID, "idx_dtype %d unsupported", idx_dtype);
+  }
+  B2_CUDA_LAUNCH_CHECK("b2_peer_bcast_ids");
   return B2_OK;
 }
 

@@ -134,12 +134,17 @@ class ShardedFront(object):
         self.bias, self.want_fm = bias, want_fm
         self.idx_dtype = idx_dtype
         self.idx_code = F2._IDX_CODE[idx_dtype]
+        if max(self.vocabs) >= 2 ** 31:
+            raise NotImplementedError("the id exchange narrows row numbers to int32 (vocabulary >= 2^31)")
         g = group
         # ids_all[p] = batch matrix of rank p: every rank BROADCASTS its ids into slot `rank` of all
         # peers (one launch of P2P stores), so the push kernel walks local memory only.
+        # the slots hold int32 row numbers: the exchange narrows the collator's float64 on the fly
         self.ids_all, self._ids_all_ptrs, self._ids_peer = g.alloc("ids_all", (g.world, batch_local, matrix_width),
-                                                                   idx_dtype)
+                                                                   torch.int32)
         esz = self.ids_all.element_size()
+        self.src_code = self.idx_code          # dtype of the batch matrix handed to phase_ids
+        self.idx_code = F2._IDX_CODE[torch.int32]
         self._slot_bytes = batch_local * matrix_width * esz
         self.ids_ptrs = [self.ids_all.data_ptr() + p * self._slot_bytes for p in range(g.world)]
         self._ids_src = torch.empty((batch_local, matrix_width), dtype=idx_dtype, device="cuda")
@@ -174,7 +179,8 @@ class ShardedFront(object):
             self._ids_src.copy_(batch_matrix)
             src = self._ids_src
         dst = [int(base) + g.rank * self._slot_bytes for base in self._ids_all_ptrs]     # my slot on every rank
-        _lib.call("b2_peer_bcast", F2._ptr(src), self._slot_bytes, _ptr_array(dst), g.world, F2._stream())
+        _lib.call("b2_peer_bcast_ids", F2._ptr(src), self.src_code, self.B * self.W, _ptr_array(dst), g.world,
+                  F2._stream())
 
     def phase_push(self):
         g = self.group

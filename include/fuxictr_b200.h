@@ -259,6 +259,10 @@ B2_API int b2_shard_pull(const b2_field* emb_fields, const b2_field* lr_fields, 
                          const float* const* peer_glogit, float scale, const int32_t* owned,
                          const int32_t* owned_count, int32_t owned_capacity, void* stream);
 B2_API int b2_peer_bcast(const void* src, int64_t nbytes, void* const* peer_dst, int world, void* stream);
+/* The id exchange, compressed: `count` contiguous ids of dtype idx_dtype (B2_F64 truncates like .long())
+ * are narrowed to int32 and stored into peer_dst[p] (16-byte aligned) for every p < world. */
+B2_API int b2_peer_bcast_ids(const void* src, int idx_dtype, int64_t count, int32_t* const* peer_dst, int world,
+                             void* stream);
 /* After the push: logit[b] = [FM product_sum of emb[b]] (if want_fm) + sum_f lrw[b,f] + bias;
  * sums[b,:] = sum_f emb[b,f,:] (saved for the backward). */
 B2_API int b2_front_reduce(const float* emb, const float* lrw, const float* bias, int64_t batch,
