@@ -6,6 +6,8 @@ tag=${1:-s}; shift
 stages=${@:-tests bench}
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
+# the snapshot may have been taken between a source edit and its rebuild: build() is digest-stamped (no-op when current)
+python -c 'import __graft_entry__ as g; g.build()' > gpurun_out/${tag}_build.log 2>&1 || tail -5 gpurun_out/${tag}_build.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
 for st in $stages; do
   case $st in

@@ -5,6 +5,8 @@ tag=$1; N=$2; shift; shift
 stages=${@:-parity profile deepfm}
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
+# the snapshot may have been taken between a source edit and its rebuild: build() is digest-stamped (no-op when current)
+python -c 'import __graft_entry__ as g; g.build()' > gpurun_out/${tag}_build.log 2>&1 || tail -5 gpurun_out/${tag}_build.log
 run() { timeout $1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) "${@:2}"; }
 for st in $stages; do
   case $st in
