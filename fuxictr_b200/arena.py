@@ -183,6 +183,9 @@ class FusedAdam(object):
         self.grad_allreduce = False  # data-parallel replicas: average G across ranks before the step
         self.sharded = False         # row-sharded tables in G[:tail_offset], replicated dense params after
         self.dense_prescaled = False # sharded: gradients were born divided by the world size (no mul_ after the all-reduce)
+        self._side = None            # overlap: side stream + its own communicator for the dense-gradient all-reduce
+        self._side_group = None
+        self._early_pending = False
 
     def enable_lazy(self, tables):
         """Evaluate the dense Adam semantics of `tables` (the arena's leading parameters) lazily."""
@@ -202,6 +205,25 @@ class FusedAdam(object):
             raise RuntimeError("lazy Adam: the per-step schedule table holds %d steps; materialize_tables() and "
                                "rebuild the optimizer (or use the dense pass) before step %d"
                                % (LazyTables.SCHED_LEN, self.host_steps))
+
+    def enable_dense_overlap(self):
+        """Sharded runs: all-reduce the dense-gradient tail on a side stream (own NCCL communicator) as soon
+        as the last dense gradient exists — the sharded front calls start_dense_allreduce() right after its
+        gradient-prep kernel — so it overlaps the barrier + pull of the row gradients; step() then only
+        exchanges the one norm scalar on the main stream.  Collective: call on every rank."""
+        import torch.distributed as dist
+        self._side = torch.cuda.Stream(device=self.arena.P.device)
+        self._side_group = dist.new_group()
+
+    def start_dense_allreduce(self):
+        a = self.arena
+        if self._side is None or not self.sharded or a.numel <= a.tail_offset:
+            return
+        import torch.distributed as dist
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(a.G[a.tail_offset:a.numel], op=dist.ReduceOp.SUM, group=self._side_group)
+        self._early_pending = True
 
     def zero_grad(self, set_to_none=True):
         self.arena.begin_step(grads_zeroed=self.zero_grad_in_step and self._stepped)
@@ -238,8 +260,14 @@ class FusedAdam(object):
             if self.max_norm is not None and a.tail_offset > 0:
                 _lib.call("b2_sumsq", ctypes.c_void_p(a.G.data_ptr()), a.tail_offset,
                           ctypes.c_void_p(slot.data_ptr()), st)   # this rank's shard part of ||g||^2
-            # ONE collective: dense gradients (to be averaged) + the shard norm term (to be summed)
-            dist.all_reduce(a._G_ext[a.tail_offset:a.numel + 1], op=dist.ReduceOp.SUM)
+            if self._early_pending:
+                # the dense gradients are already being summed on the side stream: only the norm scalar here
+                dist.all_reduce(slot, op=dist.ReduceOp.SUM)
+                torch.cuda.current_stream().wait_stream(self._side)
+                self._early_pending = False
+            else:
+                # ONE collective: dense gradients (to be averaged) + the shard norm term (to be summed)
+                dist.all_reduce(a._G_ext[a.tail_offset:a.numel + 1], op=dist.ReduceOp.SUM)
             dense = a.G[a.tail_offset:]
             if dense.numel() > 0 and not self.dense_prescaled:
                 dense.mul_(1.0 / world)                          # mean over the global batch

@@ -160,6 +160,7 @@ class ShardedFront(object):
         # mean over the GLOBAL batch (rank_model.py:130): either the pull scales every gradient row by
         # 1/world (default), or the caller seeds backward() with 1/world and sets pull_scale = 1
         self.pull_scale = 1.0 / g.world
+        self.on_dense_grads_ready = None     # set by RankModel.use_fused_optimizer (overlapped dense all-reduce)
 
     # -- descriptors --------------------------------------------------------------------------
     def _descs(self, tables, dim):
@@ -253,6 +254,8 @@ class _ShardedFrontFn(torch.autograd.Function):
         if bias is not None and bias.requires_grad:
             gbias = F2._grad_buffer(bias, zero=False)
         front.phase_gprep(gx, emb, sums, gl, gbias)      # also: LR bias gradient = sum_b glogit[b]
+        if front.on_dense_grads_ready is not None:      # every dense gradient now exists: start their all-reduce
+            front.on_dense_grads_ready()
         g.barrier()                      # every rank's gradient rows are ready to be pulled
         n = front.F
         egrads = [(F2._grad_buffer(t, zero=True) if t.requires_grad else None) for t in tables[:n]]

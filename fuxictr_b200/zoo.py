@@ -255,6 +255,11 @@ class RankModel(nn.Module):
         self._fused_optimizer = FusedAdam(self._arena, lr=self._lr, max_norm=self._max_gradient_norm)
         self._fused_optimizer.sharded = bool(getattr(self, "_sharded_params", None))
         self._fused_optimizer.dense_prescaled = getattr(self, "_loss_grad", None) is not None
+        front = getattr(self, "_sharded_front", None)
+        if front is not None and front.group.world > 1 and hasattr(front.group, "group"):
+            # real ranks (not the single-process virtual harness): overlap the dense all-reduce with the pull
+            self._fused_optimizer.enable_dense_overlap()
+            front.on_dense_grads_ready = self._fused_optimizer.start_dense_allreduce
         self.optimizer = None
         return self._fused_optimizer
 
