@@ -32,6 +32,8 @@ for st in $stages; do
         timeout 400 python bench.py --workload $w --steps 100 --cpu-seconds 6 > gpurun_out/${tag}_bench_$w.json 2> gpurun_out/${tag}_bench_$w.err
         head -c 600 gpurun_out/${tag}_bench_$w.json; echo; tail -2 gpurun_out/${tag}_bench_$w.err
       done ;;
+    debug)
+      for m in tf32 tf32x3 bf16; do timeout 120 python tools/debug_chain.py $m 2>&1 | tail -8; done ;;
     dlrm_small)
       timeout 300 python bench.py --workload dlrm --vocab-scale 0.01 --steps 30 --warmup 5 --nbatches 8 --steps-only > gpurun_out/${tag}_bench_dlrmsmall_n1.json 2> gpurun_out/${tag}_bench_dlrmsmall_n1.err
       cat gpurun_out/${tag}_bench_dlrmsmall_n1.json; tail -30 gpurun_out/${tag}_bench_dlrmsmall_n1.err ;;
