@@ -746,7 +746,9 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
                        d->c_small == nullptr && d->c_pre == nullptr && d->colsum == nullptr);
   int best_bn = 0, best_split = 1;
   double best_cost = 1e300;
-  const int bn_max = (d->a_small != nullptr) ? 128 : 256;  // 3xTF32 keeps >= 4 accumulator ranges in TMEM
+  // 3xTF32: (chains + 1 correction range) x bn <= 512 TMEM columns and 3 stages of {A, As, B, Bs} <= 227 KB:
+  // bn <= 128 keeps 3-4 chains, bn = 160 keeps 2 (used when it saves a whole wave, e.g. 8192 x 624 x 624)
+  const int bn_max = (d->a_small != nullptr) ? 160 : 256;
   const int bn_step = (d->b_mn_major && esz == 2) ? 64 : 32;   // an MN-major box is 128 bytes of rows
   for (int bn = bn_step; bn <= bn_max; bn += bn_step) {
     const int64_t tiles_n = b2_ceil_div(N, bn);
@@ -804,7 +806,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   // opt-in to > 48 KB of dynamic shared memory: an idempotent per-process property of the kernel
   // (C++11 guarantees the initialiser runs once, thread-safely)
   static const cudaError_t attr_rc = cudaFuncSetAttribute(
-      tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (4 * (tc::A_BYTES + 256 * 128) + 1024 + 128));
+      tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr_rc != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(attr_rc));
   dim3 grid((unsigned) tiles_m, (unsigned) b2_ceil_div(N, best_bn), (unsigned) splits);
   B2_REQUIRE(grid.y <= 65535, "N too large for this launch geometry");
