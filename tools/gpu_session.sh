@@ -33,7 +33,12 @@ for st in $stages; do
         head -c 600 gpurun_out/${tag}_bench_$w.json; echo; tail -2 gpurun_out/${tag}_bench_$w.err
       done ;;
     debug)
-      for m in tf32 tf32x3 bf16; do timeout 120 python tools/debug_chain.py $m 2>&1 | tail -8; done ;;
+      for m in tf32 tf32x3 bf16; do timeout 120 python tools/debug_chain.py $m 2>&1 | tail -8; done
+      # PDL A/B on the default step, the 128x160 3xTF32 tile on C3, and the full GPU suite
+      timeout 200 python bench.py --steps-only > gpurun_out/${tag}_pdl0.json 2> gpurun_out/${tag}_pdl0.err; cat gpurun_out/${tag}_pdl0.json
+      B2_PDL=1 timeout 200 python bench.py --steps-only > gpurun_out/${tag}_pdl1.json 2> gpurun_out/${tag}_pdl1.err; cat gpurun_out/${tag}_pdl1.json; tail -3 gpurun_out/${tag}_pdl1.err
+      timeout 300 python bench.py --workload dcnv2 --steps 100 --no-cpu-baseline > gpurun_out/${tag}_bench_dcnv2.json 2> gpurun_out/${tag}_bench_dcnv2.err; head -c 400 gpurun_out/${tag}_bench_dcnv2.json; echo
+      timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/${tag}_gputests.log 2>&1; tail -8 gpurun_out/${tag}_gputests.log ;;
     dlrm_small)
       timeout 300 python bench.py --workload dlrm --vocab-scale 0.01 --steps 30 --warmup 5 --nbatches 8 --steps-only > gpurun_out/${tag}_bench_dlrmsmall_n1.json 2> gpurun_out/${tag}_bench_dlrmsmall_n1.err
       cat gpurun_out/${tag}_bench_dlrmsmall_n1.json; tail -30 gpurun_out/${tag}_bench_dlrmsmall_n1.err ;;
