@@ -34,6 +34,7 @@ constexpr int UMMA_K_BYTES = 32; // kind::tf32: K = 8 elements of 4 bytes per in
 constexpr int MAX_STAGES = 4;  // 4 stages of (A,B) for one pass; 3 stages of (A,As,B,Bs) for 3xTF32
 constexpr int A_BYTES = BM * 128;
 constexpr int NTHREADS = 192;
+constexpr int PATCH_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose patches (one per epilogue warp)
 
 struct Params {
   CUtensorMap map_a[2];   // [0] the operand, [1] its 3xTF32 small part
@@ -52,6 +53,8 @@ struct Params {
   int esz;                // operand element bytes: 4 = fp32 read as tf32 (kind::tf32), 2 = bf16 (kind::f16)
   int64_t ld_aux;         // leading dimension of c_small (fp32 small part, or the bf16 copy of C when esz == 2)
   int nmain;      // TMEM accumulators for the main (big x big) product: its K range is cut in nmain chunks
+  int tiles_m, tiles_n, splits;   // tile grid; CTAs stride over tiles_m * tiles_n * splits work items
+  int nacc;       // accumulator stages in TMEM (2: the epilogue of a tile overlaps the next main loop)
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
 };
 
@@ -184,6 +187,90 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// One lane's share of the epilogue: column n of 32 consecutive rows (mrow0 ...), values in t[].
+__device__ __forceinline__ void epilogue_store(const Params& p, float (&t)[32], int mrow0, int n, bool split) {
+  float* cp = p.c + (int64_t) mrow0 * p.ldc + n;
+  if (split) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+      if (mrow0 + r < p.M) b2_red_add(cp + (int64_t) r * p.ldc, t[r]);
+  } else {
+    if (p.c_pre != nullptr) {
+      float* pp = p.c_pre + (int64_t) mrow0 * p.ldc + n;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (mrow0 + r < p.M) pp[(int64_t) r * p.ldc] = t[r];
+    }
+    if (p.mul != nullptr) {
+      const float* mp = p.mul + (int64_t) mrow0 * p.ldc + n;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (mrow0 + r < p.M) t[r] *= __ldg(mp + (int64_t) r * p.ldc);
+    }
+    if (p.add != nullptr) {
+      const float* ap = p.add + (int64_t) mrow0 * p.ldc + n;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (mrow0 + r < p.M) t[r] += __ldg(ap + (int64_t) r * p.ldc);
+    }
+    if (p.act == B2_ACT_RELU) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t[r] = fmaxf(t[r], 0.f);
+    } else if (p.act == B2_ACT_SIGMOID) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t[r] = 1.f / (1.f + expf(-t[r]));
+    }
+    if (p.ybwd != nullptr) {   // activation backward of the PRODUCER of this gradient, fused
+      const float* yp = p.ybwd + (int64_t) mrow0 * p.ldc + n;
+      if (p.act_bwd == B2_ACT_RELU) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (mrow0 + r < p.M) t[r] = (__ldg(yp + (int64_t) r * p.ldc) > 0.f) ? t[r] : 0.f;
+      } else if (p.act_bwd == B2_ACT_SIGMOID) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (mrow0 + r < p.M) {
+            const float yv = __ldg(yp + (int64_t) r * p.ldc);
+            t[r] = t[r] * ((1.f - yv) * yv);
+          }
+      }
+    }
+    if (p.beta) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (mrow0 + r < p.M) t[r] += cp[(int64_t) r * p.ldc];
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+      if (mrow0 + r < p.M) cp[(int64_t) r * p.ldc] = t[r];   // 128 contiguous bytes per row
+    if (p.c_small != nullptr && p.esz == 4) {   // the consumer's 3xTF32 small part, produced where C is produced
+      float* sp = p.c_small + (int64_t) mrow0 * p.ld_aux + n;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (mrow0 + r < p.M) sp[(int64_t) r * p.ld_aux] = tf32_small(t[r]);
+    } else if (p.c_small != nullptr) {          // bf16 mode: the consumer's bf16 operand (round-to-nearest-even)
+      __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.c_small) + (int64_t) mrow0 * p.ld_aux + n;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (mrow0 + r < p.M) sp[(int64_t) r * p.ld_aux] = __float2bfloat16_rn(t[r]);
+    }
+    if (p.colsum != nullptr) {    // bias gradient: this lane owns column n of 32 rows
+      float cs = 0.f;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (mrow0 + r < p.M) cs += t[r];
+      b2_red_add(p.colsum + n, cs);
+    }
+  }
+}
+
+// Persistent tile loop: CTA c works on tiles c, c + gridDim.x, ... (one tile per CTA when the problem
+// has no more tiles than SMs).  Three pipelines run through all of a CTA's tiles without draining:
+//   smem ring      full[s] / empty[s]            TMA producer  <->  MMA issuer
+//   TMEM stages    tmem_full[a] / tmem_empty[a]  MMA issuer    <->  epilogue warps (a < nacc = 1 or 2)
+// so the barrier / TMEM / descriptor prologue is paid once per CTA, the producer prefetches the next
+// tile's operands during an epilogue, and with nacc = 2 the epilogue of tile j overlaps the main loop
+// of tile j + 1.
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -195,22 +282,22 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   const int STAGES = x3 ? 3 : 4;
   const uint32_t stage_bytes = (x3 ? 2u : 1u) * (A_BYTES + b_bytes);
   const uint32_t off_as = A_BYTES, off_b = (x3 ? 2u : 1u) * A_BYTES, off_bs = off_b + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  // after the ring: 4 epilogue transpose patches (32 x 33 floats each), then the mbarriers
+  float* patch_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + PATCH_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES),
-                 tmem_full = smem_u32(bars + 2 * MAX_STAGES);
+                 tfull0 = smem_u32(bars + 2 * MAX_STAGES), tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.bn;
   const int bke = 128 / p.esz;                      // k elements per k-block: one 128-byte swizzle row
   const int mnb = 128 / p.esz;                      // MN elements per MN-major box (128 bytes wide)
   const uint32_t box_bytes = (uint32_t) bke * 128u; // one MN-major box: bke k-rows x 128 B
   const int num_kb_total = (p.K + bke - 1) / bke;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
-  // a short last K split may hold fewer k-blocks than accumulation chains
-  const int nmain = min(p.nmain, kb_end - kb_begin);
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_mn * p.splits;
+  const int acc_cols = (p.nmain + (x3 ? 1 : 0)) * p.bn;   // TMEM columns of one accumulator stage
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < (x3 ? 2 : 1); ++s) {
@@ -221,11 +308,14 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);    // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {  // whole warp: allocate TMEM columns for the accumulator
+  if (warp == 1) {  // whole warp: allocate TMEM columns for the accumulator stage(s)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t) p.tmem_cols)
                  : "memory");
@@ -242,31 +332,35 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 
   if (warp == 0) {
     // ---------------- TMA producer (the warp loops converged; one elected lane issues) ----------------
-    {
-      int stage = 0;
-      uint32_t phase = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int z = t / tiles_mn, r = t - z * tiles_mn;
+      const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * p.bn;
+      const int kb_begin = z * p.kb_per_split;
+      const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(empty0 + 8 * stage, phase ^ 1, 0);
         const uint32_t a_dst = smem_base + stage * stage_bytes;
         const uint32_t full = full0 + 8 * stage;
         if (elect_one()) {
-        mbar_expect_tx(full, stage_bytes);
-        // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products.
-        // K-major operand: one box (BK k-columns x rows).  MN-major operand: one box per 32 rows
-        // (32 rows x BK k-rows, coordinates {row, k}); out-of-range boxes arrive zero-filled.
-        for (int s = 0; s < (x3 ? 2 : 1); ++s) {
-          const uint32_t a_t = a_dst + (s ? off_as : 0u), b_t = a_dst + (s ? off_bs : off_b);
-          if (!p.a_mn) {
-            tma_load_2d(a_t, &p.map_a[s], full, kb * bke, m0);
-          } else {
-            for (int j = 0; j < BM / mnb; ++j) tma_load_2d(a_t + j * box_bytes, &p.map_a[s], full, m0 + mnb * j, kb * bke);
+          mbar_expect_tx(full, stage_bytes);
+          // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products.
+          // K-major operand: one box (128 B of k x rows).  MN-major operand: one box per 128 B of rows
+          // (coordinates {row, k}); out-of-range boxes arrive zero-filled.
+          for (int s = 0; s < (x3 ? 2 : 1); ++s) {
+            const uint32_t a_t = a_dst + (s ? off_as : 0u), b_t = a_dst + (s ? off_bs : off_b);
+            if (!p.a_mn) {
+              tma_load_2d(a_t, &p.map_a[s], full, kb * bke, m0);
+            } else {
+              for (int j = 0; j < BM / mnb; ++j) tma_load_2d(a_t + j * box_bytes, &p.map_a[s], full, m0 + mnb * j, kb * bke);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(b_t, &p.map_b[s], full, kb * bke, n0);
+            } else {
+              for (int j = 0; j < p.bn / mnb; ++j) tma_load_2d(b_t + j * box_bytes, &p.map_b[s], full, n0 + mnb * j, kb * bke);
+            }
           }
-          if (!p.b_mn) {
-            tma_load_2d(b_t, &p.map_b[s], full, kb * bke, n0);
-          } else {
-            for (int j = 0; j < p.bn / mnb; ++j) tma_load_2d(b_t + j * box_bytes, &p.map_b[s], full, n0 + mnb * j, kb * bke);
-          }
-        }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -274,41 +368,50 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (the warp loops converged; one elected lane issues) ----------------
-    {
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, N = bn, M = 128
-      const uint32_t fmt = (p.esz == 2) ? 1u : 2u;   // operand format: kind::f16 1 = BF16; kind::tf32 2 = TF32
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.a_mn ? 1 : 0) << 15) |
-                             ((uint32_t) (p.b_mn ? 1 : 0) << 16) | ((uint32_t) (p.bn >> 3) << 17) |
-                             ((uint32_t) (BM >> 4) << 24);
-      // one instruction consumes 32 bytes of K per row (8 tf32 / 16 bf16 elements): 32 bytes along a
-      // K-major swizzle row (+2 in the (addr >> 4) field), or 8 / 16 k-rows of an MN-major tile
-      const uint32_t mn_step = (p.esz == 2) ? 2048u : 1024u;
-      const uint64_t a_kstep = p.a_mn ? (uint64_t) (mn_step >> 4) : (uint64_t) (UMMA_K_BYTES >> 4);
-      const uint64_t b_kstep = p.b_mn ? (uint64_t) (mn_step >> 4) : (uint64_t) (UMMA_K_BYTES >> 4);
-      // The tensor core adds each instruction's 8 products into the fp32 accumulator with
-      // truncation, so rounding error grows with the length of one accumulation chain and with
-      // the magnitude of the accumulator.  For 3xTF32 the K range of the main product is
-      // therefore cut into `nmain` chains held in separate TMEM column ranges, and the two small
-      // correction products get a range of their own; the epilogue adds the ranges in fp32 RN.
-      //
-      // This ONE thread is the instruction stream behind every MMA of the CTA, so its scalar work per
-      // k-block is on the critical path: descriptors are built once (stage 0) and advanced by 32-bit
-      // adds on their low word (the 14-bit start-address field never carries), the chain boundaries
-      // are precomputed, and the bf16 / TF32 / 3xTF32 loops are separate.
-      const int nkb = kb_end - kb_begin;
-      // chain c covers k-blocks [ceil(c nkb / nmain), ceil((c+1) nkb / nmain)): divisions only at the <= 4 boundaries
-      int this_start = 0, next_start = (nkb + nmain - 1) / nmain;
-      const uint64_t a0 = p.a_mn ? make_smem_desc_mn(smem_base, box_bytes, p.esz) : make_smem_desc(smem_base);
-      const uint64_t b0 = p.b_mn ? make_smem_desc_mn(smem_base + off_b, box_bytes, p.esz) : make_smem_desc(smem_base + off_b);
-      const uint64_t as0 = p.a_mn ? make_smem_desc_mn(smem_base + off_as, box_bytes, p.esz) : make_smem_desc(smem_base + off_as);
-      const uint64_t bs0 = p.b_mn ? make_smem_desc_mn(smem_base + off_bs, box_bytes, p.esz) : make_smem_desc(smem_base + off_bs);
-      const uint32_t a_hi = (uint32_t) (a0 >> 32), b_hi = (uint32_t) (b0 >> 32);
-      const uint32_t as_hi = (uint32_t) (as0 >> 32), bs_hi = (uint32_t) (bs0 >> 32);
-      const uint32_t ak = (uint32_t) a_kstep, bk = (uint32_t) b_kstep, stage_units = stage_bytes >> 4;
-      const uint32_t d_corr = tmem_base + (uint32_t) (nmain * p.bn);
+    // instruction descriptor: D=f32, A=B=tf32 | bf16, operand majors, N = bn, M = 128
+    const uint32_t fmt = (p.esz == 2) ? 1u : 2u;   // operand format: kind::f16 1 = BF16; kind::tf32 2 = TF32
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.a_mn ? 1 : 0) << 15) |
+                           ((uint32_t) (p.b_mn ? 1 : 0) << 16) | ((uint32_t) (p.bn >> 3) << 17) |
+                           ((uint32_t) (BM >> 4) << 24);
+    // one instruction consumes 32 bytes of K per row (8 tf32 / 16 bf16 elements): 32 bytes along a
+    // K-major swizzle row (+2 in the (addr >> 4) field), or 8 / 16 k-rows of an MN-major tile
+    const uint32_t mn_step = (p.esz == 2) ? 2048u : 1024u;
+    const uint32_t ak = p.a_mn ? (mn_step >> 4) : (uint32_t) (UMMA_K_BYTES >> 4);
+    const uint32_t bk = p.b_mn ? (mn_step >> 4) : (uint32_t) (UMMA_K_BYTES >> 4);
+    // The tensor core adds each instruction's 8 products into the fp32 accumulator with
+    // truncation, so rounding error grows with the length of one accumulation chain and with
+    // the magnitude of the accumulator.  For 3xTF32 the K range of the main product is
+    // therefore cut into `nmain` chains held in separate TMEM column ranges, and the two small
+    // correction products get a range of their own; the epilogue adds the ranges in fp32 RN.
+    //
+    // The elected lane is the instruction stream behind every MMA of the CTA, so its scalar work per
+    // k-block is on the critical path: descriptors are built once (stage 0) and advanced by 32-bit
+    // adds on their low word (the 14-bit start-address field never carries), the chain boundaries
+    // are tracked incrementally, and the bf16 / TF32 / 3xTF32 loops are separate.
+    const uint64_t a0 = p.a_mn ? make_smem_desc_mn(smem_base, box_bytes, p.esz) : make_smem_desc(smem_base);
+    const uint64_t b0 = p.b_mn ? make_smem_desc_mn(smem_base + off_b, box_bytes, p.esz) : make_smem_desc(smem_base + off_b);
+    const uint64_t as0 = p.a_mn ? make_smem_desc_mn(smem_base + off_as, box_bytes, p.esz) : make_smem_desc(smem_base + off_as);
+    const uint64_t bs0 = p.b_mn ? make_smem_desc_mn(smem_base + off_bs, box_bytes, p.esz) : make_smem_desc(smem_base + off_bs);
+    const uint32_t a_hi = (uint32_t) (a0 >> 32), b_hi = (uint32_t) (b0 >> 32);
+    const uint32_t as_hi = (uint32_t) (as0 >> 32), bs_hi = (uint32_t) (bs0 >> 32);
+    const uint32_t stage_units = stage_bytes >> 4;
 #define B2_DESC(hi, lo) ((((uint64_t) (hi)) << 32) | (uint64_t) (uint32_t) (lo))
-      int stage = 0, slot = 0;
-      uint32_t phase = 0, so = 0;      // so: this stage's offset in descriptor units
+    int stage = 0;
+    uint32_t phase = 0, so = 0;      // so: this stage's offset in descriptor units
+    int j = 0;                        // this CTA's tile counter
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      const int z = t / tiles_mn;
+      const int kb_begin = z * p.kb_per_split;
+      const int nkb = min(num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
+      const int nmain = min(p.nmain, nkb);        // a short last K split may hold fewer k-blocks than chains
+      const int acc = (p.nacc == 2) ? (j & 1) : 0;
+      const uint32_t use = (uint32_t) (p.nacc == 2 ? (j >> 1) : j);
+      mbar_wait(tempty0 + 8 * acc, (use & 1u) ^ 1u, 3);    // the epilogue drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t) (acc * acc_cols);
+      const uint32_t d_corr = tacc + (uint32_t) (nmain * p.bn);
+      // chain c covers k-blocks [ceil(c nkb / nmain), ceil((c+1) nkb / nmain)): divisions only at the boundaries
+      int slot = 0, this_start = 0, next_start = (nkb + nmain - 1) / nmain;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(full0 + 8 * stage, phase, 1);
         tc_fence_after();
@@ -318,142 +421,83 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
           next_start = ((slot + 1) * nkb + nmain - 1) / nmain;
         }
         const uint32_t keep = (i == this_start) ? 0u : 1u;      // first k-block of a chain overwrites
-        const uint32_t d_main = tmem_base + (uint32_t) (slot * p.bn);
+        const uint32_t d_main = tacc + (uint32_t) (slot * p.bn);
         const uint32_t al = (uint32_t) a0 + so, bl = (uint32_t) b0 + so;
         if (elect_one()) {
-        if (p.esz == 2) {       // bf16 operands: one pass on kind::f16, fp32 accumulation in TMEM
+          if (p.esz == 2) {       // bf16 operands: one pass on kind::f16, fp32 accumulation in TMEM
 #pragma unroll
-          for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
-            umma_bf16(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep);
-        } else if (!x3) {
+            for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
+              umma_bf16(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep);
+          } else if (!x3) {
 #pragma unroll
-          for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
-            umma_tf32(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep);
-        } else {
-          const uint32_t asl = (uint32_t) as0 + so, bsl = (uint32_t) bs0 + so;
+            for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
+              umma_tf32(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep);
+          } else {
+            const uint32_t asl = (uint32_t) as0 + so, bsl = (uint32_t) bs0 + so;
 #pragma unroll
-          for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
-            const uint64_t ad = B2_DESC(a_hi, al + k * ak), bd = B2_DESC(b_hi, bl + k * bk);
-            umma_tf32(d_main, ad, bd, idesc, (k > 0) ? 1u : keep);                                       // A_big . B_big
-            umma_tf32(d_corr, ad, B2_DESC(bs_hi, bsl + k * bk), idesc, (i > 0 || k > 0) ? 1u : 0u);     // A_big . B_small
-            umma_tf32(d_corr, B2_DESC(as_hi, asl + k * ak), bd, idesc, 1u);                              // A_small . B_big
+            for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
+              const uint64_t ad = B2_DESC(a_hi, al + k * ak), bd = B2_DESC(b_hi, bl + k * bk);
+              umma_tf32(d_main, ad, bd, idesc, (k > 0) ? 1u : keep);                                       // A_big . B_big
+              umma_tf32(d_corr, ad, B2_DESC(bs_hi, bsl + k * bk), idesc, (i > 0 || k > 0) ? 1u : 0u);     // A_big . B_small
+              umma_tf32(d_corr, B2_DESC(as_hi, asl + k * ak), bd, idesc, 1u);                              // A_small . B_big
+            }
           }
-        }
-        umma_commit(empty0 + 8 * stage);  // frees this smem slot once the MMAs have read it
-        if (i == nkb - 1) umma_commit(tmem_full);  // ... and the last one: accumulator complete
+          umma_commit(empty0 + 8 * stage);                      // frees this smem slot once the MMAs have read it
+          if (i == nkb - 1) umma_commit(tfull0 + 8 * acc);      // ... and the last one: accumulator complete
         }
         __syncwarp();
         so += stage_units;
         if (++stage == STAGES) { stage = 0; phase ^= 1; so = 0; }
       }
-#undef B2_DESC
     }
+#undef B2_DESC
   } else {
     // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----------------
     const int q = warp & 3;
-    mbar_wait(tmem_full, 0, 2);
-    tc_fence_after();
-    const bool split = gridDim.z > 1;
-    const int nslots = nmain + (p.nseg > 1 ? 1 : 0);
-    // The pipeline buffers are idle now (every MMA has retired): each epilogue warp borrows a
-    // 32 x 33-float patch to transpose its TMEM rows, so that one store instruction writes 128
-    // contiguous bytes of ONE output row instead of 16 bytes of 32 different rows (partial-sector
-    // writes to untouched lines cost an L2 fill each — measured 19 us per tile before this).
-    float* patch = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
-      uint32_t v[32];
-      __syncwarp();  // tcgen05.ld is warp-collective; also fences the previous patch reads
-      tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) c0, v);
-      for (int sl = 1; sl < nslots; ++sl) {  // fp32 round-to-nearest sum of the accumulation chains
-        uint32_t w[32];
-        tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (sl * p.bn + c0), w);
+    const bool split = p.splits > 1;
+    // each epilogue warp owns a 32 x 33-float patch to transpose its TMEM rows, so that one store
+    // instruction writes 128 contiguous bytes of ONE output row instead of 16 bytes of 32 different rows
+    // (partial-sector writes to untouched lines cost an L2 fill each — measured 19 us per tile before this)
+    float* patch = patch_base + (warp - 2) * (32 * 33);
+    int j = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      const int z = t / tiles_mn, rr = t - z * tiles_mn;
+      const int m0 = (rr / p.tiles_n) * BM, n0 = (rr % p.tiles_n) * p.bn;
+      const int kb_begin = z * p.kb_per_split;
+      const int nkb = min(num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
+      const int nmain = min(p.nmain, nkb);
+      const int nslots = nmain + (x3 ? 1 : 0);
+      const int acc = (p.nacc == 2) ? (j & 1) : 0;
+      const uint32_t use = (uint32_t) (p.nacc == 2 ? (j >> 1) : j);
+      mbar_wait(tfull0 + 8 * acc, use & 1u, 2);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t) (acc * acc_cols) + ((uint32_t) (q * 32) << 16);
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is warp-collective; also fences the previous patch reads
+        tmem_ld32(tacc + (uint32_t) c0, v);
+        for (int sl = 1; sl < nslots; ++sl) {  // fp32 round-to-nearest sum of the accumulation chains
+          uint32_t w[32];
+          tmem_ld32(tacc + (uint32_t) (sl * p.bn + c0), w);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = __uint_as_float(v[j]);  // row = lane
-      __syncwarp();
-      const int n = n0 + c0 + lane;  // this lane's output column for the whole chunk
-      const bool n_ok = n < p.N;
-      const float bv = (n_ok && p.bias != nullptr && blockIdx.z == 0) ? __ldg(p.bias + n) : 0.f;
-      float t[32];
-#pragma unroll
-      for (int r = 0; r < 32; ++r) t[r] = patch[r * 33 + lane] + bv;  // 32 independent LDS in flight
-      const int mrow0 = m0 + q * 32;
-      if (n_ok) {
-        float* cp = p.c + (int64_t) mrow0 * p.ldc + n;
-        if (split) {
-#pragma unroll
-          for (int r = 0; r < 32; ++r)
-            if (mrow0 + r < p.M) b2_red_add(cp + (int64_t) r * p.ldc, t[r]);
-        } else {
-          if (p.c_pre != nullptr) {
-            float* pp = p.c_pre + (int64_t) mrow0 * p.ldc + n;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (mrow0 + r < p.M) pp[(int64_t) r * p.ldc] = t[r];
-          }
-          if (p.mul != nullptr) {
-            const float* mp = p.mul + (int64_t) mrow0 * p.ldc + n;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (mrow0 + r < p.M) t[r] *= __ldg(mp + (int64_t) r * p.ldc);
-          }
-          if (p.add != nullptr) {
-            const float* ap = p.add + (int64_t) mrow0 * p.ldc + n;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (mrow0 + r < p.M) t[r] += __ldg(ap + (int64_t) r * p.ldc);
-          }
-          if (p.act == B2_ACT_RELU) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) t[r] = fmaxf(t[r], 0.f);
-          } else if (p.act == B2_ACT_SIGMOID) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) t[r] = 1.f / (1.f + expf(-t[r]));
-          }
-          if (p.ybwd != nullptr) {   // activation backward of the PRODUCER of this gradient, fused
-            const float* yp = p.ybwd + (int64_t) mrow0 * p.ldc + n;
-            if (p.act_bwd == B2_ACT_RELU) {
-#pragma unroll
-              for (int r = 0; r < 32; ++r)
-                if (mrow0 + r < p.M) t[r] = (__ldg(yp + (int64_t) r * p.ldc) > 0.f) ? t[r] : 0.f;
-            } else if (p.act_bwd == B2_ACT_SIGMOID) {
-#pragma unroll
-              for (int r = 0; r < 32; ++r)
-                if (mrow0 + r < p.M) {
-                  const float yv = __ldg(yp + (int64_t) r * p.ldc);
-                  t[r] = t[r] * ((1.f - yv) * yv);
-                }
-            }
-          }
-          if (p.beta) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (mrow0 + r < p.M) t[r] += cp[(int64_t) r * p.ldc];
-          }
-#pragma unroll
-          for (int r = 0; r < 32; ++r)
-            if (mrow0 + r < p.M) cp[(int64_t) r * p.ldc] = t[r];   // 128 contiguous bytes per row
-          if (p.c_small != nullptr && p.esz == 4) {   // the consumer's 3xTF32 small part, produced where C is produced
-            float* sp = p.c_small + (int64_t) mrow0 * p.ld_aux + n;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (mrow0 + r < p.M) sp[(int64_t) r * p.ld_aux] = tf32_small(t[r]);
-          } else if (p.c_small != nullptr) {          // bf16 mode: the consumer's bf16 operand (round-to-nearest-even)
-            __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.c_small) + (int64_t) mrow0 * p.ld_aux + n;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (mrow0 + r < p.M) sp[(int64_t) r * p.ld_aux] = __float2bfloat16_rn(t[r]);
-          }
-          if (p.colsum != nullptr) {    // bias gradient: this lane owns column n of 32 rows
-            float cs = 0.f;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (mrow0 + r < p.M) cs += t[r];
-            b2_red_add(p.colsum + n, cs);
-          }
+          for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
         }
+        if (c0 + 32 >= p.bn) {      // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) patch[lane * 33 + jj] = __uint_as_float(v[jj]);  // row = lane
+        __syncwarp();
+        const int n = n0 + c0 + lane;  // this lane's output column for the whole chunk
+        const bool n_ok = n < p.N;
+        const float bv = (n_ok && p.bias != nullptr && z == 0) ? __ldg(p.bias + n) : 0.f;
+        float tt[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tt[r] = patch[r * 33 + lane] + bv;  // 32 independent LDS in flight
+        const int mrow0 = m0 + q * 32;
+        if (n_ok) epilogue_store(p, tt, mrow0, n, split);
       }
     }
   }
@@ -780,6 +824,11 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   p.a_mn = d->a_mn_major ? 1 : 0; p.b_mn = d->b_mn_major ? 1 : 0;
   p.beta = d->beta_accumulate ? 1 : 0;
   p.kb_per_split = (int) b2_ceil_div(num_kb, best_split);
+  const int splits = (int) b2_ceil_div(num_kb, p.kb_per_split);
+  const int64_t tiles_n = b2_ceil_div(N, best_bn);
+  const int64_t total_tiles = tiles_m * tiles_n * splits;
+  B2_REQUIRE(total_tiles < (1ll << 31), "too many tiles");
+  const bool multi = total_tiles > B2_NUM_SMS;        // some CTA processes more than one tile
   if (nseg == 1) {
     p.nmain = 1;
   } else {
@@ -787,13 +836,24 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     if (p.nmain > 4) p.nmain = 4;
     if (p.nmain > p.kb_per_split) p.nmain = p.kb_per_split;
   }
+  // Two accumulator stages (the epilogue of tile j under the main loop of tile j+1) when a CTA has
+  // several tiles and both stages fit the 512 TMEM columns; 3xTF32 gives up chains for it only down to 2
+  // (or to the k-block count of a short contraction).
+  p.nacc = 1;
+  if (multi) {
+    int nm = p.nmain;
+    const int corr = nseg > 1 ? 1 : 0;
+    while (nm > 1 && 2 * (nm + corr) * best_bn > 512) --nm;
+    const int floor_nm = (nseg > 1) ? (p.kb_per_split < 2 ? p.kb_per_split : 2) : 1;
+    if (2 * (nm + corr) * best_bn <= 512 && nm >= floor_nm) { p.nmain = nm; p.nacc = 2; }
+  }
   {
-    const int need = (p.nmain + (nseg > 1 ? 1 : 0)) * best_bn;
+    const int need = p.nacc * (p.nmain + (nseg > 1 ? 1 : 0)) * best_bn;
     int cols = 32;
     while (cols < need) cols <<= 1;
     p.tmem_cols = cols;
   }
-  const int splits = (int) b2_ceil_div(num_kb, p.kb_per_split);
+  p.tiles_m = (int) tiles_m; p.tiles_n = (int) tiles_n; p.splits = splits;
   if (splits > 1 && !p.beta && !(d->flags & B2_GEMM_C_IS_ZERO)) {
     cudaError_t e = cudaMemset2DAsync(c, (size_t) ldc * 4, 0, (size_t) N * 4, (size_t) M, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
@@ -802,14 +862,14 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     cudaError_t e = cudaMemsetAsync(d->colsum, 0, sizeof(float) * (size_t) N, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
-  const size_t smem = (nseg > 1 ? (size_t) 3 * 2 : (size_t) 4) * (tc::A_BYTES + (size_t) best_bn * 128) + 1024 + 128;
+  const size_t smem = (nseg > 1 ? (size_t) 3 * 2 : (size_t) 4) * (tc::A_BYTES + (size_t) best_bn * 128) +
+                      tc::PATCH_BYTES + 1024 + 128;
   // opt-in to > 48 KB of dynamic shared memory: an idempotent per-process property of the kernel
   // (C++11 guarantees the initialiser runs once, thread-safely)
   static const cudaError_t attr_rc = cudaFuncSetAttribute(
       tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr_rc != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(attr_rc));
-  dim3 grid((unsigned) tiles_m, (unsigned) b2_ceil_div(N, best_bn), (unsigned) splits);
-  B2_REQUIRE(grid.y <= 65535, "N too large for this launch geometry");
+  const int grid = (int) (total_tiles < B2_NUM_SMS ? total_tiles : B2_NUM_SMS);     // persistent: at most one CTA per SM
   B2_LAUNCH(tc::gemm_tf32_kernel, grid, tc::NTHREADS, smem, st, p);
   B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
   return B2_OK;
