@@ -18,10 +18,12 @@
 //     where big() is the hardware truncation itself and small = x - big(x) is produced by
 //     b2_split_tf32 — fp32-class accuracy (the 1e-5 parity bar) on tensor cores.
 //
-// Structure (one 128 x BN output tile per CTA, optional split-K across gridDim.z):
-//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles into a 4-stage ring
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias/act/mul/add -> global
+// Structure (persistent: at most one CTA per SM, striding over the 128 x BN output tiles x K splits):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles into a 3/4-stage ring
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one elect.sync lane), tcgen05.commit -> mbarriers
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> fused epilogue -> global
+//   TMEM holds 1 or 2 accumulator stages (full/empty mbarriers), so a CTA with several tiles never
+//   drains its pipelines between them.
 // Every mbarrier wait is bounded: a pipeline bug traps with a message instead of hanging the GPU.
 #include "b2_common.cuh"
 #include <string.h>
