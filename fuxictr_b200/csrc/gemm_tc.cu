@@ -27,6 +27,7 @@
 // Every mbarrier wait is bounded: a pipeline bug traps with a message instead of hanging the GPU.
 #include "b2_common.cuh"
 #include <string.h>
+#include <cstdlib>
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time
 
 namespace tc {
@@ -57,6 +58,7 @@ struct Params {
   int nmain;      // TMEM accumulators for the main (big x big) product: its K range is cut in nmain chunks
   int tiles_m, tiles_n, splits;   // tile grid; CTAs stride over tiles_m * tiles_n * splits work items
   int nacc;       // accumulator stages in TMEM (2: the epilogue of a tile overlaps the next main loop)
+  int stages;     // operand ring depth (<= MAX_STAGES), chosen by the host to fit 227 KB
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
 };
 
@@ -281,7 +283,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t b_bytes = (uint32_t) p.bn * 128u;
   const bool x3 = p.nseg > 1;
-  const int STAGES = x3 ? 3 : 4;
+  const int STAGES = p.stages;
   const uint32_t stage_bytes = (x3 ? 2u : 1u) * (A_BYTES + b_bytes);
   const uint32_t off_as = A_BYTES, off_b = (x3 ? 2u : 1u) * A_BYTES, off_bs = off_b + b_bytes;
   // after the ring: 4 epilogue transpose patches (32 x 33 floats each), then the mbarriers
@@ -794,7 +796,8 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   double best_cost = 1e300;
   // 3xTF32: (chains + 1 correction range) x bn <= 512 TMEM columns and 3 stages of {A, As, B, Bs} <= 227 KB:
   // bn <= 128 keeps 3-4 chains, bn = 160 keeps 2 (used when it saves a whole wave, e.g. 8192 x 624 x 624)
-  const int bn_max = (d->a_small != nullptr) ? 160 : 256;
+  static const int x3_bn_max = [] { const char* e = getenv("B2_X3_BN_MAX"); return e ? atoi(e) : 160; }();
+  const int bn_max = (d->a_small != nullptr) ? x3_bn_max : 256;
   const int bn_step = (d->b_mn_major && esz == 2) ? 64 : 32;   // an MN-major box is 128 bytes of rows
   for (int bn = bn_step; bn <= bn_max; bn += bn_step) {
     const int64_t tiles_n = b2_ceil_div(N, bn);
@@ -864,8 +867,14 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     cudaError_t e = cudaMemsetAsync(d->colsum, 0, sizeof(float) * (size_t) N, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
-  const size_t smem = (nseg > 1 ? (size_t) 3 * 2 : (size_t) 4) * (tc::A_BYTES + (size_t) best_bn * 128) +
-                      tc::PATCH_BYTES + 1024 + 128;
+  // operand ring: 4 stages of {A, B}, or 3 of {A, As, B, Bs} for 3xTF32 — one fewer when the widest
+  // 3xTF32 tile (bn = 160) would not leave room for the epilogue patches under 227 KB
+  const size_t stage_bytes = (nseg > 1 ? (size_t) 2 : (size_t) 1) * (tc::A_BYTES + (size_t) best_bn * 128);
+  const size_t fixed_bytes = tc::PATCH_BYTES + 1024 + 128;
+  p.stages = nseg > 1 ? 3 : tc::MAX_STAGES;
+  while (p.stages > 2 && p.stages * stage_bytes + fixed_bytes > (size_t) 227 * 1024) --p.stages;
+  B2_REQUIRE(p.stages * stage_bytes + fixed_bytes <= (size_t) 227 * 1024, "tile does not fit shared memory");
+  const size_t smem = p.stages * stage_bytes + fixed_bytes;
   // opt-in to > 48 KB of dynamic shared memory: an idempotent per-process property of the kernel
   // (C++11 guarantees the initialiser runs once, thread-safely)
   static const cudaError_t attr_rc = cudaFuncSetAttribute(

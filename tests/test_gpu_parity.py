@@ -678,13 +678,26 @@ def test_mlp_chain_matches_torch_autograd(mode, dims, acts, B):
         yg.backward(gout.cuda())
     finally:
         F2.set_matmul_precision("fp32")
-    # single-pass modes truncate (TF32: ~3e-3 per contraction, see test_gemm_tc_vs_fp64) / round (bf16) every
-    # operand of up to 8 chained contractions (forward + backward of 4 layers): percent-level, non-parity modes
-    tol = {"tf32x3": RTOL, "tf32": 5e-2, "bf16": 1e-1}[mode]
-    assert close(yg, yr, tol)
-    assert close(xg.grad, xr.grad, tol, atol=tol * float(xr.grad.abs().max()))
+    if mode == "tf32x3":                    # the parity-grade arithmetic: element-wise, north_star's 1e-5
+        assert close(yg, yr, RTOL)
+        assert close(xg.grad, xr.grad, RTOL, atol=RTOL * float(xr.grad.abs().max()))
+        for (k, pg), (_, pr) in zip(mlp.named_parameters(), ref.named_parameters()):
+            assert close(pg.grad, pr.grad, RTOL, atol=RTOL * float(pr.grad.abs().max())), k
+        return
+    # Single-pass modes truncate (TF32, ~1e-3 per contraction) or round (bf16, ~3e-3) every operand, so a
+    # pre-activation within that distance of zero takes the other ReLU branch than in float64 and moves
+    # its row of the input gradient by a whole unit's contribution (a few % of the row, and WHICH rows
+    # depends on rounding).  These are throughput modes, not parity modes: hold them to the size of the
+    # error over the whole tensor (Frobenius), not element by element.
+    tol = {"tf32": 2e-2, "bf16": 5e-2}[mode]
+
+    def fro(a, b):
+        b = b.to(torch.float64)
+        return float((a.detach().cpu().double() - b.cpu()).norm() / b.norm().clamp_min(1e-30))
+    assert fro(yg, yr) <= tol
+    assert fro(xg.grad, xr.grad) <= tol
     for (k, pg), (_, pr) in zip(mlp.named_parameters(), ref.named_parameters()):
-        assert close(pg.grad, pr.grad, tol, atol=tol * float(pr.grad.abs().max())), k
+        assert fro(pg.grad, pr.grad) <= tol, k
 
 
 @pytest.mark.parametrize("name", ["DeepFM", "DCNv2", "DLRM", "xDeepFM", "DIN"])
