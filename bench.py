@@ -194,9 +194,20 @@ class ClockSampler(object):
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, seconds=8.0):
+        """nvidia-smi takes a second or two to print its first row: wait for it before the timed region."""
+        t_end = time.time() + seconds
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.05)
+
+    def count_between(self, t0, t1):
+        return sum(1 for t, _ in self.rows if t0 <= t <= t1)
+
+    def stop(self, windows=None):
+        """Median SM clock and the throttle reasons over the rows sampled inside `windows`
+        (a list of (t0, t1) wall-clock intervals under load); all rows when windows is None."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -206,7 +217,9 @@ class ClockSampler(object):
             pass
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if windows is not None and not any(a <= t <= b for a, b in windows):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
@@ -726,9 +739,27 @@ def run_b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+    t_w0 = time.time()
     ms_total = timed(False, args.steps, warmup)
     ms_e2e = timed(True, args.steps, warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    t_w1 = time.time()
+    windows, clock_note = [(t_w0, t_w1)], "rows sampled inside the two timed regions"
+    if ms_total + ms_e2e < 600.0:
+        # a few hundred sub-millisecond steps end before nvidia-smi's 100 ms sampling sees them: keep the
+        # same step running back to back (untimed, every rank: the count follows from the all-reduced time)
+        # for ~0.8 s right after, and sample the clocks over it as well
+        n_extra = int(800.0 / max(ms_total / args.steps, 1e-3))
+        t_x0 = time.time()
+        for i in range(n_extra):
+            run_step(i, False)
+        torch.cuda.synchronize()
+        windows.append((t_x0, time.time()))
+        clock_note = ("timed regions (%.0f ms) are shorter than the sampling period: sampled over them plus "
+                      "%d further identical steps run back to back right after" % (ms_total + ms_e2e, n_extra))
+    clocks = sampler.stop(windows) if rank == 0 else None
+    if clocks is not None:
+        clocks["sampled"] = clock_note
     final_loss = pipe.loss()
     note("timed regions done")
     if rank != 0:

@@ -684,17 +684,18 @@ def test_mlp_chain_matches_torch_autograd(mode, dims, acts, B):
         for (k, pg), (_, pr) in zip(mlp.named_parameters(), ref.named_parameters()):
             assert close(pg.grad, pr.grad, RTOL, atol=RTOL * float(pr.grad.abs().max())), k
         return
-    # Single-pass modes truncate (TF32, ~1e-3 per contraction) or round (bf16, ~3e-3) every operand, so a
-    # pre-activation within that distance of zero takes the other ReLU branch than in float64 and moves
-    # its row of the input gradient by a whole unit's contribution (a few % of the row, and WHICH rows
-    # depends on rounding).  These are throughput modes, not parity modes: hold them to the size of the
-    # error over the whole tensor (Frobenius), not element by element.
-    tol = {"tf32": 2e-2, "bf16": 5e-2}[mode]
+    # Single-pass modes truncate (TF32, eps ~1e-3 per contraction) or round (bf16, ~4e-3) every operand, so
+    # the fraction ~0.8*eps of pre-activations that sit within eps of zero take the other ReLU branch than
+    # in float64; each such unit moves its row of the gradients by that unit's whole contribution, hence a
+    # gradient error of ~sqrt(0.8*eps) of the Frobenius norm (3 % TF32, 6-8 % bf16) however exact the GEMMs
+    # are (each one is held to its own bar in test_gemm_tc_*; torch's allow_tf32 behaves the same).  These
+    # are throughput modes, not parity modes: forward within a few eps, gradients within that kink bound.
+    tol_y, tol = {"tf32": (1e-2, 6e-2), "bf16": (3e-2, 1.5e-1)}[mode]
 
     def fro(a, b):
         b = b.to(torch.float64)
         return float((a.detach().cpu().double() - b.cpu()).norm() / b.norm().clamp_min(1e-30))
-    assert fro(yg, yr) <= tol
+    assert fro(yg, yr) <= tol_y
     assert fro(xg.grad, xr.grad) <= tol
     for (k, pg), (_, pr) in zip(mlp.named_parameters(), ref.named_parameters()):
         assert fro(pg.grad, pr.grad) <= tol, k

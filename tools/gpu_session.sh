@@ -39,6 +39,14 @@ for st in $stages; do
       B2_PDL=1 timeout 200 python bench.py --steps-only > gpurun_out/${tag}_pdl1.json 2> gpurun_out/${tag}_pdl1.err; cat gpurun_out/${tag}_pdl1.json; tail -3 gpurun_out/${tag}_pdl1.err
       timeout 300 python bench.py --workload dcnv2 --steps 100 --no-cpu-baseline > gpurun_out/${tag}_bench_dcnv2.json 2> gpurun_out/${tag}_bench_dcnv2.err; head -c 400 gpurun_out/${tag}_bench_dcnv2.json; echo
       timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/${tag}_gputests.log 2>&1; tail -8 gpurun_out/${tag}_gputests.log ;;
+    ab)
+      # A/B of the launch options on the default step: PDL on/off, widest 3xTF32 tile 128 vs 160
+      for v in "B2_PDL=0 B2_X3_BN_MAX=160" "B2_PDL=1 B2_X3_BN_MAX=160" "B2_PDL=0 B2_X3_BN_MAX=128" "B2_PDL=1 B2_X3_BN_MAX=128"; do
+        n=$(echo $v | tr -d ' =_A-Z')
+        env $v timeout 200 python bench.py --steps-only > gpurun_out/${tag}_ab_$n.json 2> gpurun_out/${tag}_ab_$n.err
+        echo "$v: $(python -c "import json,sys; d=json.loads(open('gpurun_out/${tag}_ab_$n.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'])" 2>&1 | tail -1)"
+      done
+      timeout 300 python bench.py --workload dcnv2 --steps 100 --no-cpu-baseline > gpurun_out/${tag}_bench_dcnv2.json 2> gpurun_out/${tag}_bench_dcnv2.err; head -c 400 gpurun_out/${tag}_bench_dcnv2.json; echo ;;
     dlrm_small)
       timeout 300 python bench.py --workload dlrm --vocab-scale 0.01 --steps 30 --warmup 5 --nbatches 8 --steps-only > gpurun_out/${tag}_bench_dlrmsmall_n1.json 2> gpurun_out/${tag}_bench_dlrmsmall_n1.err
       cat gpurun_out/${tag}_bench_dlrmsmall_n1.json; tail -30 gpurun_out/${tag}_bench_dlrmsmall_n1.err ;;
