@@ -40,6 +40,14 @@ struct BcastDst { void* p[16]; };
 #define B2_OWN_EMB (1 << 17)
 #define B2_OWN_LR (1 << 16)
 
+#define B2_OWN_ZERO (1 << 18)    // out-of-range id: the slot is defined as a zero row, no gradient
+
+// Two phases per 256-item chunk.  SCAN: one thread per (requester, sample, field) candidate reads the id
+// and keeps it only when this rank owns the row — the (world-1)/world candidates that belong to other
+// ranks cost one coalesced 4-byte load each.  SERVE: the block walks the compacted list in shared memory
+// with dim/4 lanes per entry (gather the table row, 16-byte P2P stores into the requester's slot), and
+// appends the entries that will receive a gradient to the rank's owned-row list with ONE global atomic
+// per chunk (a per-warp atomic on the one counter serialises ~1e5 times per launch at 8 ranks).
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 shard_push_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant__ B2FieldPack lr,
@@ -52,23 +60,24 @@ shard_push_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant
   SmemFields lf;
   lf.f = nullptr;
   lf.slot_start = nullptr;
-  if (has_lr) lf = b2_stage_fields(lr, smem_raw + ((pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15));
+  const size_t pack_bytes = (pack_smem_bytes(emb.nfields) + 15) & ~(size_t) 15;
+  if (has_lr) lf = b2_stage_fields(lr, smem_raw + pack_bytes);
+  int4* list = reinterpret_cast<int4*>(smem_raw + 2 * pack_bytes);      // 256 entries
+  __shared__ int s_front, s_back, s_gbase;
   const int F = emb.nfields;
   const int LPR = 1 << lpr_log2;
   const int lane = threadIdx.x & 31;
-  const int sub = lane & (LPR - 1);
-  const int my_group = lane >> lpr_log2;
+  const int sub = threadIdx.x & (LPR - 1);
   const int e = sub * 4;
   const int64_t per_rank = batch_local * (int64_t) F;
   const int64_t nitems = per_rank * world;
-  const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> lpr_log2;
-  const int64_t group = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> lpr_log2;
-  const int64_t warp_first = group - my_group;
-  const int64_t FD = (int64_t) F * dim;
-  for (int64_t wbase = warp_first; wbase < nitems; wbase += ngroups) {   // warp-uniform trip count
-    const int64_t item = wbase + my_group;
+  for (int64_t base = (int64_t) blockIdx.x * 256; base < nitems; base += (int64_t) gridDim.x * 256) {
+    if (threadIdx.x == 0) { s_front = 0; s_back = 0; }
+    __syncthreads();
+    // ---- scan
+    const int64_t item = base + threadIdx.x;
     int4 entry = make_int4(0, 0, 0, 0);
-    bool append = false;
+    int kind = 0;                       // 1: goes on the owned list (front), 2: served only (back)
     if (item < nitems) {
       const int p = (int) (item / per_rank);           // requesting rank
       const int64_t rem = item - (int64_t) p * per_rank;
@@ -78,42 +87,57 @@ shard_push_kernel(const __grid_constant__ B2FieldPack emb, const __grid_constant
       // fd.idx_stride carries the COLUMN of this field inside the batch matrix
       const int64_t row = b2_load_index<IdxT>(peers.ids[p], b * ids_stride + fd.idx_stride);
       if (row < 0 || row >= fd.vocab) {
-        if (status != nullptr && sub == 0 && p == rank) atomicMax(status, f + 1);
+        if (status != nullptr && p == rank) atomicMax(status, f + 1);
         if ((row < 0 ? 0 : (int) (row % world)) == rank) {  // keep the slot defined: zero row
-          if (e < dim)
-            *reinterpret_cast<float4*>(peers.emb[p] + b * FD + (int64_t) f * dim + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_lr && sub == 0) peers.lrw[p][b * F + f] = 0.f;
+          entry = make_int4(p, (int) rem, 0, f | B2_OWN_ZERO);
+          kind = 2;
         }
       } else if ((int) (row % world) == rank) {          // my row
-        const int64_t lrow = row / world;
+        int flags = (row != (int64_t) fd.padding_idx) ? B2_OWN_EMB : 0;     // padding rows get no gradient
+        if (has_lr && row != (int64_t) lf.f[f].padding_idx) flags |= B2_OWN_LR;
+        entry = make_int4(p, (int) rem, (int) (row / world), f | flags);
+        kind = (flags != 0 && owned != nullptr) ? 1 : 2;
+      }
+    }
+    // block compaction: list entries from the front, serve-only entries from the back
+    const unsigned m1 = __ballot_sync(0xffffffffu, kind == 1), m2 = __ballot_sync(0xffffffffu, kind == 2);
+    int b1 = 0, b2 = 0;
+    if (lane == 0) {
+      if (m1 != 0u) b1 = atomicAdd(&s_front, __popc(m1));
+      if (m2 != 0u) b2 = atomicAdd(&s_back, __popc(m2));
+    }
+    b1 = __shfl_sync(0xffffffffu, b1, 0);
+    b2 = __shfl_sync(0xffffffffu, b2, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (kind == 1) list[b1 + __popc(m1 & below)] = entry;
+    if (kind == 2) list[255 - (b2 + __popc(m2 & below))] = entry;
+    __syncthreads();
+    const int nfront = s_front, nback = s_back;
+    if (threadIdx.x == 0 && nfront > 0) s_gbase = atomicAdd(owned_count, nfront);
+    // ---- serve
+    const int nserve = nfront + nback;
+    for (int k = threadIdx.x >> lpr_log2; k < nserve; k += 256 >> lpr_log2) {
+      const int4 it = list[k < nfront ? k : 255 - (k - nfront)];
+      const int p = it.x, f = it.w & 0xffff;
+      const int64_t bf = it.y, lrow = it.z;
+      if (it.w & B2_OWN_ZERO) {
+        if (e < dim) *reinterpret_cast<float4*>(peers.emb[p] + bf * dim + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_lr && sub == 0) peers.lrw[p][bf] = 0.f;
+      } else {
         if (e < dim) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(fd.table) + lrow * dim + e));
-          *reinterpret_cast<float4*>(peers.emb[p] + b * FD + (int64_t) f * dim + e) = v;   // P2P store
+          const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sf.f[f].table) + lrow * dim + e));
+          *reinterpret_cast<float4*>(peers.emb[p] + bf * dim + e) = v;   // P2P store
         }
         if (has_lr && sub == 0)
-          peers.lrw[p][b * F + f] = __ldg(reinterpret_cast<const float*>(lf.f[f].table) + lrow);
-        if (owned != nullptr && sub == 0) {
-          int flags = (row != (int64_t) fd.padding_idx) ? B2_OWN_EMB : 0;     // padding rows get no gradient
-          if (has_lr && row != (int64_t) lf.f[f].padding_idx) flags |= B2_OWN_LR;
-          if (flags != 0) {
-            entry = make_int4(p, (int) rem, (int) lrow, f | flags);
-            append = true;
-          }
-        }
+          peers.lrw[p][bf] = __ldg(reinterpret_cast<const float*>(lf.f[f].table) + lrow);
       }
     }
-    if (owned != nullptr) {      // warp-aggregated append: one atomic per warp
-      const unsigned m = __ballot_sync(0xffffffffu, append);
-      if (m != 0u) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(owned_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (append) {
-          const int pos = base + __popc(m & ((1u << lane) - 1u));
-          if (pos < owned_cap) owned[pos] = entry;
-        }
-      }
+    __syncthreads();
+    if (threadIdx.x < nfront) {
+      const int pos = s_gbase + threadIdx.x;
+      if (pos < owned_cap) owned[pos] = list[threadIdx.x];
     }
+    __syncthreads();
   }
 }
 
@@ -361,8 +385,8 @@ extern "C" B2_API int b2_shard_push(const b2_field* emb_fields, const b2_field* 
   }
   const int dim = emb_fields[0].dim;
   const int lpr_log2 = next_pow2_log2((dim + 3) / 4);
-  const size_t smem = ((pack_smem_bytes(nfields) + 15) & ~(size_t) 15) + pack_smem_bytes(nfields) + 16;
-  const int grid = grid_for((batch_local * (int64_t) nfields * world) << lpr_log2, 256);
+  const size_t smem = 2 * ((pack_smem_bytes(nfields) + 15) & ~(size_t) 15) + 256 * sizeof(int4);
+  const int grid = grid_for(batch_local * (int64_t) nfields * world, 256);
   int4* ow = reinterpret_cast<int4*>(owned);
   switch (idx_dtype) {
     case B2_F64: shard_push_kernel<double><<<grid, 256, smem, st>>>(epack, lpack, pp, batch_local, ids_stride, dim, lpr_log2, has_lr, world, rank, status, ow, owned_count, owned_capacity); break;

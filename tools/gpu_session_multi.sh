@@ -1,6 +1,6 @@
 #!/bin/bash
 # Multi-GPU session (charged N x the box time: keep it short).  usage: tools/gpu_session_multi.sh <tag> <N> [stages...]
-#   stages: parity profile deepfm dlrm dlrm_small
+#   stages: parity profile deepfm dlrm dlrm_small, each optionally as stage@ranks (e.g. deepfm@4)
 tag=$1; N=$2; shift; shift
 stages=${@:-parity profile deepfm}
 mkdir -p gpurun_out
@@ -8,10 +8,13 @@ export PYTHONUNBUFFERED=1
 # the snapshot may have been taken between a source edit and its rebuild: build() is digest-stamped (no-op when current)
 python -c 'import __graft_entry__ as g; g.build()' > gpurun_out/${tag}_build.log 2>&1 || tail -5 gpurun_out/${tag}_build.log
 run() { timeout $1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) "${@:2}"; }
-for st in $stages; do
+N0=$N
+for tok in $stages; do
+  st=${tok%@*}; N=$N0
+  if [[ $tok == *@* ]]; then N=${tok#*@}; fi      # stage@ranks: run this stage on fewer ranks of the same box
   case $st in
     parity)
-      for model in DeepFM DLRM; do
+      for model in ${PARITY_MODELS:-DeepFM DLRM}; do
         run 300 tools/dist_sharded_check.py --model $model --precision tf32x3 > gpurun_out/${tag}_parity_${model}_n$N.log 2>&1
         grep -E "err|OK|FAIL|Error" gpurun_out/${tag}_parity_${model}_n$N.log | tail -$((N + 3))
       done ;;
