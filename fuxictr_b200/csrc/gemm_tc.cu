@@ -36,7 +36,8 @@ constexpr int BK = 32;           // fp32 elements per k-block == one 128-byte sw
 constexpr int UMMA_K_BYTES = 32; // kind::tf32: K = 8 elements of 4 bytes per instruction
 constexpr int MAX_STAGES = 4;  // 4 stages of (A,B) for one pass; 3 stages of (A,As,B,Bs) for 3xTF32
 constexpr int A_BYTES = BM * 128;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 192;          // producer, MMA issuer, 4 epilogue warps
+constexpr int NTHREADS_SPLIT = 320;    // + 4 converter warps (3xTF32 small parts made in shared memory)
 constexpr int PATCH_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose patches (one per epilogue warp)
 
 struct Params {
@@ -59,6 +60,7 @@ struct Params {
   int tiles_m, tiles_n, splits;   // tile grid; CTAs stride over tiles_m * tiles_n * splits work items
   int nacc;       // accumulator stages in TMEM (2: the epilogue of a tile overlaps the next main loop)
   int stages;     // operand ring depth (<= MAX_STAGES), chosen by the host to fit 227 KB
+  int inline_split;  // 3xTF32 with the small parts computed in shared memory by warps 6..9 (no As/Bs in HBM)
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
 };
 
@@ -275,7 +277,7 @@ __device__ __forceinline__ void epilogue_store(const Params& p, float (&t)[32], 
 // so the barrier / TMEM / descriptor prologue is paid once per CTA, the producer prefetches the next
 // tile's operands during an epilogue, and with nacc = 2 the epilogue of tile j overlaps the main loop
 // of tile j + 1.
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_SPLIT, 1)
 gemm_tf32_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte aligned bases: align by hand (1 KB of slack is requested).
@@ -289,10 +291,12 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   // after the ring: 4 epilogue transpose patches (32 x 33 floats each), then the mbarriers
   float* patch_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + PATCH_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES),
-                 tfull0 = smem_u32(bars + 2 * MAX_STAGES), tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
+                 tfull0 = smem_u32(bars + 2 * MAX_STAGES), tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2),
+                 conv0 = smem_u32(bars + 2 * MAX_STAGES + 4);
+  const bool inl = p.inline_split != 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bke = 128 / p.esz;                      // k elements per k-block: one 128-byte swizzle row
@@ -304,13 +308,14 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   const int acc_cols = (p.nmain + (x3 ? 1 : 0)) * p.bn;   // TMEM columns of one accumulator stage
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < (x3 ? 2 : 1); ++s) {
+    for (int s = 0; s < ((x3 && !inl) ? 2 : 1); ++s) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_a[s])) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_b[s])) : "memory");
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
+      mbar_init(conv0 + 8 * s, 4);      // one arrival per converter warp
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -348,11 +353,11 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         const uint32_t a_dst = smem_base + stage * stage_bytes;
         const uint32_t full = full0 + 8 * stage;
         if (elect_one()) {
-          mbar_expect_tx(full, stage_bytes);
+          mbar_expect_tx(full, inl ? (A_BYTES + b_bytes) : stage_bytes);
           // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products.
           // K-major operand: one box (128 B of k x rows).  MN-major operand: one box per 128 B of rows
           // (coordinates {row, k}); out-of-range boxes arrive zero-filled.
-          for (int s = 0; s < (x3 ? 2 : 1); ++s) {
+          for (int s = 0; s < ((x3 && !inl) ? 2 : 1); ++s) {
             const uint32_t a_t = a_dst + (s ? off_as : 0u), b_t = a_dst + (s ? off_bs : off_b);
             if (!p.a_mn) {
               tma_load_2d(a_t, &p.map_a[s], full, kb * bke, m0);
@@ -417,7 +422,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       // chain c covers k-blocks [ceil(c nkb / nmain), ceil((c+1) nkb / nmain)): divisions only at the boundaries
       int slot = 0, this_start = 0, next_start = (nkb + nmain - 1) / nmain;
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(full0 + 8 * stage, phase, 1);
+        mbar_wait((inl ? conv0 : full0) + 8 * stage, phase, 1);   // operands (and their small parts) are in place
         tc_fence_after();
         if (i == next_start) {
           ++slot;
@@ -455,7 +460,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       }
     }
 #undef B2_DESC
-  } else {
+  } else if (warp < 6) {
     // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----------------
     const int q = warp & 3;
     const bool split = p.splits > 1;
@@ -502,6 +507,52 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         for (int r = 0; r < 32; ++r) tt[r] = patch[r * 33 + lane] + bv;  // 32 independent LDS in flight
         const int mrow0 = m0 + q * 32;
         if (n_ok) epilogue_store(p, tt, mrow0, n, split);
+      }
+    }
+  } else {
+    // ---------------- converter warps 6..9 (inline 3xTF32): small = x - tf32(x), element for element ----------
+    // The small tiles have their operand's own shared-memory layout (whatever the swizzle), so the
+    // conversion is a flat 16-byte-per-lane pass: A -> As, B -> Bs.  Generic-proxy stores are made visible
+    // to the tensor core (async proxy) by fence.proxy.async before the arrival the MMA warp waits on.
+    const int cw = threadIdx.x - 6 * 32;          // 0..127
+    const int b_chunks = (int) (b_bytes >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int z = t / tiles_mn;
+      const int kb_begin = z * p.kb_per_split;
+      const int nkb = min(num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full0 + 8 * stage, phase, 4);
+        uint8_t* sb = smem + (size_t) stage * stage_bytes;
+        {
+          float4 v[A_BYTES / 16 / 128];
+#pragma unroll
+          for (int u = 0; u < A_BYTES / 16 / 128; ++u) v[u] = *reinterpret_cast<const float4*>(sb + 16 * (cw + 128 * u));
+#pragma unroll
+          for (int u = 0; u < A_BYTES / 16 / 128; ++u) {
+            float4 w;
+            w.x = tf32_small(v[u].x); w.y = tf32_small(v[u].y); w.z = tf32_small(v[u].z); w.w = tf32_small(v[u].w);
+            *reinterpret_cast<float4*>(sb + off_as + 16 * (cw + 128 * u)) = w;
+          }
+        }
+        for (int c = cw; c < b_chunks; c += 256) {
+          const float4 v0 = *reinterpret_cast<const float4*>(sb + off_b + 16 * c);
+          const bool two = c + 128 < b_chunks;
+          float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (two) v1 = *reinterpret_cast<const float4*>(sb + off_b + 16 * (c + 128));
+          float4 w;
+          w.x = tf32_small(v0.x); w.y = tf32_small(v0.y); w.z = tf32_small(v0.z); w.w = tf32_small(v0.w);
+          *reinterpret_cast<float4*>(sb + off_bs + 16 * c) = w;
+          if (two) {
+            w.x = tf32_small(v1.x); w.y = tf32_small(v1.y); w.z = tf32_small(v1.z); w.w = tf32_small(v1.w);
+            *reinterpret_cast<float4*>(sb + off_bs + 16 * (c + 128)) = w;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv0 + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -777,6 +828,9 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   B2_REQUIRE(d->act_bwd == B2_ACT_NONE || d->ybwd != nullptr, "act_bwd needs ybwd");
   B2_REQUIRE((d->a_small == nullptr) == (d->b_small == nullptr), "3xTF32 needs both small operands");
   B2_REQUIRE(esz == 4 || d->a_small == nullptr, "bf16 operands are single-pass (no small parts)");
+  const bool inline_split = (d->flags & B2_GEMM_X3_INLINE) != 0;
+  B2_REQUIRE(!inline_split || (esz == 4 && d->a_small == nullptr), "B2_GEMM_X3_INLINE: fp32 operands, no small parts");
+  const bool three_pass = inline_split || d->a_small != nullptr;
   const int64_t ld_aux = d->ld_aux > 0 ? d->ld_aux : ldc;
   B2_REQUIRE(d->c_small == nullptr || ld_aux >= N, "ld_aux too small");
   if (!tma_ok_e(a, lda, esz) || !tma_ok_e(b, ldb, esz) ||
@@ -797,7 +851,13 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   // 3xTF32: (chains + 1 correction range) x bn <= 512 TMEM columns and 3 stages of {A, As, B, Bs} <= 227 KB:
   // bn <= 128 keeps 3-4 chains, bn = 160 keeps 2 (used when it saves a whole wave, e.g. 8192 x 624 x 624)
   static const int x3_bn_max = [] { const char* e = getenv("B2_X3_BN_MAX"); return e ? atoi(e) : 160; }();
-  const int bn_max = (d->a_small != nullptr) ? x3_bn_max : 256;
+  // (inline split: 3 full stages matter more than the widest tile — the converters add a pipeline step)
+  const int bn_max = three_pass ? (inline_split ? (x3_bn_max < 128 ? x3_bn_max : 128) : x3_bn_max) : 256;
+  // cycles per k-block (128 bytes of K): the tensor pipe needs passes x 4 instructions x bn/2, the L2->SM
+  // fabric (~6300 B/cycle chip-wide, ~43 per SM) needs the operand bytes — 3xTF32 with small parts from HBM
+  // moves them twice
+  const double mma_per_bn = (three_pass ? 3.0 : 1.0) * 2.0;
+  const double l2_per_row = 3.0 * ((three_pass && !inline_split) ? 2.0 : 1.0);
   const int bn_step = (d->b_mn_major && esz == 2) ? 64 : 32;   // an MN-major box is 128 bytes of rows
   for (int bn = bn_step; bn <= bn_max; bn += bn_step) {
     const int64_t tiles_n = b2_ceil_div(N, bn);
@@ -807,15 +867,16 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
       const int64_t waves = b2_ceil_div(ctas, B2_NUM_SMS);
       const double kb = (double) b2_ceil_div(num_kb, split);
       // per-CTA time ~ fixed prologue/epilogue + k-blocks x bytes per k-block
-      const double cost = (double) waves * (24.0 * 160.0 + kb * (double) (tc::BM + bn));
+      const double per_kb = fmax(mma_per_bn * bn, l2_per_row * (double) (tc::BM + bn));
+      const double cost = (double) waves * (10000.0 + kb * per_kb);
       if (cost < best_cost) { best_cost = cost; best_bn = bn; best_split = split; }
     }
   }
   tc::Params p;
-  const int nseg = (d->a_small != nullptr) ? 3 : 1;
+  const int nseg = three_pass ? 3 : 1;
   const void* as[2] = {a, d->a_small};
   const void* bs[2] = {b, d->b_small};
-  for (int s = 0; s < (nseg > 1 ? 2 : 1); ++s) {
+  for (int s = 0; s < (d->a_small != nullptr ? 2 : 1); ++s) {
     int rc = encode_operand(&p.map_a[s], as[s], M, K, lda, d->a_mn_major, tc::BM, esz);
     if (rc != B2_OK) return rc;
     rc = encode_operand(&p.map_b[s], bs[s], N, K, ldb, d->b_mn_major, best_bn, esz);
@@ -824,7 +885,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   p.c = c; p.c_small = reinterpret_cast<float*>(d->c_small); p.c_pre = d->c_pre; p.ldc = ldc; p.ld_aux = ld_aux;
   p.bias = d->bias; p.mul = d->mul; p.add = d->add;
   p.ybwd = d->ybwd; p.colsum = d->colsum;
-  p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.act = d->act;
+  p.M = (int) M; p.N = (int) N; p.K = (int) K; p.bn = best_bn; p.nseg = nseg; p.inline_split = inline_split ? 1 : 0; p.act = d->act;
   p.act_bwd = d->act_bwd; p.esz = esz;
   p.a_mn = d->a_mn_major ? 1 : 0; p.b_mn = d->b_mn_major ? 1 : 0;
   p.beta = d->beta_accumulate ? 1 : 0;
@@ -870,7 +931,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   // operand ring: 4 stages of {A, B}, or 3 of {A, As, B, Bs} for 3xTF32 — one fewer when the widest
   // 3xTF32 tile (bn = 160) would not leave room for the epilogue patches under 227 KB
   const size_t stage_bytes = (nseg > 1 ? (size_t) 2 : (size_t) 1) * (tc::A_BYTES + (size_t) best_bn * 128);
-  const size_t fixed_bytes = tc::PATCH_BYTES + 1024 + 128;
+  const size_t fixed_bytes = tc::PATCH_BYTES + 1024 + 192;
   p.stages = nseg > 1 ? 3 : tc::MAX_STAGES;
   while (p.stages > 2 && p.stages * stage_bytes + fixed_bytes > (size_t) 227 * 1024) --p.stages;
   B2_REQUIRE(p.stages * stage_bytes + fixed_bytes <= (size_t) 227 * 1024, "tile does not fit shared memory");
@@ -881,7 +942,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
       tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr_rc != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(attr_rc));
   const int grid = (int) (total_tiles < B2_NUM_SMS ? total_tiles : B2_NUM_SMS);     // persistent: at most one CTA per SM
-  B2_LAUNCH(tc::gemm_tf32_kernel, grid, tc::NTHREADS, smem, st, p);
+  B2_LAUNCH(tc::gemm_tf32_kernel, grid, inline_split ? tc::NTHREADS_SPLIT : tc::NTHREADS, smem, st, p);
   B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
   return B2_OK;
 }

@@ -5,6 +5,7 @@ tape; all arithmetic happens in libfuxictr_b200.so.  Every function requires CUD
 tensors and raises otherwise — there is no eager/CPU fallback on this path.
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -375,7 +376,19 @@ def gemm_f32(a, b, out, a_t=False, b_t=False, bias=None, act=B2_ACT_NONE, mul=No
 #   "tf32"   tcgen05 tensor cores, single TF32 pass (10-bit mantissa, >= the bf16 of BASELINE configs[1])
 #   "bf16"   tcgen05 kind::f16 on bf16 copies of the operands, fp32 accumulation (BASELINE configs[1] "bf16");
 #            activations / weights / gradients stay fp32 in HBM, every producer also emits the bf16 operand
-_MATMUL = {"mode": "fp32"}
+#            3xTF32 reads the fp32 operands alone and derives the small parts in shared memory inside the
+#            GEMM (B2_GEMM_X3_INLINE, default); set_x3_inline(False) / B2_X3_INLINE=0 selects the older
+#            layout where every producer also writes its small part to HBM (kept as the A/B baseline)
+_MATMUL = {"mode": "fp32", "x3_inline": os.environ.get("B2_X3_INLINE", "1") != "0"}
+
+
+def set_x3_inline(on):
+    _MATMUL["x3_inline"] = bool(on)
+
+
+def _x3_aux():
+    """True when 3xTF32 wants auxiliary small-part tensors in HBM (the non-inline layout)."""
+    return _MATMUL["mode"] == "tf32x3" and not _MATMUL["x3_inline"]
 
 
 def set_matmul_precision(mode):
@@ -454,6 +467,8 @@ def gemm_ex(a, b, out, a_mn=False, b_mn=False, a_small=None, b_small=None, bias=
     d.act, d.act_bwd = act, (act_bwd if ybwd is not None else B2_ACT_NONE)
     d.beta_accumulate = 1 if accumulate else 0
     d.flags = (_lib.B2_GEMM_C_IS_ZERO if out_is_zero else 0) | (_lib.B2_GEMM_COLSUM_IS_ZERO if _is_zeroed(colsum) else 0)
+    if a_small is None and not bf16 and _MATMUL["mode"] == "tf32x3" and _MATMUL["x3_inline"]:
+        d.flags |= _lib.B2_GEMM_X3_INLINE
     _lib.call("b2_gemm_tc_ex", ctypes.byref(d), _stream())
     return out
 
@@ -497,7 +512,7 @@ def empty_aux(rows, cols, device):
     """Uninitialised auxiliary operand of a (rows, cols) fp32 tensor for the current precision: its 3xTF32
     small part (fp32, same layout), or its bf16 copy (row pitch padded to 16 bytes for TMA); None otherwise."""
     mode = _MATMUL["mode"]
-    if mode == "tf32x3":
+    if _x3_aux():
         return torch.empty((rows, cols), dtype=torch.float32, device=device)
     if mode == "bf16":
         return torch.empty((rows, _pad8(cols)), dtype=torch.bfloat16, device=device)[:, :cols]
@@ -507,6 +522,8 @@ def empty_aux(rows, cols, device):
 def make_aux(t):
     """The auxiliary operand of a contiguous-row fp32 matrix `t` (see empty_aux), computed in one launch."""
     mode = _MATMUL["mode"]
+    if mode == "tf32x3" and not _x3_aux():
+        return None
     base = t._base if t._base is not None else t
     hint = getattr(base, "_b2_aux", None)       # the producer already emitted it (fused front -> first MLP layer)
     if hint is not None and hint[0] == mode and hint[2] == base._version and t.is_contiguous() \
@@ -525,7 +542,7 @@ def make_aux(t):
 def weight_aux(w):
     """Auxiliary operand of a WEIGHT, cached until the weight changes (see bump_weight_epoch)."""
     mode = _MATMUL["mode"]
-    if mode not in ("tf32x3", "bf16"):
+    if mode != "bf16" and not _x3_aux():
         return None
     if not w.is_contiguous():
         raise RuntimeError("tensor-core GEMM weights must be contiguous")
@@ -625,7 +642,7 @@ class _LinearAct(torch.autograd.Function):
         gb = _grad_buffer(ctx.bias, zero=False) if need_b else None
         fused = act != B2_ACT_NONE
         if ctx.kind == "tc":
-            x3 = _MATMUL["mode"] == "tf32x3"
+            x3 = _x3_aux()
             # dZ = act'(Y) * dY, its 3xTF32 small part and the bias gradient: one pass over dY
             gz, gz_small, _, _ = prep_operand(gy, y if fused else None, act, want_out=fused, want_small=x3, colsum=gb)
             if not fused:
@@ -668,7 +685,7 @@ class _MLPChain(torch.autograd.Function):
         M = x.shape[0]
         L = len(acts)
         Ws, bs = params[0::2], params[1::2]
-        x3 = _MATMUL["mode"] == "tf32x3"
+        x3 = _x3_aux()
         kinds = []
         for W in Ws:
             if W.shape[0] == 1 and W.is_contiguous():
@@ -710,7 +727,7 @@ class _MLPChain(torch.autograd.Function):
         L = len(acts)
         M = hs[0].shape[0]
         dev = hs[0].device
-        x3 = _MATMUL["mode"] == "tf32x3"
+        x3 = _x3_aux()
         grads = [None] * len(params)
 
         def bias_buf(i):
@@ -816,7 +833,7 @@ class _CrossV2Layer(torch.autograd.Function):
         g = _f32c(g)
         bias = ctx.bias
         gb = _grad_buffer(bias, zero=False) if (bias is not None and bias.requires_grad) else None
-        x3 = _MATMUL["mode"] == "tf32x3"
+        x3 = _x3_aux()
         dlin, dlin_small, _, _ = prep_operand(g, x0, B2_PREP_MUL, want_out=True, want_small=x3 and ctx.tc, colsum=gb)
         if ctx.tc and dlin_small is None:
             dlin_small = make_aux(dlin)          # bf16 mode (None for single-pass TF32)
@@ -1135,7 +1152,7 @@ class _Front(torch.autograd.Function):
         lz = lazy.ctx_for(plan, lr_plan, emb_tables, lr_tables) if lazy is not None else None
         # 3xTF32: the rows' small parts are written by the same kernel (no split pass over the arena);
         # the MLP finds them through the arena tensor (make_aux looks at `_b2_aux` of its input's base)
-        small = torch.empty_like(arena) if (_MATMUL["mode"] == "tf32x3" and batch > 0) else None
+        small = torch.empty_like(arena) if (_x3_aux() and batch > 0) else None
         _lib.call("b2_front_fwd", descs, lr_descs, len(plan.fields), batch, ctx_code(idx_list),
                   1 if want_fm else 0, _ptr(bias), _ptr(logit), _ptr(sums), _ptr(status),
                   ctypes.byref(lz) if lz is not None else None, _ptr(small), _stream())

@@ -433,6 +433,7 @@ typedef struct b2_gemm_desc {
 } b2_gemm_desc;
 #define B2_GEMM_C_IS_ZERO 1      /* split-K accumulates into C with red.global: C needs no clearing */
 #define B2_GEMM_COLSUM_IS_ZERO 2
+#define B2_GEMM_X3_INLINE 4      /* 3xTF32 from the fp32 operands alone: the small parts are made in shared memory */
 B2_API int b2_gemm_tc_ex(const b2_gemm_desc* desc, void* stream);
 B2_API int b2_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                       void* stream);

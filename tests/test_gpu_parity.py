@@ -585,7 +585,7 @@ MN_SHAPES = [(128, 32, 32), (300, 624, 4096), (4096, 624, 300), (624, 300, 8192)
 
 @pytest.mark.parametrize("M,N,K", MN_SHAPES)
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("mode", ["tf32", "tf32x3", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3", "tf32x3_aux", "bf16"])
 def test_gemm_tc_mn_major_operands_vs_fp64(M, N, K, a_mn, b_mn, mode):
     """The contraction reads operands as they lie in memory: A stored (K, M) and/or B stored (K, N)
     (the dgrad / wgrad layouts of nn.Linear) through MN-major matrix descriptors — no transpose."""
@@ -597,6 +597,9 @@ def test_gemm_tc_mn_major_operands_vs_fp64(M, N, K, a_mn, b_mn, mode):
     a_dev = (a.t().contiguous() if a_mn else a).cuda()
     b_dev = (b.t().contiguous() if b_mn else b).cuda()
     out = torch.full((M, N), float("nan"), device="cuda")
+    # "tf32x3": small parts derived in shared memory inside the GEMM (default); "tf32x3_aux": read from HBM
+    F2.set_x3_inline(mode != "tf32x3_aux")
+    mode = mode.replace("_aux", "")
     F2.set_matmul_precision(mode)
     try:
         out_aux = F2.empty_aux(M, N, "cuda") if mode == "bf16" else None
@@ -604,6 +607,7 @@ def test_gemm_tc_mn_major_operands_vs_fp64(M, N, K, a_mn, b_mn, mode):
                    out_small=out_aux)
     finally:
         F2.set_matmul_precision("fp32")
+        F2.set_x3_inline(True)
     torch.cuda.synchronize()
     assert not torch.isnan(out).any()
     if mode == "bf16":      # checker: the same contraction of the bf16-rounded operands, in float64
@@ -643,7 +647,7 @@ def test_gemm_tc_fused_backward_epilogue(act_bwd):
     assert close(colsum, want.sum(dim=0), RTOL, atol=1e-5 * float(want.abs().sum(dim=0).max()))
 
 
-@pytest.mark.parametrize("mode", ["tf32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32x3_aux", "tf32", "bf16"])
 @pytest.mark.parametrize("dims,acts,B", [((624, 300, 300, 300, 1), ("relu", "relu", "relu", None), 4096),
                                          ((325, 64, 64, 64, 1), ("relu", "relu", "relu", "sigmoid"), 1000),
                                          ((128, 64, 1), ("sigmoid", None), 777),
@@ -671,6 +675,8 @@ def test_mlp_chain_matches_torch_autograd(mode, dims, acts, B):
     yr = ref.mlp(xr)
     yr.backward(gout.double())
     xg = x.cuda().requires_grad_(True)
+    F2.set_x3_inline(mode != "tf32x3_aux")
+    mode = mode.replace("_aux", "")
     F2.set_matmul_precision(mode)
     try:
         yg = mlp(xg)
@@ -678,6 +684,7 @@ def test_mlp_chain_matches_torch_autograd(mode, dims, acts, B):
         yg.backward(gout.cuda())
     finally:
         F2.set_matmul_precision("fp32")
+        F2.set_x3_inline(True)
     if mode == "tf32x3":                    # the parity-grade arithmetic: element-wise, north_star's 1e-5
         assert close(yg, yr, RTOL)
         assert close(xg.grad, xr.grad, RTOL, atol=RTOL * float(xr.grad.abs().max()))

@@ -40,13 +40,22 @@ for st in $stages; do
       timeout 300 python bench.py --workload dcnv2 --steps 100 --no-cpu-baseline > gpurun_out/${tag}_bench_dcnv2.json 2> gpurun_out/${tag}_bench_dcnv2.err; head -c 400 gpurun_out/${tag}_bench_dcnv2.json; echo
       timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/${tag}_gputests.log 2>&1; tail -8 gpurun_out/${tag}_gputests.log ;;
     ab)
-      # A/B of the launch options on the default step: PDL on/off, widest 3xTF32 tile 128 vs 160
-      for v in "B2_PDL=0 B2_X3_BN_MAX=160" "B2_PDL=1 B2_X3_BN_MAX=160" "B2_PDL=0 B2_X3_BN_MAX=128" "B2_PDL=1 B2_X3_BN_MAX=128"; do
+      # A/B of the launch options on the default step: inline 3xTF32 split on/off, PDL on/off
+      for v in "B2_X3_INLINE=0 B2_PDL=0" "B2_X3_INLINE=1 B2_PDL=0" "B2_X3_INLINE=1 B2_PDL=1" "B2_X3_INLINE=1 B2_X3_BN_MAX=96"; do
         n=$(echo $v | tr -d ' =_A-Z')
         env $v timeout 200 python bench.py --steps-only > gpurun_out/${tag}_ab_$n.json 2> gpurun_out/${tag}_ab_$n.err
         echo "$v: $(python -c "import json,sys; d=json.loads(open('gpurun_out/${tag}_ab_$n.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'])" 2>&1 | tail -1)"
-      done
-      timeout 300 python bench.py --workload dcnv2 --steps 100 --no-cpu-baseline > gpurun_out/${tag}_bench_dcnv2.json 2> gpurun_out/${tag}_bench_dcnv2.err; head -c 400 gpurun_out/${tag}_bench_dcnv2.json; echo ;;
+      done ;;
+    kernels)
+      timeout 400 python bench.py --no-cpu-baseline > gpurun_out/${tag}_kern.json 2> gpurun_out/${tag}_kern.err
+      python -c "
+import json; d=json.loads(open('gpurun_out/${tag}_kern.json').read().strip().splitlines()[-1])
+print(d['ms_per_step'], d['value'], d['clocks'])
+for k,v in d['kernels'].items(): print(k, round(v['ms']*1e3,2), 'us', v.get('frac_of_tf32_peak_counting_passes', v.get('frac_of_measured_hbm')))
+print({k:(v['launches'], round(v['us'],1)) for k,v in d['step_profile']['calls'].items()})
+" 2>&1 | tail -14; tail -3 gpurun_out/${tag}_kern.err ;;
+    pdltests)
+      B2_PDL=1 timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider -x --deselect tests/test_reference_boundary.py > gpurun_out/${tag}_pdltests.log 2>&1; tail -5 gpurun_out/${tag}_pdltests.log ;;
     dlrm_small)
       timeout 300 python bench.py --workload dlrm --vocab-scale 0.01 --steps 30 --warmup 5 --nbatches 8 --steps-only > gpurun_out/${tag}_bench_dlrmsmall_n1.json 2> gpurun_out/${tag}_bench_dlrmsmall_n1.err
       cat gpurun_out/${tag}_bench_dlrmsmall_n1.json; tail -30 gpurun_out/${tag}_bench_dlrmsmall_n1.err ;;
