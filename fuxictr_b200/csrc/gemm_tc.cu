@@ -36,9 +36,9 @@ constexpr int BK = 32;           // fp32 elements per k-block == one 128-byte sw
 constexpr int UMMA_K_BYTES = 32; // kind::tf32: K = 8 elements of 4 bytes per instruction
 constexpr int MAX_STAGES = 4;  // 4 stages of (A,B) for one pass; 3 stages of (A,As,B,Bs) for 3xTF32
 constexpr int A_BYTES = BM * 128;
-constexpr int NTHREADS = 192;          // producer, MMA issuer, 4 epilogue warps
-constexpr int NTHREADS_SPLIT = 320;    // + 4 converter warps (3xTF32 small parts made in shared memory)
-constexpr int PATCH_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose patches (one per epilogue warp)
+constexpr int NTHREADS = 320;   // producer, MMA issuer, 4 epilogue warps, 4 helper warps (second half of the epilogue
+                                // columns; with B2_GEMM_X3_INLINE they first make the 3xTF32 small parts in shared memory)
+constexpr int PATCH_BYTES = 8 * 32 * 33 * 4;   // epilogue transpose patches (one per epilogue / helper warp)
 
 struct Params {
   CUtensorMap map_a[2];   // [0] the operand, [1] its 3xTF32 small part
@@ -60,6 +60,7 @@ struct Params {
   int tiles_m, tiles_n, splits;   // tile grid; CTAs stride over tiles_m * tiles_n * splits work items
   int nacc;       // accumulator stages in TMEM (2: the epilogue of a tile overlaps the next main loop)
   int stages;     // operand ring depth (<= MAX_STAGES), chosen by the host to fit 227 KB
+  int dbg;        // B2_GEMM_DBG probe bits (timing experiments only: results are wrong when set)
   int inline_split;  // 3xTF32 with the small parts computed in shared memory by warps 6..9 (no As/Bs in HBM)
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
 };
@@ -277,7 +278,7 @@ __device__ __forceinline__ void epilogue_store(const Params& p, float (&t)[32], 
 // so the barrier / TMEM / descriptor prologue is paid once per CTA, the producer prefetches the next
 // tile's operands during an epilogue, and with nacc = 2 the epilogue of tile j overlaps the main loop
 // of tile j + 1.
-__global__ void __launch_bounds__(NTHREADS_SPLIT, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte aligned bases: align by hand (1 KB of slack is requested).
@@ -306,6 +307,10 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_mn * p.splits;
   const int acc_cols = (p.nmain + (x3 ? 1 : 0)) * p.bn;   // TMEM columns of one accumulator stage
+  // Warps 6..9 take every second 32-column chunk of the epilogue (TMEM lane quadrant = warp % 4, like warps
+  // 2..5).  With the inline split they are the converters first, so they help only when this CTA has a
+  // single tile (otherwise they are already converting the next tile's operands).
+  const bool helpers = (!inl || total_tiles <= (int) gridDim.x) && !(p.dbg & 32);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < ((x3 && !inl) ? 2 : 1); ++s) {
@@ -319,7 +324,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);    // one arrival per epilogue warp
+      mbar_init(tempty0 + 8 * a, helpers ? 8 : 4);    // one arrival per warp that reads the accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -339,6 +344,58 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   b2_pdl_trigger();
   b2_pdl_wait();
 
+  // One warp's share of a tile's epilogue: 32-column chunks first, first + step, ... of TMEM lane quadrant
+  // warp % 4.  Each warp owns a 32 x 33-float patch to transpose its TMEM rows, so that one store
+  // instruction writes 128 contiguous bytes of ONE output row instead of 16 bytes of 32 different rows
+  // (partial-sector writes to untouched lines cost an L2 fill each — measured 19 us per tile before this).
+  auto epilogue_tile = [&](int t, int j, int first, int step) {
+    const int q = warp & 3;
+    const bool split = p.splits > 1;
+    float* patch = patch_base + (warp - 2) * (32 * 33);
+    const int z = t / tiles_mn, rr = t - z * tiles_mn;
+    const int m0 = (rr / p.tiles_n) * BM, n0 = (rr % p.tiles_n) * p.bn;
+    const int kb_begin = z * p.kb_per_split;
+    const int nkb = min(num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
+    const int nmain = min(p.nmain, nkb);
+    const int nslots = nmain + (x3 ? 1 : 0);
+    const int acc = (p.nacc == 2) ? (j & 1) : 0;
+    const uint32_t use = (uint32_t) (p.nacc == 2 ? (j >> 1) : j);
+    mbar_wait(tfull0 + 8 * acc, use & 1u, 2);
+    tc_fence_after();
+    const uint32_t tacc = tmem_base + (uint32_t) (acc * acc_cols) + ((uint32_t) (q * 32) << 16);
+    if (first >= p.bn) {          // a helper warp with no chunk in a narrow tile still owes its arrival
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+    for (int c0 = first; c0 < p.bn; c0 += step) {
+      uint32_t v[32];
+      __syncwarp();  // tcgen05.ld is warp-collective; also fences the previous patch reads
+      tmem_ld32(tacc + (uint32_t) c0, v);
+      for (int sl = 1; sl < nslots; ++sl) {  // fp32 round-to-nearest sum of the accumulation chains
+        uint32_t w[32];
+        tmem_ld32(tacc + (uint32_t) (sl * p.bn + c0), w);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
+      }
+      if (c0 + step >= p.bn) {      // this warp's last TMEM read of the tile: hand the accumulator stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) patch[lane * 33 + jj] = __uint_as_float(v[jj]);  // row = lane
+      __syncwarp();
+      const int n = n0 + c0 + lane;  // this lane's output column for the whole chunk
+      const bool n_ok = n < p.N;
+      const float bv = (n_ok && p.bias != nullptr && z == 0) ? __ldg(p.bias + n) : 0.f;
+      float tt[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) tt[r] = patch[r * 33 + lane] + bv;  // 32 independent LDS in flight
+      const int mrow0 = m0 + q * 32;
+      if (n_ok && !(p.dbg & 2)) epilogue_store(p, tt, mrow0, n, split);
+    }
+  };
+
   if (warp == 0) {
     // ---------------- TMA producer (the warp loops converged; one elected lane issues) ----------------
     int stage = 0;
@@ -352,7 +409,8 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         mbar_wait(empty0 + 8 * stage, phase ^ 1, 0);
         const uint32_t a_dst = smem_base + stage * stage_bytes;
         const uint32_t full = full0 + 8 * stage;
-        if (elect_one()) {
+        if ((p.dbg & 16) && elect_one()) mbar_arrive(full);      // probe: no operand traffic at all
+        if (!(p.dbg & 16) && elect_one()) {
           mbar_expect_tx(full, inl ? (A_BYTES + b_bytes) : stage_bytes);
           // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products.
           // K-major operand: one box (128 B of k x rows).  MN-major operand: one box per 128 B of rows
@@ -421,9 +479,9 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       const uint32_t d_corr = tacc + (uint32_t) (nmain * p.bn);
       // chain c covers k-blocks [ceil(c nkb / nmain), ceil((c+1) nkb / nmain)): divisions only at the boundaries
       int slot = 0, this_start = 0, next_start = (nkb + nmain - 1) / nmain;
+      const uint32_t ready0 = inl ? conv0 : full0;           // operands (and their small parts) are in place
+      mbar_wait(ready0 + 8 * stage, phase, 1);
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait((inl ? conv0 : full0) + 8 * stage, phase, 1);   // operands (and their small parts) are in place
-        tc_fence_after();
         if (i == next_start) {
           ++slot;
           this_start = next_start;
@@ -432,100 +490,72 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         const uint32_t keep = (i == this_start) ? 0u : 1u;      // first k-block of a chain overwrites
         const uint32_t d_main = tacc + (uint32_t) (slot * p.bn);
         const uint32_t al = (uint32_t) a0 + so, bl = (uint32_t) b0 + so;
-        if (elect_one()) {
-          if (p.esz == 2) {       // bf16 operands: one pass on kind::f16, fp32 accumulation in TMEM
-#pragma unroll
-            for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
-              umma_bf16(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep);
-          } else if (!x3) {
-#pragma unroll
-            for (int k = 0; k < 128 / UMMA_K_BYTES; ++k)
-              umma_tf32(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep);
-          } else {
-            const uint32_t asl = (uint32_t) as0 + so, bsl = (uint32_t) bs0 + so;
-#pragma unroll
-            for (int k = 0; k < 128 / UMMA_K_BYTES; ++k) {
-              const uint64_t ad = B2_DESC(a_hi, al + k * ak), bd = B2_DESC(b_hi, bl + k * bk);
-              umma_tf32(d_main, ad, bd, idesc, (k > 0) ? 1u : keep);                                       // A_big . B_big
-              umma_tf32(d_corr, ad, B2_DESC(bs_hi, bsl + k * bk), idesc, (i > 0 || k > 0) ? 1u : 0u);     // A_big . B_small
-              umma_tf32(d_corr, B2_DESC(as_hi, asl + k * ak), bd, idesc, 1u);                              // A_small . B_big
-            }
-          }
-          umma_commit(empty0 + 8 * stage);                      // frees this smem slot once the MMAs have read it
-          if (i == nkb - 1) umma_commit(tfull0 + 8 * acc);      // ... and the last one: accumulator complete
-        }
+        const uint32_t asl = (uint32_t) as0 + so, bsl = (uint32_t) bs0 + so;
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
+        // The tensor pipe's instruction queue is short: whatever this thread does between the last MMA of
+        // one k-block and the first of the next is a bubble (measured ~380 cycles per k-block against 576 of
+        // MMA work).  So each k-block is issued in two halves and the wait for the NEXT stage sits between
+        // them, under the queued instructions of the first half.
+#define B2_ISSUE_HALF(K0)                                                                                      \
+        if (elect_one()) {                                                                                     \
+          if (p.dbg & 4) {        /* probe: no tensor work, only the pipeline hand-offs */                      \
+          } else if (p.esz == 2) {                                                                             \
+            _Pragma("unroll") for (int k = (K0); k < (K0) + 2; ++k)                                            \
+              umma_bf16(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep); \
+          } else if (!x3) {                                                                                    \
+            _Pragma("unroll") for (int k = (K0); k < (K0) + 2; ++k)                                            \
+              umma_tf32(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep); \
+          } else {                                                                                             \
+            _Pragma("unroll") for (int k = (K0); k < (K0) + 2; ++k) {                                          \
+              const uint64_t ad = B2_DESC(a_hi, al + k * ak), bd = B2_DESC(b_hi, bl + k * bk);                 \
+              umma_tf32(d_main, ad, bd, idesc, (k > 0) ? 1u : keep);                                   /* A_big . B_big */   \
+              umma_tf32(d_corr, ad, B2_DESC(bs_hi, bsl + k * bk), idesc, (i > 0 || k > 0) ? 1u : 0u); /* A_big . B_small */ \
+              umma_tf32(d_corr, B2_DESC(as_hi, asl + k * ak), bd, idesc, 1u);                          /* A_small . B_big */ \
+            }                                                                                                  \
+          }                                                                                                    \
+          if ((K0) == 2) {                                                                                     \
+            umma_commit(empty0 + 8 * stage);                      /* frees this smem slot once the MMAs have read it */ \
+            if (i == nkb - 1) umma_commit(tfull0 + 8 * acc);      /* ... and the last one: accumulator complete */      \
+          }                                                                                                    \
+        }                                                                                                      \
         __syncwarp();
+        B2_ISSUE_HALF(0)
+        if (i + 1 < nkb) mbar_wait(ready0 + 8 * nstage, nphase, 1);
+        B2_ISSUE_HALF(2)
+#undef B2_ISSUE_HALF
         so += stage_units;
-        if (++stage == STAGES) { stage = 0; phase ^= 1; so = 0; }
+        stage = nstage;
+        phase = nphase;
+        if (stage == 0) so = 0;
       }
     }
 #undef B2_DESC
   } else if (warp < 6) {
     // ---------------- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----------------
-    const int q = warp & 3;
-    const bool split = p.splits > 1;
-    // each epilogue warp owns a 32 x 33-float patch to transpose its TMEM rows, so that one store
-    // instruction writes 128 contiguous bytes of ONE output row instead of 16 bytes of 32 different rows
-    // (partial-sector writes to untouched lines cost an L2 fill each — measured 19 us per tile before this)
-    float* patch = patch_base + (warp - 2) * (32 * 33);
     int j = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
-      const int z = t / tiles_mn, rr = t - z * tiles_mn;
-      const int m0 = (rr / p.tiles_n) * BM, n0 = (rr % p.tiles_n) * p.bn;
-      const int kb_begin = z * p.kb_per_split;
-      const int nkb = min(num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
-      const int nmain = min(p.nmain, nkb);
-      const int nslots = nmain + (x3 ? 1 : 0);
-      const int acc = (p.nacc == 2) ? (j & 1) : 0;
-      const uint32_t use = (uint32_t) (p.nacc == 2 ? (j >> 1) : j);
-      mbar_wait(tfull0 + 8 * acc, use & 1u, 2);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t) (acc * acc_cols) + ((uint32_t) (q * 32) << 16);
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is warp-collective; also fences the previous patch reads
-        tmem_ld32(tacc + (uint32_t) c0, v);
-        for (int sl = 1; sl < nslots; ++sl) {  // fp32 round-to-nearest sum of the accumulation chains
-          uint32_t w[32];
-          tmem_ld32(tacc + (uint32_t) (sl * p.bn + c0), w);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(w[jj]));
-        }
-        if (c0 + 32 >= p.bn) {      // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-        }
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) patch[lane * 33 + jj] = __uint_as_float(v[jj]);  // row = lane
-        __syncwarp();
-        const int n = n0 + c0 + lane;  // this lane's output column for the whole chunk
-        const bool n_ok = n < p.N;
-        const float bv = (n_ok && p.bias != nullptr && z == 0) ? __ldg(p.bias + n) : 0.f;
-        float tt[32];
-#pragma unroll
-        for (int r = 0; r < 32; ++r) tt[r] = patch[r * 33 + lane] + bv;  // 32 independent LDS in flight
-        const int mrow0 = m0 + q * 32;
-        if (n_ok) epilogue_store(p, tt, mrow0, n, split);
-      }
-    }
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j)
+      epilogue_tile(t, j, 0, helpers ? 64 : 32);
   } else {
-    // ---------------- converter warps 6..9 (inline 3xTF32): small = x - tf32(x), element for element ----------
-    // The small tiles have their operand's own shared-memory layout (whatever the swizzle), so the
-    // conversion is a flat 16-byte-per-lane pass: A -> As, B -> Bs.  Generic-proxy stores are made visible
-    // to the tensor core (async proxy) by fence.proxy.async before the arrival the MMA warp waits on.
+    // ---------------- helper warps 6..9 ----------------
+    // Inline 3xTF32: small = x - tf32(x), element for element.  The small tiles have their operand's own
+    // shared-memory layout (whatever the swizzle), so the conversion is a flat 16-byte-per-lane pass:
+    // A -> As, B -> Bs.  Generic-proxy stores are made visible to the tensor core (async proxy) by
+    // fence.proxy.async before the arrival the MMA warp waits on.  Then (or only) the odd epilogue chunks.
     const int cw = threadIdx.x - 6 * 32;          // 0..127
     const int b_chunks = (int) (b_bytes >> 4);
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int j = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       const int z = t / tiles_mn;
       const int kb_begin = z * p.kb_per_split;
       const int nkb = min(num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = 0; inl && i < nkb; ++i) {
         mbar_wait(full0 + 8 * stage, phase, 4);
         uint8_t* sb = smem + (size_t) stage * stage_bytes;
-        {
+        if (!(p.dbg & 1)) {
           float4 v[A_BYTES / 16 / 128];
 #pragma unroll
           for (int u = 0; u < A_BYTES / 16 / 128; ++u) v[u] = *reinterpret_cast<const float4*>(sb + 16 * (cw + 128 * u));
@@ -536,7 +566,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
             *reinterpret_cast<float4*>(sb + off_as + 16 * (cw + 128 * u)) = w;
           }
         }
-        for (int c = cw; c < b_chunks; c += 256) {
+        for (int c = cw; c < ((p.dbg & 1) ? 0 : b_chunks); c += 256) {
           const float4 v0 = *reinterpret_cast<const float4*>(sb + off_b + 16 * c);
           const bool two = c + 128 < b_chunks;
           float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -554,6 +584,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         if (lane == 0) mbar_arrive(conv0 + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (helpers) epilogue_tile(t, j, 32, 64);
     }
   }
   tc_fence_before();
@@ -850,9 +881,8 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   double best_cost = 1e300;
   // 3xTF32: (chains + 1 correction range) x bn <= 512 TMEM columns and 3 stages of {A, As, B, Bs} <= 227 KB:
   // bn <= 128 keeps 3-4 chains, bn = 160 keeps 2 (used when it saves a whole wave, e.g. 8192 x 624 x 624)
-  static const int x3_bn_max = [] { const char* e = getenv("B2_X3_BN_MAX"); return e ? atoi(e) : 160; }();
-  // (inline split: 3 full stages matter more than the widest tile — the converters add a pipeline step)
-  const int bn_max = three_pass ? (inline_split ? (x3_bn_max < 128 ? x3_bn_max : 128) : x3_bn_max) : 256;
+  const int x3_bn_max = [] { const char* e = getenv("B2_X3_BN_MAX"); return e ? atoi(e) : 160; }();
+  const int bn_max = three_pass ? x3_bn_max : 256;
   // cycles per k-block (128 bytes of K): the tensor pipe needs passes x 4 instructions x bn/2, the L2->SM
   // fabric (~6300 B/cycle chip-wide, ~43 per SM) needs the operand bytes — 3xTF32 with small parts from HBM
   // moves them twice
@@ -932,7 +962,9 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   // 3xTF32 tile (bn = 160) would not leave room for the epilogue patches under 227 KB
   const size_t stage_bytes = (nseg > 1 ? (size_t) 2 : (size_t) 1) * (tc::A_BYTES + (size_t) best_bn * 128);
   const size_t fixed_bytes = tc::PATCH_BYTES + 1024 + 192;
+  { const char* e = getenv("B2_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.stages = nseg > 1 ? 3 : tc::MAX_STAGES;
+  if (p.dbg & 8) p.stages = 2;
   while (p.stages > 2 && p.stages * stage_bytes + fixed_bytes > (size_t) 227 * 1024) --p.stages;
   B2_REQUIRE(p.stages * stage_bytes + fixed_bytes <= (size_t) 227 * 1024, "tile does not fit shared memory");
   const size_t smem = p.stages * stage_bytes + fixed_bytes;
@@ -942,7 +974,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
       tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr_rc != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(attr_rc));
   const int grid = (int) (total_tiles < B2_NUM_SMS ? total_tiles : B2_NUM_SMS);     // persistent: at most one CTA per SM
-  B2_LAUNCH(tc::gemm_tf32_kernel, grid, inline_split ? tc::NTHREADS_SPLIT : tc::NTHREADS, smem, st, p);
+  B2_LAUNCH(tc::gemm_tf32_kernel, grid, tc::NTHREADS, smem, st, p);
   B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
   return B2_OK;
 }

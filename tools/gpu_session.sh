@@ -54,6 +54,8 @@ print(d['ms_per_step'], d['value'], d['clocks'])
 for k,v in d['kernels'].items(): print(k, round(v['ms']*1e3,2), 'us', v.get('frac_of_tf32_peak_counting_passes', v.get('frac_of_measured_hbm')))
 print({k:(v['launches'], round(v['us'],1)) for k,v in d['step_profile']['calls'].items()})
 " 2>&1 | tail -14; tail -3 gpurun_out/${tag}_kern.err ;;
+    probe)
+      timeout 300 python tools/gemm_probe.py > gpurun_out/${tag}_probe.log 2>&1; cat gpurun_out/${tag}_probe.log | cut -c1-400 ;;
     pdltests)
       B2_PDL=1 timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider -x --deselect tests/test_reference_boundary.py > gpurun_out/${tag}_pdltests.log 2>&1; tail -5 gpurun_out/${tag}_pdltests.log ;;
     dlrm_small)
