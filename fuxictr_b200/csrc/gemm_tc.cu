@@ -60,6 +60,7 @@ struct Params {
   int tiles_m, tiles_n, splits;   // tile grid; CTAs stride over tiles_m * tiles_n * splits work items
   int nacc;       // accumulator stages in TMEM (2: the epilogue of a tile overlaps the next main loop)
   int stages;     // operand ring depth (<= MAX_STAGES), chosen by the host to fit 227 KB
+  long long* trace;   // B2_GEMM_TRACE probe: CTA 0 writes clock64() stamps of its producer / MMA loops here
   int dbg;        // B2_GEMM_DBG probe bits (timing experiments only: results are wrong when set)
   int inline_split;  // 3xTF32 with the small parts computed in shared memory by warps 6..9 (no As/Bs in HBM)
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
@@ -289,9 +290,12 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   const int STAGES = p.stages;
   const uint32_t stage_bytes = (x3 ? 2u : 1u) * (A_BYTES + b_bytes);
   const uint32_t off_as = A_BYTES, off_b = (x3 ? 2u : 1u) * A_BYTES, off_bs = off_b + b_bytes;
-  // after the ring: 4 epilogue transpose patches (32 x 33 floats each), then the mbarriers
-  float* patch_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + PATCH_BYTES);
+  // The 8 epilogue transpose patches (32 x 33 floats each) follow the ring — or, when every CTA has exactly
+  // one tile, lie ON the ring: the accumulator is complete only after every MMA has read its operands and
+  // nothing is loaded afterwards, so the ring is dead by then and its bytes buy one more stage instead.
+  const bool single_tile = p.tiles_m * p.tiles_n * p.splits <= (int) gridDim.x;
+  float* patch_base = reinterpret_cast<float*>(smem + (single_tile ? 0u : STAGES * stage_bytes));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + (single_tile ? 0 : PATCH_BYTES));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES),
@@ -339,6 +343,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[640] = clock64();
   // PDL: everything above touched only shared memory, TMEM and the kernel parameters; from here on the
   // predecessor's outputs are read.  Let the successor begin ITS prologue once every CTA got this far.
   b2_pdl_trigger();
@@ -360,7 +365,9 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     const int nslots = nmain + (x3 ? 1 : 0);
     const int acc = (p.nacc == 2) ? (j & 1) : 0;
     const uint32_t use = (uint32_t) (p.nacc == 2 ? (j >> 1) : j);
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[512 + 4 * warp + 0] = clock64();
     mbar_wait(tfull0 + 8 * acc, use & 1u, 2);
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[512 + 4 * warp + 1] = clock64();
     tc_fence_after();
     const uint32_t tacc = tmem_base + (uint32_t) (acc * acc_cols) + ((uint32_t) (q * 32) << 16);
     if (first >= p.bn) {          // a helper warp with no chunk in a narrow tile still owes its arrival
@@ -394,6 +401,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       const int mrow0 = m0 + q * 32;
       if (n_ok && !(p.dbg & 2)) epilogue_store(p, tt, mrow0, n, split);
     }
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[512 + 4 * warp + 2] = clock64();
   };
 
   if (warp == 0) {
@@ -406,7 +414,10 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       const int kb_begin = z * p.kb_per_split;
       const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && kb - kb_begin < 60;
+        if (tr) p.trace[4 * (kb - kb_begin) + 0] = clock64();
         mbar_wait(empty0 + 8 * stage, phase ^ 1, 0);
+        if (tr) p.trace[4 * (kb - kb_begin) + 1] = clock64();
         const uint32_t a_dst = smem_base + stage * stage_bytes;
         const uint32_t full = full0 + 8 * stage;
         if ((p.dbg & 16) && elect_one()) mbar_arrive(full);      // probe: no operand traffic at all
@@ -430,6 +441,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
           }
         }
         __syncwarp();
+        if (tr) p.trace[4 * (kb - kb_begin) + 2] = clock64();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -496,8 +508,8 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
         // The tensor pipe's instruction queue is short: whatever this thread does between the last MMA of
         // one k-block and the first of the next is a bubble (measured ~380 cycles per k-block against 576 of
-        // MMA work).  So each k-block is issued in two halves and the wait for the NEXT stage sits between
-        // them, under the queued instructions of the first half.
+        // MMA work).  So each k-block is issued in two halves and the look at the NEXT stage's barrier sits
+        // between them, under the queued instructions of the first half.
 #define B2_ISSUE_HALF(K0)                                                                                      \
         if (elect_one()) {                                                                                     \
           if (p.dbg & 4) {        /* probe: no tensor work, only the pipeline hand-offs */                      \
@@ -521,10 +533,19 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
           }                                                                                                    \
         }                                                                                                      \
         __syncwarp();
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && i < 60;
+        if (tr) p.trace[256 + 4 * i + 0] = clock64();
         B2_ISSUE_HALF(0)
-        if (i + 1 < nkb) mbar_wait(ready0 + 8 * nstage, nphase, 1);
+        if (tr) p.trace[256 + 4 * i + 1] = clock64();
+        // non-blocking look at the next stage under the queued first half; block for it only after the
+        // second half is queued too (a blocking wait here would hold back MMAs whose operands are present)
+        const bool more = i + 1 < nkb;
+        const bool next_ready = more && __all_sync(0xffffffffu, mbar_try_wait(ready0 + 8 * nstage, nphase));
         B2_ISSUE_HALF(2)
 #undef B2_ISSUE_HALF
+        if (tr) p.trace[256 + 4 * i + 2] = clock64();
+        if (more && !next_ready) mbar_wait(ready0 + 8 * nstage, nphase, 1);
+        if (tr) p.trace[256 + 4 * i + 3] = clock64();
         so += stage_units;
         stage = nstage;
         phase = nphase;
@@ -961,19 +982,22 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   // operand ring: 4 stages of {A, B}, or 3 of {A, As, B, Bs} for 3xTF32 — one fewer when the widest
   // 3xTF32 tile (bn = 160) would not leave room for the epilogue patches under 227 KB
   const size_t stage_bytes = (nseg > 1 ? (size_t) 2 : (size_t) 1) * (tc::A_BYTES + (size_t) best_bn * 128);
-  const size_t fixed_bytes = tc::PATCH_BYTES + 1024 + 192;
+  const int grid = (int) (total_tiles < B2_NUM_SMS ? total_tiles : B2_NUM_SMS);     // persistent: at most one CTA per SM
+  // (one tile per CTA: the epilogue patches reuse the ring, see the kernel)
+  const size_t fixed_bytes = (total_tiles <= grid ? 0 : tc::PATCH_BYTES) + 1024 + 192;
   { const char* e = getenv("B2_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
-  p.stages = nseg > 1 ? 3 : tc::MAX_STAGES;
+  { const char* e = getenv("B2_GEMM_TRACE"); p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+  p.stages = tc::MAX_STAGES;       // as deep as 227 KB allows (3xTF32 stages are twice the size)
   if (p.dbg & 8) p.stages = 2;
   while (p.stages > 2 && p.stages * stage_bytes + fixed_bytes > (size_t) 227 * 1024) --p.stages;
   B2_REQUIRE(p.stages * stage_bytes + fixed_bytes <= (size_t) 227 * 1024, "tile does not fit shared memory");
+  B2_REQUIRE(p.stages * stage_bytes >= (size_t) tc::PATCH_BYTES, "ring smaller than the epilogue patches");
   const size_t smem = p.stages * stage_bytes + fixed_bytes;
   // opt-in to > 48 KB of dynamic shared memory: an idempotent per-process property of the kernel
   // (C++11 guarantees the initialiser runs once, thread-safely)
   static const cudaError_t attr_rc = cudaFuncSetAttribute(
       tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr_rc != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: smem attribute: %s", cudaGetErrorString(attr_rc));
-  const int grid = (int) (total_tiles < B2_NUM_SMS ? total_tiles : B2_NUM_SMS);     // persistent: at most one CTA per SM
   B2_LAUNCH(tc::gemm_tf32_kernel, grid, tc::NTHREADS, smem, st, p);
   B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
   return B2_OK;

@@ -56,6 +56,8 @@ print({k:(v['launches'], round(v['us'],1)) for k,v in d['step_profile']['calls']
 " 2>&1 | tail -14; tail -3 gpurun_out/${tag}_kern.err ;;
     probe)
       timeout 300 python tools/gemm_probe.py > gpurun_out/${tag}_probe.log 2>&1; cat gpurun_out/${tag}_probe.log | cut -c1-400 ;;
+    trace)
+      for k in fwd dgrad wgrad; do for m in aux inline; do timeout 120 python tools/gemm_trace.py $m $k > gpurun_out/${tag}_trace_${m}_$k.log 2>&1; done; done; cat gpurun_out/${tag}_trace_aux_fwd.log gpurun_out/${tag}_trace_aux_dgrad.log ;;
     pdltests)
       B2_PDL=1 timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider -x --deselect tests/test_reference_boundary.py > gpurun_out/${tag}_pdltests.log 2>&1; tail -5 gpurun_out/${tag}_pdltests.log ;;
     dlrm_small)
