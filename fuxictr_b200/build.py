@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
 ]
+if os.environ.get("B2_BUILD_PROBE", "0") != "0":     # timing probes of gemm_tc.cu (tools/gemm_probe.py, gemm_trace.py)
+    NVCC_FLAGS.append("-DB2_GEMM_PROBE")
 
 
 def _nvcc():

@@ -40,6 +40,16 @@ constexpr int NTHREADS = 320;   // producer, MMA issuer, 4 epilogue warps, 4 hel
                                 // columns; with B2_GEMM_X3_INLINE they first make the 3xTF32 small parts in shared memory)
 constexpr int PATCH_BYTES = 8 * 32 * 33 * 4;   // epilogue transpose patches (one per epilogue / helper warp)
 
+// Timing probes (tools/gemm_probe.py, tools/gemm_trace.py): compiled in only with -DB2_GEMM_PROBE
+// (B2_BUILD_PROBE=1 python -m fuxictr_b200.build); the product build has no debug hooks.
+#ifdef B2_GEMM_PROBE
+#define B2_DBG(bit) ((p.dbg & (bit)) != 0)
+#define B2_STAMP(cond, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (cond)) p.trace[idx] = clock64(); } while (0)
+#else
+#define B2_DBG(bit) false
+#define B2_STAMP(cond, idx) do { } while (0)
+#endif
+
 struct Params {
   CUtensorMap map_a[2];   // [0] the operand, [1] its 3xTF32 small part
   CUtensorMap map_b[2];
@@ -60,8 +70,8 @@ struct Params {
   int tiles_m, tiles_n, splits;   // tile grid; CTAs stride over tiles_m * tiles_n * splits work items
   int nacc;       // accumulator stages in TMEM (2: the epilogue of a tile overlaps the next main loop)
   int stages;     // operand ring depth (<= MAX_STAGES), chosen by the host to fit 227 KB
-  long long* trace;   // B2_GEMM_TRACE probe: CTA 0 writes clock64() stamps of its producer / MMA loops here
-  int dbg;        // B2_GEMM_DBG probe bits (timing experiments only: results are wrong when set)
+  long long* trace;   // probe build only: CTA 0 writes clock64() stamps of its loops here (B2_GEMM_TRACE)
+  int dbg;        // probe build only: B2_GEMM_DBG bits (timing experiments; results are wrong when set)
   int inline_split;  // 3xTF32 with the small parts computed in shared memory by warps 6..9 (no As/Bs in HBM)
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
 };
@@ -314,7 +324,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   // Warps 6..9 take every second 32-column chunk of the epilogue (TMEM lane quadrant = warp % 4, like warps
   // 2..5).  With the inline split they are the converters first, so they help only when this CTA has a
   // single tile (otherwise they are already converting the next tile's operands).
-  const bool helpers = (!inl || total_tiles <= (int) gridDim.x) && !(p.dbg & 32);
+  const bool helpers = (!inl || total_tiles <= (int) gridDim.x) && !B2_DBG(32);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < ((x3 && !inl) ? 2 : 1); ++s) {
@@ -343,7 +353,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[640] = clock64();
+  B2_STAMP(threadIdx.x == 0, 640);
   // PDL: everything above touched only shared memory, TMEM and the kernel parameters; from here on the
   // predecessor's outputs are read.  Let the successor begin ITS prologue once every CTA got this far.
   b2_pdl_trigger();
@@ -365,9 +375,9 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     const int nslots = nmain + (x3 ? 1 : 0);
     const int acc = (p.nacc == 2) ? (j & 1) : 0;
     const uint32_t use = (uint32_t) (p.nacc == 2 ? (j >> 1) : j);
-    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[512 + 4 * warp + 0] = clock64();
+    B2_STAMP(lane == 0, 512 + 4 * warp + 0);
     mbar_wait(tfull0 + 8 * acc, use & 1u, 2);
-    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[512 + 4 * warp + 1] = clock64();
+    B2_STAMP(lane == 0, 512 + 4 * warp + 1);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (uint32_t) (acc * acc_cols) + ((uint32_t) (q * 32) << 16);
     if (first >= p.bn) {          // a helper warp with no chunk in a narrow tile still owes its arrival
@@ -399,9 +409,9 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 #pragma unroll
       for (int r = 0; r < 32; ++r) tt[r] = patch[r * 33 + lane] + bv;  // 32 independent LDS in flight
       const int mrow0 = m0 + q * 32;
-      if (n_ok && !(p.dbg & 2)) epilogue_store(p, tt, mrow0, n, split);
+      if (n_ok && !B2_DBG(2)) epilogue_store(p, tt, mrow0, n, split);
     }
-    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[512 + 4 * warp + 2] = clock64();
+    B2_STAMP(lane == 0, 512 + 4 * warp + 2);
   };
 
   if (warp == 0) {
@@ -414,14 +424,13 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       const int kb_begin = z * p.kb_per_split;
       const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && kb - kb_begin < 60;
-        if (tr) p.trace[4 * (kb - kb_begin) + 0] = clock64();
+        B2_STAMP(lane == 0 && kb - kb_begin < 60, 4 * (kb - kb_begin) + 0);
         mbar_wait(empty0 + 8 * stage, phase ^ 1, 0);
-        if (tr) p.trace[4 * (kb - kb_begin) + 1] = clock64();
+        B2_STAMP(lane == 0 && kb - kb_begin < 60, 4 * (kb - kb_begin) + 1);
         const uint32_t a_dst = smem_base + stage * stage_bytes;
         const uint32_t full = full0 + 8 * stage;
-        if ((p.dbg & 16) && elect_one()) mbar_arrive(full);      // probe: no operand traffic at all
-        if (!(p.dbg & 16) && elect_one()) {
+        if (B2_DBG(16) && elect_one()) mbar_arrive(full);      // probe: no operand traffic at all
+        if (!B2_DBG(16) && elect_one()) {
           mbar_expect_tx(full, inl ? (A_BYTES + b_bytes) : stage_bytes);
           // every operand tile is loaded ONCE per k-block; 3xTF32 reuses them for its 3 products.
           // K-major operand: one box (128 B of k x rows).  MN-major operand: one box per 128 B of rows
@@ -441,7 +450,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
           }
         }
         __syncwarp();
-        if (tr) p.trace[4 * (kb - kb_begin) + 2] = clock64();
+        B2_STAMP(lane == 0 && kb - kb_begin < 60, 4 * (kb - kb_begin) + 2);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -512,7 +521,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
         // between them, under the queued instructions of the first half.
 #define B2_ISSUE_HALF(K0)                                                                                      \
         if (elect_one()) {                                                                                     \
-          if (p.dbg & 4) {        /* probe: no tensor work, only the pipeline hand-offs */                      \
+          if (B2_DBG(4)) {        /* probe: no tensor work, only the pipeline hand-offs */                      \
           } else if (p.esz == 2) {                                                                             \
             _Pragma("unroll") for (int k = (K0); k < (K0) + 2; ++k)                                            \
               umma_bf16(d_main, B2_DESC(a_hi, al + k * ak), B2_DESC(b_hi, bl + k * bk), idesc, (k > 0) ? 1u : keep); \
@@ -533,19 +542,18 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
           }                                                                                                    \
         }                                                                                                      \
         __syncwarp();
-        const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && i < 60;
-        if (tr) p.trace[256 + 4 * i + 0] = clock64();
+        B2_STAMP(lane == 0 && i < 60, 256 + 4 * i + 0);
         B2_ISSUE_HALF(0)
-        if (tr) p.trace[256 + 4 * i + 1] = clock64();
+        B2_STAMP(lane == 0 && i < 60, 256 + 4 * i + 1);
         // non-blocking look at the next stage under the queued first half; block for it only after the
         // second half is queued too (a blocking wait here would hold back MMAs whose operands are present)
         const bool more = i + 1 < nkb;
         const bool next_ready = more && __all_sync(0xffffffffu, mbar_try_wait(ready0 + 8 * nstage, nphase));
         B2_ISSUE_HALF(2)
 #undef B2_ISSUE_HALF
-        if (tr) p.trace[256 + 4 * i + 2] = clock64();
+        B2_STAMP(lane == 0 && i < 60, 256 + 4 * i + 2);
         if (more && !next_ready) mbar_wait(ready0 + 8 * nstage, nphase, 1);
-        if (tr) p.trace[256 + 4 * i + 3] = clock64();
+        B2_STAMP(lane == 0 && i < 60, 256 + 4 * i + 3);
         so += stage_units;
         stage = nstage;
         phase = nphase;
@@ -576,7 +584,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       for (int i = 0; inl && i < nkb; ++i) {
         mbar_wait(full0 + 8 * stage, phase, 4);
         uint8_t* sb = smem + (size_t) stage * stage_bytes;
-        if (!(p.dbg & 1)) {
+        if (!B2_DBG(1)) {
           float4 v[A_BYTES / 16 / 128];
 #pragma unroll
           for (int u = 0; u < A_BYTES / 16 / 128; ++u) v[u] = *reinterpret_cast<const float4*>(sb + 16 * (cw + 128 * u));
@@ -587,7 +595,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
             *reinterpret_cast<float4*>(sb + off_as + 16 * (cw + 128 * u)) = w;
           }
         }
-        for (int c = cw; c < ((p.dbg & 1) ? 0 : b_chunks); c += 256) {
+        for (int c = cw; c < (B2_DBG(1) ? 0 : b_chunks); c += 256) {
           const float4 v0 = *reinterpret_cast<const float4*>(sb + off_b + 16 * c);
           const bool two = c + 128 < b_chunks;
           float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -985,8 +993,11 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   const int grid = (int) (total_tiles < B2_NUM_SMS ? total_tiles : B2_NUM_SMS);     // persistent: at most one CTA per SM
   // (one tile per CTA: the epilogue patches reuse the ring, see the kernel)
   const size_t fixed_bytes = (total_tiles <= grid ? 0 : tc::PATCH_BYTES) + 1024 + 192;
+  p.dbg = 0; p.trace = nullptr;
+#ifdef B2_GEMM_PROBE
   { const char* e = getenv("B2_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("B2_GEMM_TRACE"); p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+#endif
   p.stages = tc::MAX_STAGES;       // as deep as 227 KB allows (3xTF32 stages are twice the size)
   if (p.dbg & 8) p.stages = 2;
   while (p.stages > 2 && p.stages * stage_bytes + fixed_bytes > (size_t) 227 * 1024) --p.stages;

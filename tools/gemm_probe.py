@@ -5,9 +5,14 @@ import json
 import os
 import sys
 
+os.environ.setdefault("B2_BUILD_PROBE", "1")     # the probes exist only in a -DB2_GEMM_PROBE build
+
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fuxictr_b200 import build as _build  # noqa: E402
+
+_build.build()       # rebuilds in probe mode when the in-tree library is the product build (and vice versa later)
 import bench  # noqa: E402
 from fuxictr_b200 import functional as F2  # noqa: E402
 

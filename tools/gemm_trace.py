@@ -3,9 +3,14 @@ usage: python tools/gemm_trace.py [inline|aux] [M N K]"""
 import os
 import sys
 
+os.environ.setdefault("B2_BUILD_PROBE", "1")     # the probes exist only in a -DB2_GEMM_PROBE build
+
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fuxictr_b200 import build as _build  # noqa: E402
+
+_build.build()       # rebuilds in probe mode when the in-tree library is the product build (and vice versa later)
 from fuxictr_b200 import functional as F2  # noqa: E402
 
 inline = (sys.argv[1] if len(sys.argv) > 1 else "aux") == "inline"
@@ -45,8 +50,9 @@ for i in range(min(nkb, 60)):
     r = t[256 + 4 * i:256 + 4 * i + 4]
     if r[0]:
         print("   %2d %8d %8d %8d %8d" % (i, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0))
-print("epilogue warps: wait_start  tmem_full  done")
+print("epilogue warps: wait_start  tmem_full  done | first chunk: tmem_read  transposed+bias  stored")
 for w in range(2, 10):
     r = t[512 + 4 * w:512 + 4 * w + 3]
     if r[0]:
-        print("   w%d %8d %8d %8d" % (w, r[0] - t0, r[1] - t0, r[2] - t0))
+        e = t[700 + 8 * w:700 + 8 * w + 3]
+        print("   w%d %8d %8d %8d | %8d %8d %8d" % (w, r[0] - t0, r[1] - t0, r[2] - t0, e[0] - t0, e[1] - t0, e[2] - t0))
