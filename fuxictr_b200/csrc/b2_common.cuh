@@ -28,14 +28,14 @@ int b2_fail(int code, const char* fmt, ...);
 
 static inline int64_t b2_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// ---- programmatic dependent launch (opt-in: B2_PDL=1) --------------------------------------------
+// ---- programmatic dependent launch (on by default; B2_PDL=0 launches plainly) --------------------
 // The step is a chain of ~45 short kernels; with PDL a kernel's CTAs are scheduled while its predecessor
 // drains and sit at griddepcontrol.wait (which returns only when the predecessor has COMPLETED and its
 // writes are visible), so the launch latency — and, for the GEMM, the barrier/TMEM/tensormap prologue —
 // overlaps the predecessor's tail.  Captured into CUDA graphs as programmatic dependency edges.
 #include <stdlib.h>
 static inline bool b2_pdl_on() {
-  static const bool on = [] { const char* e = getenv("B2_PDL"); return e != nullptr && atoi(e) != 0; }();
+  static const bool on = [] { const char* e = getenv("B2_PDL"); return e == nullptr || atoi(e) != 0; }();
   return on;
 }
 #define B2_LAUNCH(kernel, grid, block, smem, st, ...)                                             \

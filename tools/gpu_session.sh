@@ -41,7 +41,7 @@ for st in $stages; do
       timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/${tag}_gputests.log 2>&1; tail -8 gpurun_out/${tag}_gputests.log ;;
     ab)
       # A/B of the launch options on the default step: inline 3xTF32 split on/off, PDL on/off
-      for v in "B2_X3_INLINE=0 B2_PDL=0" "B2_X3_INLINE=1 B2_PDL=0" "B2_X3_INLINE=1 B2_PDL=1" "B2_X3_INLINE=1 B2_X3_BN_MAX=96"; do
+      for v in "B2_X3_INLINE=0 B2_PDL=0" "B2_X3_INLINE=1 B2_PDL=0" "B2_X3_INLINE=0 B2_PDL=1" "B2_X3_INLINE=1 B2_PDL=1"; do
         n=$(echo $v | tr -d ' =_A-Z')
         env $v timeout 200 python bench.py --steps-only > gpurun_out/${tag}_ab_$n.json 2> gpurun_out/${tag}_ab_$n.err
         echo "$v: $(python -c "import json,sys; d=json.loads(open('gpurun_out/${tag}_ab_$n.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'])" 2>&1 | tail -1)"
@@ -74,8 +74,8 @@ print({k:(v['launches'], round(v['us'],1)) for k,v in d['step_profile']['calls']
         python bench.py --steps 1 --warmup 3 --graph 0 --steps-only --nbatches 4 > gpurun_out/${tag}_ncu_gemm.log 2>&1
       tail -3 gpurun_out/${tag}_ncu_gemm.log ;;
     sanitize)
-      timeout 1500 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -m gpu -x -p no:cacheprovider \
-        -k "gemm_tc_mn_major and (128-32-32 or 77-44-36 or 129-260) or fused_backward or mlp_chain and 40 or lazy_adam_optimizer or cin_fused" \
+      timeout 1500 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_sharded.py -q -m gpu -x -p no:cacheprovider \
+        -k "gemm_tc_mn_major and (128-32-32 or 76-44-36 or 132-260) or fused_backward or mlp_chain and 40 or virtual_ranks or shard_roundtrip or cin_fused or din_softmax or hot_row" \
         > gpurun_out/${tag}_memcheck.log 2>&1
       tail -8 gpurun_out/${tag}_memcheck.log ;;
   esac
