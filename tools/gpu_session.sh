@@ -78,6 +78,18 @@ print({k:(v['launches'], round(v['us'],1)) for k,v in d['step_profile']['calls']
         -k "gemm_tc_mn_major and (128-32-32 or 76-44-36 or 132-260) or fused_backward or mlp_chain and 40 or virtual_ranks or shard_roundtrip or cin_fused or din_softmax or hot_row" \
         > gpurun_out/${tag}_memcheck.log 2>&1
       tail -8 gpurun_out/${tag}_memcheck.log ;;
+    racecheck)
+      # shared-memory hazards: the GEMM's patches / converter tiles, the push kernel's block list, CIN / DIN tiles
+      timeout 1500 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_sharded.py -q -m gpu -x -p no:cacheprovider \
+        -k "gemm_tc_mn_major and (128-32-32 or 76-44-36) or mlp_chain and 40 or virtual_ranks and 2 or cin_fused or din_softmax or hot_row" \
+        > gpurun_out/${tag}_racecheck.log 2>&1
+      tail -8 gpurun_out/${tag}_racecheck.log ;;
+    c5prop)
+      timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k c5_full_shape -p no:cacheprovider > gpurun_out/${tag}_c5prop.log 2>&1; tail -5 gpurun_out/${tag}_c5prop.log ;;
+    ncu_cin)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:cin_ -s 18 -c 9 -o gpurun_out/${tag}_cin \
+        python bench.py --workload xdeepfm --steps 1 --warmup 3 --graph 0 --steps-only --nbatches 4 > gpurun_out/${tag}_ncu_cin.log 2>&1
+      tail -3 gpurun_out/${tag}_ncu_cin.log ;;
   esac
 done
 echo "[gpu_session $tag] done"
