@@ -53,6 +53,7 @@ constexpr int PATCH_BYTES = 8 * 32 * 33 * 4;   // epilogue transpose patches (on
 struct Params {
   CUtensorMap map_a[2];   // [0] the operand, [1] its 3xTF32 small part
   CUtensorMap map_b[2];
+  CUtensorMap map_c;      // C as a (N, M) tensor with 32 x 32 boxes: the epilogue's TMA store (tma_store != 0)
   float* c;
   float* c_small;         // optional: tf32_small(C) for the consumer's 3xTF32 operand
   float* c_pre;           // optional: acc + bias BEFORE mul/add/act (CrossNetV2 saves it for its backward)
@@ -72,6 +73,7 @@ struct Params {
   int stages;     // operand ring depth (<= MAX_STAGES), chosen by the host to fit 227 KB
   long long* trace;   // probe build only: CTA 0 writes clock64() stamps of its loops here (B2_GEMM_TRACE)
   int dbg;        // probe build only: B2_GEMM_DBG bits (timing experiments; results are wrong when set)
+  int tma_store;  // the epilogue hands finished 32 x 32 chunks to cp.async.bulk.tensor stores (plain C output only)
   int inline_split;  // 3xTF32 with the small parts computed in shared memory by warps 6..9 (no As/Bs in HBM)
   int tmem_cols;  // power of two >= (nmain + (nseg > 1)) * bn
 };
@@ -120,6 +122,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
 }
 // One elected lane of a fully converged warp (elect.sync): unlike `lane == 0`, the compiler knows the
 // enclosing control flow is warp-uniform, so descriptors / coordinates stay in uniform registers and
@@ -206,7 +213,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // One lane's share of the epilogue: column n of 32 consecutive rows (mrow0 ...), values in t[].
-__device__ __forceinline__ void epilogue_store(const Params& p, float (&t)[32], int mrow0, int n, bool split) {
+// `store_c` false: everything but the store of C itself (the caller hands the chunk to a TMA store).
+__device__ __forceinline__ void epilogue_store(const Params& p, float (&t)[32], int mrow0, int n, bool split, bool store_c) {
   float* cp = p.c + (int64_t) mrow0 * p.ldc + n;
   if (split) {
 #pragma unroll
@@ -258,9 +266,11 @@ __device__ __forceinline__ void epilogue_store(const Params& p, float (&t)[32], 
       for (int r = 0; r < 32; ++r)
         if (mrow0 + r < p.M) t[r] += cp[(int64_t) r * p.ldc];
     }
+    if (store_c) {
 #pragma unroll
-    for (int r = 0; r < 32; ++r)
-      if (mrow0 + r < p.M) cp[(int64_t) r * p.ldc] = t[r];   // 128 contiguous bytes per row
+      for (int r = 0; r < 32; ++r)
+        if (mrow0 + r < p.M) cp[(int64_t) r * p.ldc] = t[r];   // 128 contiguous bytes per row
+    }
     if (p.c_small != nullptr && p.esz == 4) {   // the consumer's 3xTF32 small part, produced where C is produced
       float* sp = p.c_small + (int64_t) mrow0 * p.ld_aux + n;
 #pragma unroll
@@ -331,6 +341,7 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_a[s])) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_b[s])) : "memory");
     }
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.map_c)) : "memory");
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
@@ -409,8 +420,27 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 #pragma unroll
       for (int r = 0; r < 32; ++r) tt[r] = patch[r * 33 + lane] + bv;  // 32 independent LDS in flight
       const int mrow0 = m0 + q * 32;
-      if (n_ok && !B2_DBG(2)) epilogue_store(p, tt, mrow0, n, split);
+      if (!p.tma_store) {
+        if (n_ok && !B2_DBG(2)) epilogue_store(p, tt, mrow0, n, split, true);
+      } else {
+        // TMA store: the finished chunk goes back into the warp's patch as a dense 32 x 32 box (row = output
+        // row, 128 B per row) and ONE bulk tensor store writes it; rows >= M and columns >= N are clipped by
+        // the tensor map, so nothing here is predicated on the tile edges.
+        if (n_ok) epilogue_store(p, tt, mrow0, n, split, false);
+        __syncwarp();                  // every lane has read its column out of the 33-pitch patch
+#pragma unroll
+        for (int r = 0; r < 32; ++r) patch[r * 32 + lane] = tt[r];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && !B2_DBG(2)) {
+          tma_store_2d(&p.map_c, smem_u32(patch), n0 + c0, mrow0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the patch is rewritten by the next chunk
+        }
+        __syncwarp();
+      }
     }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     B2_STAMP(lane == 0, 512 + 4 * warp + 2);
   };
 
@@ -940,6 +970,22 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     if (rc != B2_OK) return rc;
     rc = encode_operand(&p.map_b[s], bs[s], N, K, ldb, d->b_mn_major, best_bn, esz);
     if (rc != B2_OK) return rc;
+  }
+  // TMA-store epilogue for a plain C output (no split-K reduction, no accumulate, no second output):
+  // C is described as an (N, M) fp32 tensor with pitch ldc and written in 32 x 32 boxes
+  p.tma_store = 0;
+  if (best_split == 1 && !d->beta_accumulate && d->c_small == nullptr && d->c_pre == nullptr && tma_ok(c, ldc)) {
+    b2_encode_tiled_fn enc = b2_get_encode();
+    cuuint64_t dims[2] = {(cuuint64_t) N, (cuuint64_t) M}, strides[1] = {(cuuint64_t) ldc * 4};
+    cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    if (enc != nullptr &&
+        enc(&p.map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      p.tma_store = 1;
+  }
+  {
+    static const bool off = [] { const char* e = getenv("B2_GEMM_TMA_STORE"); return e != nullptr && atoi(e) == 0; }();
+    if (off) p.tma_store = 0;
   }
   p.c = c; p.c_small = reinterpret_cast<float*>(d->c_small); p.c_pre = d->c_pre; p.ldc = ldc; p.ld_aux = ld_aux;
   p.bias = d->bias; p.mul = d->mul; p.add = d->add;

@@ -1017,6 +1017,7 @@ def test_c5_full_shape_lookup_properties():
     if free < 60e9:
         pytest.skip("needs ~40 GB of free HBM")
     from fuxictr_b200 import layers
+    from fuxictr_b200.schema import FeatureMap
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import bench
