@@ -1003,9 +1003,17 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   if (nseg == 1) {
     p.nmain = 1;
   } else {
-    p.nmain = 512 / best_bn - 1;                       // all of TMEM: nmain main chains + 1 correction
+    // Accumulation chains of the main product: the truncating accumulator loses accuracy with the LENGTH of
+    // a chain, and 64 k-blocks (2,048 products) per chain is what the 2e-6-vs-fp64 bar was established with
+    // (K = 8,192 in 4 chains).  So short contractions get ONE chain: the epilogue then sums 2 TMEM ranges
+    // per chunk instead of 5, and TMEM has room for a second accumulator stage.
+    static const int chain_kb = [] { const char* e = getenv("B2_X3_CHAIN_KB"); return e ? atoi(e) : 64; }();
+    const int fit = 512 / best_bn - 1;                 // all of TMEM: nmain main chains + 1 correction
+    p.nmain = chain_kb > 0 ? (int) b2_ceil_div(p.kb_per_split, chain_kb) : fit;
+    if (p.nmain > fit) p.nmain = fit;
     if (p.nmain > 4) p.nmain = 4;
     if (p.nmain > p.kb_per_split) p.nmain = p.kb_per_split;
+    if (p.nmain < 1) p.nmain = 1;
   }
   // Two accumulator stages (the epilogue of tile j under the main loop of tile j+1) when a CTA has
   // several tiles and both stages fit the 512 TMEM columns; 3xTF32 gives up chains for it only down to 2
@@ -1015,7 +1023,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     int nm = p.nmain;
     const int corr = nseg > 1 ? 1 : 0;
     while (nm > 1 && 2 * (nm + corr) * best_bn > 512) --nm;
-    const int floor_nm = (nseg > 1) ? (p.kb_per_split < 2 ? p.kb_per_split : 2) : 1;
+    const int floor_nm = (nseg > 1) ? (p.nmain < 2 ? p.nmain : 2) : 1;
     if (2 * (nm + corr) * best_bn <= 512 && nm >= floor_nm) { p.nmain = nm; p.nacc = 2; }
   }
   {

@@ -41,7 +41,7 @@ for st in $stages; do
       timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/${tag}_gputests.log 2>&1; tail -8 gpurun_out/${tag}_gputests.log ;;
     ab)
       # A/B of the launch options on the default step: TMA-store epilogue on/off, inline 3xTF32 split on/off
-      for v in "B2_GEMM_TMA_STORE=0" "B2_GEMM_TMA_STORE=1" "B2_GEMM_TMA_STORE=0 B2_X3_INLINE=0" "B2_GEMM_TMA_STORE=1 B2_X3_INLINE=0"; do
+      for v in "B2_X3_CHAIN_KB=0" "B2_X3_CHAIN_KB=64" "B2_X3_CHAIN_KB=16" "B2_X3_CHAIN_KB=64 B2_X3_BN_MAX=256"; do
         n=$(echo $v | tr -d ' =_A-Z')
         env $v timeout 200 python bench.py --steps-only > gpurun_out/${tag}_ab_$n.json 2> gpurun_out/${tag}_ab_$n.err
         echo "$v: $(python -c "import json,sys; d=json.loads(open('gpurun_out/${tag}_ab_$n.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'])" 2>&1 | tail -1)"
