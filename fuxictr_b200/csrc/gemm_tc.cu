@@ -1004,10 +1004,11 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     p.nmain = 1;
   } else {
     // Accumulation chains of the main product: the truncating accumulator loses accuracy with the LENGTH of
-    // a chain.  16 k-blocks (512 products) per chain keeps every tested shape under the 2e-6-vs-fp64 bar
-    // (64 per chain measured 2.1-2.8e-6 at K = 8,192 and broke the 1e-5 MLP-chain parity); short contractions
-    // therefore get one or two chains, and the epilogue sums 2-3 TMEM ranges per chunk instead of 5.
-    static const int chain_kb = [] { const char* e = getenv("B2_X3_CHAIN_KB"); return e ? atoi(e) : 16; }();
+    // a chain, so the K range is cut into as many chains as TMEM holds (<= 4).  Fewer, longer chains were
+    // measured (B2_X3_CHAIN_KB = k-blocks per chain): 0.003 ms faster per step, but 64 per chain gives
+    // 2.1-2.8e-6 vs fp64 at K = 8,192 and even 16 per chain breaks the 1e-5 MLP-chain parity at 500-wide
+    // layers — the default (0) keeps every chain TMEM has room for.
+    static const int chain_kb = [] { const char* e = getenv("B2_X3_CHAIN_KB"); return e ? atoi(e) : 0; }();
     const int fit = 512 / best_bn - 1;                 // all of TMEM: nmain main chains + 1 correction
     p.nmain = chain_kb > 0 ? (int) b2_ceil_div(p.kb_per_split, chain_kb) : fit;
     if (p.nmain > fit) p.nmain = fit;
