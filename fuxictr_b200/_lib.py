@@ -66,6 +66,13 @@ class b2_gemm_desc(ctypes.Structure):
         ("flags", c_int64),
     ]
 
+class b2_gemm_plan(ctypes.Structure):
+    """struct b2_gemm_plan of include/fuxictr_b200.h."""
+    _fields_ = [(k, c_int32) for k in ("bn", "splits", "stages", "nacc", "nmain", "tmem_cols", "grid", "threads",
+                                       "tiles_m", "tiles_n", "tma_store", "passes", "kb_per_split", "pad_")] + \
+               [("smem_bytes", c_int64)]
+
+
 # name -> (restype, argtypes); every symbol the header declares must appear here
 # (tests/test_abi.py cross-checks this table against the header text).
 SIGNATURES = {
@@ -127,6 +134,7 @@ SIGNATURES = {
     "b2_gemm_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                            c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_gemm_tc_ex": (c_int, [c_void_p, c_void_p]),
+    "b2_gemm_tc_plan": (c_int, [c_void_p, c_void_p]),
     "b2_to_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "b2_split_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "b2_transpose_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -903,7 +903,9 @@ extern "C" B2_API int b2_gemm_tc_supported(const float* a, int64_t lda, const fl
           N < (1ll << 31) && K < (1ll << 31)) ? 1 : 0;
 }
 
-extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
+// plan != NULL: fill in the launch plan (tile shape, ring depth, TMEM, shared memory) and return without
+// touching the device — pure host arithmetic, so the CPU test-suite can sweep it (tests/test_abi.py).
+static int gemm_tc_impl(const b2_gemm_desc* d, void* stream, b2_gemm_plan* plan) {
   B2_REQUIRE(d != nullptr, "NULL descriptor");
   const void* a = d->a; const void* b = d->b; float* c = d->c;
   const int64_t M = d->M, N = d->N, K = d->K, lda = d->lda, ldb = d->ldb, ldc = d->ldc;
@@ -965,7 +967,7 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   const int nseg = three_pass ? 3 : 1;
   const void* as[2] = {a, d->a_small};
   const void* bs[2] = {b, d->b_small};
-  for (int s = 0; s < (d->a_small != nullptr ? 2 : 1); ++s) {
+  for (int s = 0; plan == nullptr && s < (d->a_small != nullptr ? 2 : 1); ++s) {
     int rc = encode_operand(&p.map_a[s], as[s], M, K, lda, d->a_mn_major, tc::BM, esz);
     if (rc != B2_OK) return rc;
     rc = encode_operand(&p.map_b[s], bs[s], N, K, ldb, d->b_mn_major, best_bn, esz);
@@ -975,9 +977,10 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   // C is described as an (N, M) fp32 tensor with pitch ldc and written in 32 x 32 boxes
   p.tma_store = 0;
   if (best_split == 1 && !d->beta_accumulate && d->c_small == nullptr && d->c_pre == nullptr && tma_ok(c, ldc)) {
-    b2_encode_tiled_fn enc = b2_get_encode();
+    b2_encode_tiled_fn enc = plan != nullptr ? nullptr : b2_get_encode();
     cuuint64_t dims[2] = {(cuuint64_t) N, (cuuint64_t) M}, strides[1] = {(cuuint64_t) ldc * 4};
     cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    if (plan != nullptr) p.tma_store = 1;
     if (enc != nullptr &&
         enc(&p.map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
@@ -1034,11 +1037,11 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
     p.tmem_cols = cols;
   }
   p.tiles_m = (int) tiles_m; p.tiles_n = (int) tiles_n; p.splits = splits;
-  if (splits > 1 && !p.beta && !(d->flags & B2_GEMM_C_IS_ZERO)) {
+  if (plan == nullptr && splits > 1 && !p.beta && !(d->flags & B2_GEMM_C_IS_ZERO)) {
     cudaError_t e = cudaMemset2DAsync(c, (size_t) ldc * 4, 0, (size_t) N * 4, (size_t) M, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
-  if (d->colsum != nullptr && !(d->flags & B2_GEMM_COLSUM_IS_ZERO)) {
+  if (plan == nullptr && d->colsum != nullptr && !(d->flags & B2_GEMM_COLSUM_IS_ZERO)) {
     cudaError_t e = cudaMemsetAsync(d->colsum, 0, sizeof(float) * (size_t) N, st);
     if (e != cudaSuccess) return b2_fail(B2_E_CUDA, "b2_gemm_tc: memset: %s", cudaGetErrorString(e));
   }
@@ -1059,6 +1062,13 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   B2_REQUIRE(p.stages * stage_bytes + fixed_bytes <= (size_t) 227 * 1024, "tile does not fit shared memory");
   B2_REQUIRE(p.stages * stage_bytes >= (size_t) tc::PATCH_BYTES, "ring smaller than the epilogue patches");
   const size_t smem = p.stages * stage_bytes + fixed_bytes;
+  if (plan != nullptr) {
+    plan->bn = p.bn; plan->splits = p.splits; plan->stages = p.stages; plan->nacc = p.nacc; plan->nmain = p.nmain;
+    plan->tmem_cols = p.tmem_cols; plan->grid = grid; plan->threads = tc::NTHREADS; plan->tiles_m = p.tiles_m;
+    plan->tiles_n = p.tiles_n; plan->tma_store = p.tma_store; plan->passes = nseg; plan->kb_per_split = p.kb_per_split;
+    plan->smem_bytes = (int64_t) smem;
+    return B2_OK;
+  }
   // opt-in to > 48 KB of dynamic shared memory: an idempotent per-process property of the kernel
   // (C++11 guarantees the initialiser runs once, thread-safely)
   static const cudaError_t attr_rc = cudaFuncSetAttribute(
@@ -1067,6 +1077,13 @@ extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) {
   B2_LAUNCH(tc::gemm_tf32_kernel, grid, tc::NTHREADS, smem, st, p);
   B2_CUDA_LAUNCH_CHECK("b2_gemm_tc");
   return B2_OK;
+}
+
+extern "C" B2_API int b2_gemm_tc_ex(const b2_gemm_desc* d, void* stream) { return gemm_tc_impl(d, stream, nullptr); }
+
+extern "C" B2_API int b2_gemm_tc_plan(const b2_gemm_desc* d, b2_gemm_plan* plan) {
+  B2_REQUIRE(plan != nullptr, "NULL plan");
+  return gemm_tc_impl(d, nullptr, plan);
 }
 
 // fp32 (rows, cols; ld_in) -> bf16 (rows, cols; ld_out), round-to-nearest-even: the bf16-mode operand of a

@@ -435,6 +435,14 @@ typedef struct b2_gemm_desc {
 #define B2_GEMM_COLSUM_IS_ZERO 2
 #define B2_GEMM_X3_INLINE 4      /* 3xTF32 from the fp32 operands alone: the small parts are made in shared memory */
 B2_API int b2_gemm_tc_ex(const b2_gemm_desc* desc, void* stream);
+/* The launch plan b2_gemm_tc_ex would use for `desc` (pure host arithmetic: no device call, no stream): lets a
+   host-only test check that every plan fits the SM (<= 227 KB of shared memory, <= 512 TMEM columns). */
+typedef struct b2_gemm_plan {
+  int32_t bn, splits, stages, nacc, nmain, tmem_cols, grid, threads, tiles_m, tiles_n, tma_store, passes, kb_per_split;
+  int32_t pad_;
+  int64_t smem_bytes;
+} b2_gemm_plan;
+B2_API int b2_gemm_tc_plan(const b2_gemm_desc* desc, b2_gemm_plan* plan);
 B2_API int b2_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                       void* stream);
 /* small[i] = x[i] - (x[i] with the 13 low mantissa bits cleared). */
