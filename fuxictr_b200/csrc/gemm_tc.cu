@@ -15,15 +15,23 @@
 //   precision 1 ("tf32"):   one pass, ~1e-3 relative — at least the bf16 the config names.
 //   precision 3 ("tf32x3"): error-compensated 3xTF32: with x = big(x) + small(x),
 //        A.B ~= A_big.B_big + A_big.B_small + A_small.B_big
-//     where big() is the hardware truncation itself and small = x - big(x) is produced by
-//     b2_split_tf32 — fp32-class accuracy (the 1e-5 parity bar) on tensor cores.
+//     where big() is the hardware truncation itself and small = rna_tf32(x - big(x)) — fp32-class accuracy
+//     (the 1e-5 parity bar) on tensor cores.  The small tiles are made in shared memory by the helper
+//     warps (B2_GEMM_X3_INLINE: the GEMM then reads only the fp32 operands) or loaded from HBM (a_small /
+//     b_small of the descriptor, produced by b2_split_tf32 or a previous epilogue).
+//   bf16 operands (elem_dtype B2_BF16): kind::f16, 64-element k-blocks, fp32 accumulation.
 //
 // Structure (persistent: at most one CTA per SM, striding over the 128 x BN output tiles x K splits):
-//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles into a 3/4-stage ring
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles into a 2-4-stage mbarrier ring
 //   warp 1      TMEM allocator + tcgen05.mma issuer (one elect.sync lane), tcgen05.commit -> mbarriers
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> fused epilogue -> global
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> smem transpose -> fused epilogue ->
+//               TMA tensor store of the finished 32 x 32 chunk (register stores for split-K / accumulate / c_pre)
+//   warps 6-9   helpers: (inline 3xTF32) A -> As, B -> Bs in shared memory, then every second epilogue chunk
 //   TMEM holds 1 or 2 accumulator stages (full/empty mbarriers), so a CTA with several tiles never
-//   drains its pipelines between them.
+//   drains its pipelines between them; in one-tile CTAs the epilogue's patches reuse the dead ring.
+//   Kernels of a step are chained with programmatic dependent launch (prologue under the predecessor's tail).
+// Where the time goes (probe build): SS-mode operand fetch from shared memory and the
+// short MMA issue queue bound the main loop; the output burst bounds the epilogue.
 // Every mbarrier wait is bounded: a pipeline bug traps with a message instead of hanging the GPU.
 #include "b2_common.cuh"
 #include <string.h>
