@@ -365,7 +365,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRICS[args.workload], "value": r["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": r["steps"], "warmup": warm, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak" if args.workload == "deepfm" else "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
             "cpu_baseline": cpu_baseline_entry(r, args, "(this run)"),
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -826,9 +826,11 @@ def run_b200_arm(args):
             "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core GEMMs, fp32 everything else)",
                       "tf32": "tf32 GEMMs, f32 elsewhere",
                       "bf16": "bf16 GEMM operands (fp32 accumulation in TMEM), f32 tables / optimizer"}[args.precision],
-            "data": "synthetic", "config": dict(workload_config(args, world), matmul=args.precision,
-                                             adam=("dense semantics, lazy row-wise evaluation" if args.lazy_adam and world == 1
-                                                   else "dense pass over the arena")),
+            # `config` names the WORKLOAD only (both arms print the same dict); how this arm computes it:
+            "data": "synthetic", "config": workload_config(args, world),
+            "matmul": args.precision,
+            "optimizer_pass": ("dense semantics, lazy row-wise evaluation" if args.lazy_adam and world == 1
+                               else "dense pass over the arena"),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": pipe.h2d_bytes_per_step * world, "d2h_bytes_per_step": pipe.d2h_bytes_per_step * world,
