@@ -22,7 +22,7 @@ def recorder(monkeypatch):
             info = dict(M=d.M, N=d.N, K=d.K, a_mn=d.a_mn_major, b_mn=d.b_mn_major, inline=bool(d.flags & _lib.B2_GEMM_X3_INLINE),
                         aux=bool(d.a_small) and bool(d.b_small), bf16=d.elem_dtype == _lib.B2_BF16, act=d.act,
                         ybwd=bool(d.ybwd), act_bwd=d.act_bwd, colsum=bool(d.colsum), bias=bool(d.bias),
-                        c_small=bool(d.c_small))
+                        c_small=bool(d.c_small), mul=bool(d.mul), add=bool(d.add), c_pre=bool(d.c_pre))
         calls.append((name, info))
         return 0
 
@@ -99,3 +99,23 @@ def test_single_pass_modes(recorder, mode):
     assert all(not d["aux"] for d in g)               # bf16 copies ARE the operands; 1xTF32 has none
     names = [n for n, _ in recorder]
     assert ("b2_to_bf16" in names) == (mode == "bf16") and "b2_split_tf32" not in names
+
+
+def test_crossnet_v2_layer_is_one_gemm_forward_and_three_launches_backward(recorder):
+    """x_next = x_i + x_0 * (x_i W^T + b) (cross_net.py:126-129): the cross itself is the GEMM's epilogue
+    (mul = x_0, add = x_i, lin kept for the backward); backward = one g*x_0 pass + dgrad (+g in its epilogue) + wgrad."""
+    F2.set_matmul_precision("tf32x3")
+    torch.manual_seed(1)
+    d = 624
+    x0 = torch.randn(512, d, requires_grad=True)
+    xi = torch.randn(512, d, requires_grad=True)
+    w = torch.nn.Parameter(torch.randn(d, d) * 0.02)
+    b = torch.nn.Parameter(torch.zeros(d))
+    out = F2.cross_v2_layer(x0, xi, w, b)
+    out.backward(torch.randn_like(out))
+    names = [n for n, _ in recorder]
+    assert names == ["b2_gemm_tc_ex", "b2_prep_operand", "b2_gemm_tc_ex", "b2_gemm_tc_ex"]
+    fwd, dgrad, wgrad = [i for _, i in recorder if i is not None]
+    assert fwd["mul"] and fwd["add"] and fwd["c_pre"] and fwd["bias"] and fwd["inline"] and not fwd["b_mn"]
+    assert (dgrad["M"], dgrad["N"], dgrad["K"], dgrad["b_mn"], dgrad["add"]) == (512, d, d, 1, True)
+    assert (wgrad["M"], wgrad["N"], wgrad["K"], wgrad["a_mn"], wgrad["b_mn"]) == (d, d, 512, 1, 1)
